@@ -1,0 +1,289 @@
+"""ctypes binding of the C ABI in include/ekfvio_c.h (libekfvio_b200.so).
+
+This is plumbing for tests and bench.py: torch only provides device memory and streams; every
+computation happens in the hand-written CUDA behind the ABI.  There is no fallback — if the
+shared library is missing, importing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libekfvio_b200.so")
+
+
+class EkfvioError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C ekf_vio_b200/csrc).  There is no CPU fallback."
+        )
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+c_void_p, c_int, c_double = C.c_void_p, C.c_int, C.c_double
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("default_point_depth", C.c_double),
+        ("default_point_depth_variance", C.c_double),
+        ("default_point_homogenous_variance", C.c_double),
+        ("flags", C.c_uint32),
+    ]
+
+
+class KltParams(C.Structure):
+    _fields_ = [
+        ("window_size", C.c_int),
+        ("max_pyramid_level", C.c_int),
+        ("max_iterations", C.c_int),
+        ("epsilon", C.c_double),
+        ("min_eigen", C.c_double),
+        ("kill_pad", C.c_int),
+        ("use_initial_flow", C.c_int),
+    ]
+
+
+class BatchView(C.Structure):
+    _fields_ = [
+        ("d_mu", c_void_p), ("d_feat", c_void_p), ("d_P", c_void_p), ("d_nfeat", c_void_p), ("d_status", c_void_p),
+        ("ldP", C.c_int), ("num_filters", C.c_int), ("max_features", C.c_int),
+    ]
+
+
+FLAG_FORCE_GENERAL_PATH = 0x1
+FLAG_FRESH_DQ_CACHE = 0x2
+
+# name -> (restype, argtypes); every symbol include/ekfvio_c.h declares
+SIGNATURES = {
+    "ekfvio_last_error": (C.c_char_p, []),
+    "ekfvio_default_params": (None, [C.POINTER(Params)]),
+    "ekfvio_batch_create": (c_int, [C.POINTER(c_void_p), c_int, c_int, c_int, C.POINTER(Params)]),
+    "ekfvio_batch_destroy": (c_int, [c_void_p]),
+    "ekfvio_batch_num_filters": (c_int, [c_void_p]),
+    "ekfvio_batch_max_features": (c_int, [c_void_p]),
+    "ekfvio_batch_reset": (c_int, [c_void_p, c_void_p]),
+    "ekfvio_batch_add_features": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "ekfvio_batch_process": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "ekfvio_batch_process_dt": (c_int, [c_void_p, c_double, c_void_p]),
+    "ekfvio_batch_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ekfvio_batch_linearize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ekfvio_batch_check_sigma": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ekfvio_batch_get_state": (c_int, [c_void_p] + [c_void_p] * 8),
+    "ekfvio_batch_set_state": (c_int, [c_void_p] + [c_void_p] * 7),
+    "ekfvio_batch_add_features_h": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "ekfvio_batch_update_h": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ekfvio_batch_read_mu_h": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ekfvio_batch_get_view": (c_int, [c_void_p, C.POINTER(BatchView)]),
+    "ekfvio_batch_launch_count": (C.c_longlong, [c_void_p]),
+    "ekfvio_batch_accumulate_errors": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ekfvio_klt_default_params": (None, [C.POINTER(KltParams)]),
+    "ekfvio_klt_create": (c_int, [C.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, C.POINTER(KltParams)]),
+    "ekfvio_klt_destroy": (c_int, [c_void_p]),
+    "ekfvio_klt_num_levels": (c_int, [c_void_p]),
+    "ekfvio_klt_build_pyramid": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "ekfvio_klt_track": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "ekfvio_klt_postprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ekfvio_klt_track_pair_h": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ekfvio_klt_read_level": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, C.POINTER(c_int), C.POINTER(c_int)]),
+    "ekfvio_klt_launch_count": (C.c_longlong, [c_void_p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here = header and library disagree
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise EkfvioError(lib.ekfvio_last_error().decode())
+
+
+def _ptr(x):
+    """Device or host pointer of a torch tensor / numpy array / None."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data
+    assert x.is_contiguous()
+    return x.data_ptr()
+
+
+def _stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def default_params(flags: int = 0) -> Params:
+    p = Params()
+    lib.ekfvio_default_params(C.byref(p))
+    p.flags = flags
+    return p
+
+
+class EkfBatch:
+    """F independent TightlyCoupledEKF filters on one GPU (reference: TightlyCoupledEKF.h:25-70)."""
+
+    def __init__(self, num_filters: int, max_features: int, device: int = 0, params: Params | None = None):
+        self._h = c_void_p()
+        self.F, self.nmax = num_filters, max_features
+        self.Nmax = 22 + 3 * max_features
+        self.device = device
+        p = params if params is not None else default_params()
+        _check(lib.ekfvio_batch_create(C.byref(self._h), device, num_filters, max_features, C.byref(p)))
+
+    def close(self):
+        if self._h:
+            lib.ekfvio_batch_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- device-pointer entry points (torch cuda tensors) --
+    def reset(self):
+        _check(lib.ekfvio_batch_reset(self._h, _stream()))
+
+    def add_features(self, k, uv):
+        """k: int32 [F] cuda, uv: float64 [F, kmax, 2] cuda."""
+        _check(lib.ekfvio_batch_add_features(self._h, _ptr(k), _ptr(uv), int(uv.shape[1]), _stream()))
+
+    def process(self, dt):
+        if isinstance(dt, (float, int)):
+            _check(lib.ekfvio_batch_process_dt(self._h, float(dt), _stream()))
+        else:
+            _check(lib.ekfvio_batch_process(self._h, _ptr(dt), _stream()))
+
+    def update(self, z, R, passed):
+        """z [F,nmax,2] f64, R [F,nmax,4] f64, passed [F,nmax] u8 — cuda tensors."""
+        _check(lib.ekfvio_batch_update(self._h, _ptr(z), _ptr(R), _ptr(passed), _stream()))
+
+    def linearize(self, dt, F_out):
+        _check(lib.ekfvio_batch_linearize(self._h, _ptr(dt), _ptr(F_out), _stream()))
+
+    def check_sigma(self, neg, asym):
+        _check(lib.ekfvio_batch_check_sigma(self._h, _ptr(neg), _ptr(asym), _stream()))
+
+    def accumulate_errors(self, truth_mu, acc):
+        _check(lib.ekfvio_batch_accumulate_errors(self._h, _ptr(truth_mu), _ptr(acc), _stream()))
+
+    # -- host-buffer entry points (numpy) --
+    def add_features_h(self, k: np.ndarray, uv: np.ndarray):
+        k = np.ascontiguousarray(k, np.int32)
+        uv = np.ascontiguousarray(uv, np.float64)
+        _check(lib.ekfvio_batch_add_features_h(self._h, _ptr(k), _ptr(uv), int(uv.shape[1]), _stream()))
+
+    def update_h(self, z: np.ndarray, R: np.ndarray, passed: np.ndarray):
+        _check(lib.ekfvio_batch_update_h(self._h, _ptr(z), _ptr(R), _ptr(passed), _stream()))
+
+    def read_mu_h(self, mu: np.ndarray, feat: np.ndarray | None = None):
+        _check(lib.ekfvio_batch_read_mu_h(self._h, _ptr(mu), _ptr(feat), _stream()))
+
+    def get_state(self, want_P: bool = True) -> dict:
+        F, nm, Nm = self.F, max(self.nmax, 1), self.Nmax
+        out = {
+            "mu": np.zeros((F, 22)), "feat": np.zeros((F, nm, 3)), "P": np.zeros((F, Nm, Nm)) if want_P else None,
+            "nfeat": np.zeros(F, np.int32), "cache": np.zeros((F, 7)), "flags": np.zeros((F, nm), np.uint8),
+            "klt_last": np.zeros((F, nm, 2)), "status": np.zeros(F, np.int32),
+        }
+        _check(lib.ekfvio_batch_get_state(self._h, _ptr(out["mu"]), _ptr(out["feat"]), _ptr(out["P"]), _ptr(out["nfeat"]),
+                                          _ptr(out["cache"]), _ptr(out["flags"]), _ptr(out["klt_last"]), _ptr(out["status"])))
+        return out
+
+    def set_state(self, mu=None, feat=None, P=None, nfeat=None, cache=None, flags=None, klt_last=None):
+        def c(a, dt):
+            return None if a is None else np.ascontiguousarray(a, dt)
+        mu, feat, P, cache, klt_last = (c(a, np.float64) for a in (mu, feat, P, cache, klt_last))
+        nfeat, flags = c(nfeat, np.int32), c(flags, np.uint8)
+        _check(lib.ekfvio_batch_set_state(self._h, _ptr(mu), _ptr(feat), _ptr(P), _ptr(nfeat), _ptr(cache), _ptr(flags), _ptr(klt_last)))
+
+    def view(self) -> BatchView:
+        v = BatchView()
+        _check(lib.ekfvio_batch_get_view(self._h, C.byref(v)))
+        return v
+
+    @property
+    def launches(self) -> int:
+        return int(lib.ekfvio_batch_launch_count(self._h))
+
+
+def default_klt_params() -> KltParams:
+    p = KltParams()
+    lib.ekfvio_klt_default_params(C.byref(p))
+    return p
+
+
+class KltTracker:
+    """Batched pyramidal LK tracker (reference: KLTTracker.h:85-98 -> cv::calcOpticalFlowPyrLK)."""
+
+    def __init__(self, width: int, height: int, max_batch: int, max_points: int, num_slots: int = 2, device: int = 0,
+                 params: KltParams | None = None):
+        self._h = c_void_p()
+        self.width, self.height, self.max_batch, self.max_points = width, height, max_batch, max_points
+        p = params if params is not None else default_klt_params()
+        self.params = p
+        _check(lib.ekfvio_klt_create(C.byref(self._h), device, width, height, max_batch, max_points, num_slots, C.byref(p)))
+
+    def close(self):
+        if self._h:
+            lib.ekfvio_klt_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def num_levels(self) -> int:
+        return int(lib.ekfvio_klt_num_levels(self._h))
+
+    def build_pyramid(self, slot: int, imgs, with_derivs: bool):
+        """imgs: uint8 cuda tensor [batch, H, pitch]."""
+        _check(lib.ekfvio_klt_build_pyramid(self._h, slot, _ptr(imgs), int(imgs.shape[2]), int(imgs.shape[0]), int(with_derivs), _stream()))
+
+    def track(self, prev_slot, next_slot, prev_pts, next_pts, status, err, npts):
+        _check(lib.ekfvio_klt_track(self._h, prev_slot, next_slot, _ptr(prev_pts), _ptr(next_pts), _ptr(status), _ptr(err), _ptr(npts),
+                                    int(prev_pts.shape[0]), _stream()))
+
+    def postprocess(self, next_pts, status, npts, K9, measured, cov, passed):
+        _check(lib.ekfvio_klt_postprocess(self._h, _ptr(next_pts), _ptr(status), _ptr(npts), _ptr(K9), int(next_pts.shape[0]),
+                                          _ptr(measured), _ptr(cov), _ptr(passed), _stream()))
+
+    def track_pair_h(self, prev: np.ndarray, nxt: np.ndarray, prev_pts: np.ndarray, next_pts: np.ndarray, npts: np.ndarray):
+        """Host images [batch,H,W] u8; prev_pts/next_pts [batch,max_points,2] f32 (next_pts in/out). Returns status, err."""
+        batch = prev.shape[0]
+        status = np.zeros((batch, self.max_points), np.uint8)
+        err = np.zeros((batch, self.max_points), np.float32)
+        npts = np.ascontiguousarray(npts, np.int32)
+        _check(lib.ekfvio_klt_track_pair_h(self._h, _ptr(prev), _ptr(nxt), int(prev.shape[2]), batch, _ptr(prev_pts), _ptr(next_pts),
+                                           _ptr(status), _ptr(err), _ptr(npts), _stream()))
+        return status, err
+
+    def read_level(self, slot: int, img: int, level: int, want_deriv: bool):
+        w, h = c_int(), c_int()
+        _check(lib.ekfvio_klt_read_level(self._h, slot, img, level, None, None, C.byref(w), C.byref(h)))
+        out = np.zeros((h.value, w.value), np.uint8)
+        der = np.zeros((h.value, w.value, 2), np.int16) if want_deriv else None
+        _check(lib.ekfvio_klt_read_level(self._h, slot, img, level, _ptr(out), _ptr(der), C.byref(w), C.byref(h)))
+        return out, der
+
+    @property
+    def launches(self) -> int:
+        return int(lib.ekfvio_klt_launch_count(self._h))

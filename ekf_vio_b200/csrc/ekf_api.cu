@@ -1,0 +1,276 @@
+// C-ABI layer for the batched EKF (include/ekfvio_c.h).  Owns device memory, picks the kernel
+// path, counts launches.  No CPU fallback: every entry point fails if CUDA does.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "ekf_common.cuh"
+#include "ekf_kernels.h"
+
+using namespace ekfvio;
+
+namespace ekfvio {
+thread_local std::string g_last_error;
+int fail(const char* what, cudaError_t e) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return 1;
+}
+int fail_msg(const std::string& msg) { g_last_error = msg; return 1; }
+}  // namespace ekfvio
+
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return ekfvio::fail(#x, e_); } while (0)
+
+static EkfPtrs ptrs(const ekfvio_batch* b) {
+    EkfPtrs p;
+    p.mu = b->d_mu; p.feat = b->d_feat; p.nfeat = b->d_nfeat; p.cache = b->d_cache; p.dflags = b->d_flags;
+    p.klt_last = b->d_klt_last; p.status = b->d_status; p.idx = b->d_idx; p.y = b->d_y; p.m = b->d_m; p.K = b->d_K; p.W = b->d_W;
+    p.F = b->F; p.nmax = b->nmax; p.Nmax = b->Nmax; p.ldP = b->ldP; p.ldK = b->ldK; p.mmax = b->mmax;
+    p.flags = b->prm.flags;
+    p.depth = b->prm.default_point_depth; p.depth_var = b->prm.default_point_depth_variance;
+    p.uv_var = b->prm.default_point_homogenous_variance;
+    p.gain_smem_doubles = gain_general_smem_doubles(b->mmax);
+    return p;
+}
+
+extern "C" {
+
+const char* ekfvio_last_error(void) { return ekfvio::g_last_error.c_str(); }
+
+void ekfvio_default_params(ekfvio_params* p) {
+    p->default_point_depth = 0.5;
+    p->default_point_depth_variance = 100;
+    p->default_point_homogenous_variance = 0.00001;
+    p->flags = 0;
+}
+
+int ekfvio_batch_destroy(ekfvio_batch* b) {
+    if (!b) return 0;
+    cudaSetDevice(b->device);
+    cudaFree(b->d_mu); cudaFree(b->d_feat); cudaFree(b->d_P[0]); cudaFree(b->d_P[1]); cudaFree(b->d_nfeat); cudaFree(b->d_cache);
+    cudaFree(b->d_flags); cudaFree(b->d_klt_last); cudaFree(b->d_status); cudaFree(b->d_dt); cudaFree(b->d_K); cudaFree(b->d_W);
+    cudaFree(b->d_S); cudaFree(b->d_y); cudaFree(b->d_idx); cudaFree(b->d_m); cudaFree(b->d_fjac);
+    cudaFree(b->dd_z); cudaFree(b->dd_R); cudaFree(b->dd_pass);
+    cudaFreeHost(b->h_z); cudaFreeHost(b->h_R); cudaFreeHost(b->h_pass); cudaFreeHost(b->h_out);
+    delete b;
+    return 0;
+}
+
+int ekfvio_batch_create(ekfvio_batch** out, int device, int num_filters, int max_features, const ekfvio_params* params) {
+    if (!out || num_filters <= 0 || max_features < 0) return fail_msg("ekfvio_batch_create: bad arguments");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail_msg("ekfvio_batch_create: no CUDA device (this library has no CPU path)");
+    CU(cudaSetDevice(device));
+    ekfvio_batch* b = new (std::nothrow) ekfvio_batch();
+    if (!b) return fail_msg("out of host memory");
+    b->device = device;
+    b->F = num_filters; b->nmax = max_features;
+    b->Nmax = BASE + 3 * max_features;
+    b->ldP = (b->Nmax + 7) / 8 * 8;
+    b->mmax = 2 * max_features > 0 ? 2 * max_features : 2;
+    b->ldK = (b->mmax + 7) / 8 * 8 + 4;   // == 4 (mod 8): conflict-free DMMA fragment loads from shared memory
+    if (params) b->prm = *params; else ekfvio_default_params(&b->prm);
+    size_t F = b->F, nm = b->nmax > 0 ? b->nmax : 1;
+    size_t Pbytes = F * b->ldP * b->ldP * sizeof(double), Kbytes = F * b->ldP * b->ldK * sizeof(double);
+#define ALLOC(ptr, bytes) do { cudaError_t e2 = cudaMalloc((void**)&(ptr), (bytes)); if (e2 != cudaSuccess) { ekfvio_batch_destroy(b); return ekfvio::fail("cudaMalloc " #ptr, e2); } cudaMemset((ptr), 0, (bytes)); } while (0)
+    ALLOC(b->d_mu, F * BASE * sizeof(double));
+    ALLOC(b->d_feat, F * nm * 3 * sizeof(double));
+    ALLOC(b->d_P[0], Pbytes);
+    ALLOC(b->d_P[1], Pbytes);
+    ALLOC(b->d_nfeat, F * sizeof(int));
+    ALLOC(b->d_cache, F * 7 * sizeof(double));
+    ALLOC(b->d_flags, F * nm);
+    ALLOC(b->d_klt_last, F * nm * 2 * sizeof(double));
+    ALLOC(b->d_status, F * sizeof(int));
+    ALLOC(b->d_dt, F * sizeof(double));
+    ALLOC(b->d_K, Kbytes);
+    ALLOC(b->d_W, Kbytes);
+    ALLOC(b->d_y, F * b->mmax * sizeof(double));
+    ALLOC(b->d_idx, F * b->mmax * sizeof(int));
+    ALLOC(b->d_m, F * sizeof(int));
+    if (gain_general_smem_doubles(b->mmax) == 0) ALLOC(b->d_S, F * ((size_t)b->mmax * b->mmax + b->mmax) * sizeof(double));
+    ALLOC(b->dd_z, F * nm * 2 * sizeof(double));
+    ALLOC(b->dd_R, F * nm * 4 * sizeof(double));
+    ALLOC(b->dd_pass, F * nm);
+#undef ALLOC
+    if (cudaMallocHost((void**)&b->h_z, F * nm * 2 * sizeof(double)) != cudaSuccess || cudaMallocHost((void**)&b->h_R, F * nm * 4 * sizeof(double)) != cudaSuccess ||
+        cudaMallocHost((void**)&b->h_pass, F * nm) != cudaSuccess || cudaMallocHost((void**)&b->h_out, F * (BASE + nm * 3) * sizeof(double)) != cudaSuccess) {
+        ekfvio_batch_destroy(b);
+        return fail_msg("cudaMallocHost failed");
+    }
+    *out = b;
+    int rc = ekfvio_batch_reset(b, nullptr);
+    if (rc) { ekfvio_batch_destroy(b); *out = nullptr; return rc; }
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+
+int ekfvio_batch_num_filters(const ekfvio_batch* b) { return b ? b->F : 0; }
+int ekfvio_batch_max_features(const ekfvio_batch* b) { return b ? b->nmax : 0; }
+long long ekfvio_batch_launch_count(const ekfvio_batch* b) { return b ? b->launches : 0; }
+
+int ekfvio_batch_reset(ekfvio_batch* b, void* stream) {
+    CU(cudaSetDevice(b->device));
+    CU(launch_reset(ptrs(b), b->d_P[b->cur], (cudaStream_t)stream));
+    b->launches += 1;
+    return 0;
+}
+
+int ekfvio_batch_add_features(ekfvio_batch* b, const int* d_k, const double* d_uv, int kmax, void* stream) {
+    CU(cudaSetDevice(b->device));
+    CU(launch_add_features(ptrs(b), b->d_P[b->cur], d_k, d_uv, kmax, (cudaStream_t)stream));
+    b->launches += 1;
+    return 0;
+}
+
+int ekfvio_batch_process(ekfvio_batch* b, const double* d_dt, void* stream) {
+    CU(cudaSetDevice(b->device));
+    CU(launch_process_general(ptrs(b), b->d_P[b->cur], b->d_P[b->cur ^ 1], d_dt, 0, nullptr, (cudaStream_t)stream));
+    b->cur ^= 1;
+    b->launches += 1;
+    return 0;
+}
+
+int ekfvio_batch_process_dt(ekfvio_batch* b, double dt, void* stream) {
+    CU(cudaSetDevice(b->device));
+    CU(launch_fill_dt(b->d_dt, dt, b->F, (cudaStream_t)stream));
+    b->launches += 1;
+    return ekfvio_batch_process(b, b->d_dt, stream);
+}
+
+int ekfvio_batch_linearize(ekfvio_batch* b, const double* d_dt, double* d_F, void* stream) {
+    CU(cudaSetDevice(b->device));
+    CU(launch_process_general(ptrs(b), b->d_P[b->cur], nullptr, d_dt, 1, d_F, (cudaStream_t)stream));
+    b->launches += 1;
+    return 0;
+}
+
+int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, const uint8_t* d_pass, void* stream) {
+    CU(cudaSetDevice(b->device));
+    CU(launch_update_general(ptrs(b), b->d_P[b->cur], b->d_P[b->cur ^ 1], d_z, d_R, d_pass, b->d_S, (cudaStream_t)stream));
+    b->cur ^= 1;
+    b->launches += 2;
+    return 0;
+}
+
+int ekfvio_batch_check_sigma(ekfvio_batch* b, int* d_neg_diag, double* d_max_asym, void* stream) {
+    CU(cudaSetDevice(b->device));
+    CU(launch_check_sigma(ptrs(b), b->d_P[b->cur], d_neg_diag, d_max_asym, (cudaStream_t)stream));
+    b->launches += 1;
+    return 0;
+}
+
+int ekfvio_batch_accumulate_errors(ekfvio_batch* b, const double* d_truth_mu, double* d_acc, void* stream) {
+    CU(cudaSetDevice(b->device));
+    CU(launch_accumulate_errors(ptrs(b), d_truth_mu, d_acc, (cudaStream_t)stream));
+    b->launches += 1;
+    return 0;
+}
+
+int ekfvio_batch_get_view(ekfvio_batch* b, ekfvio_batch_view* v) {
+    v->d_mu = b->d_mu; v->d_feat = b->d_feat; v->d_P = b->d_P[b->cur]; v->d_nfeat = b->d_nfeat; v->d_status = b->d_status;
+    v->ldP = b->ldP; v->num_filters = b->F; v->max_features = b->nmax;
+    return 0;
+}
+
+int ekfvio_batch_get_state(ekfvio_batch* b, double* h_mu, double* h_feat, double* h_P, int* h_nfeat, double* h_cache, uint8_t* h_flags,
+                           double* h_klt_last, int* h_status) {
+    CU(cudaSetDevice(b->device));
+    CU(cudaDeviceSynchronize());
+    size_t F = b->F, nm = b->nmax;
+    if (h_mu) CU(cudaMemcpy(h_mu, b->d_mu, F * BASE * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_feat && nm) CU(cudaMemcpy(h_feat, b->d_feat, F * nm * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_nfeat) CU(cudaMemcpy(h_nfeat, b->d_nfeat, F * sizeof(int), cudaMemcpyDeviceToHost));
+    if (h_cache) CU(cudaMemcpy(h_cache, b->d_cache, F * 7 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_flags && nm) CU(cudaMemcpy(h_flags, b->d_flags, F * nm, cudaMemcpyDeviceToHost));
+    if (h_klt_last && nm) CU(cudaMemcpy(h_klt_last, b->d_klt_last, F * nm * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_status) CU(cudaMemcpy(h_status, b->d_status, F * sizeof(int), cudaMemcpyDeviceToHost));
+    if (h_P) {
+        double* tmp = nullptr;
+        size_t bytes = F * (size_t)b->Nmax * b->Nmax * sizeof(double);
+        CU(cudaMalloc((void**)&tmp, bytes));
+        cudaError_t e = launch_pack_P(b->d_P[b->cur], tmp, b->ldP, b->Nmax, b->F, 1, nullptr);
+        b->launches += 1;
+        if (e == cudaSuccess) e = cudaMemcpy(h_P, tmp, bytes, cudaMemcpyDeviceToHost);
+        cudaFree(tmp);
+        if (e != cudaSuccess) return ekfvio::fail("get_state P", e);
+    }
+    return 0;
+}
+
+int ekfvio_batch_set_state(ekfvio_batch* b, const double* h_mu, const double* h_feat, const double* h_P, const int* h_nfeat,
+                           const double* h_cache, const uint8_t* h_flags, const double* h_klt_last) {
+    CU(cudaSetDevice(b->device));
+    CU(cudaDeviceSynchronize());
+    size_t F = b->F, nm = b->nmax;
+    if (h_nfeat) {
+        for (size_t i = 0; i < F; ++i) if (h_nfeat[i] < 0 || h_nfeat[i] > b->nmax) return fail_msg("set_state: nfeat out of range");
+        CU(cudaMemcpy(b->d_nfeat, h_nfeat, F * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (h_mu) CU(cudaMemcpy(b->d_mu, h_mu, F * BASE * sizeof(double), cudaMemcpyHostToDevice));
+    if (h_feat && nm) CU(cudaMemcpy(b->d_feat, h_feat, F * nm * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    if (h_cache) CU(cudaMemcpy(b->d_cache, h_cache, F * 7 * sizeof(double), cudaMemcpyHostToDevice));
+    if (h_flags && nm) CU(cudaMemcpy(b->d_flags, h_flags, F * nm, cudaMemcpyHostToDevice));
+    if (h_klt_last && nm) CU(cudaMemcpy(b->d_klt_last, h_klt_last, F * nm * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    if (h_P) {
+        double* tmp = nullptr;
+        size_t bytes = F * (size_t)b->Nmax * b->Nmax * sizeof(double);
+        CU(cudaMalloc((void**)&tmp, bytes));
+        cudaError_t e = cudaMemcpy(tmp, h_P, bytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = launch_pack_P(b->d_P[b->cur], tmp, b->ldP, b->Nmax, b->F, 0, nullptr);
+        b->launches += 1;
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        cudaFree(tmp);
+        if (e != cudaSuccess) return ekfvio::fail("set_state P", e);
+    }
+    return 0;
+}
+
+int ekfvio_batch_add_features_h(ekfvio_batch* b, const int* h_k, const double* h_uv, int kmax, void* stream) {
+    CU(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kmax > b->nmax) return fail_msg("add_features_h: kmax exceeds max_features");
+    size_t F = b->F;
+    int* d_k = nullptr; double* d_uv = nullptr;
+    CU(cudaMalloc((void**)&d_k, F * sizeof(int)));
+    if (cudaMalloc((void**)&d_uv, F * (size_t)(kmax > 0 ? kmax : 1) * 2 * sizeof(double)) != cudaSuccess) { cudaFree(d_k); return fail_msg("add_features_h: cudaMalloc"); }
+    cudaError_t e = cudaMemcpyAsync(d_k, h_k, F * sizeof(int), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && kmax > 0) e = cudaMemcpyAsync(d_uv, h_uv, F * (size_t)kmax * 2 * sizeof(double), cudaMemcpyHostToDevice, st);
+    int rc = 0;
+    if (e == cudaSuccess) rc = ekfvio_batch_add_features(b, d_k, d_uv, kmax, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_k); cudaFree(d_uv);
+    if (e != cudaSuccess) return ekfvio::fail("add_features_h", e);
+    return rc;
+}
+
+int ekfvio_batch_update_h(ekfvio_batch* b, const double* h_z, const double* h_R, const uint8_t* h_pass, void* stream) {
+    CU(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t F = b->F, nm = b->nmax;
+    if (nm == 0) return ekfvio_batch_update(b, b->dd_z, b->dd_R, b->dd_pass, stream);
+    // the staging buffers are reused: wait for the previous consumer before overwriting them
+    CU(cudaStreamSynchronize(st));
+    memcpy(b->h_z, h_z, F * nm * 2 * sizeof(double));
+    memcpy(b->h_R, h_R, F * nm * 4 * sizeof(double));
+    memcpy(b->h_pass, h_pass, F * nm);
+    CU(cudaMemcpyAsync(b->dd_z, b->h_z, F * nm * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b->dd_R, b->h_R, F * nm * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(b->dd_pass, b->h_pass, F * nm, cudaMemcpyHostToDevice, st));
+    return ekfvio_batch_update(b, b->dd_z, b->dd_R, b->dd_pass, stream);
+}
+
+int ekfvio_batch_read_mu_h(ekfvio_batch* b, double* h_mu, double* h_feat, void* stream) {
+    CU(cudaSetDevice(b->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t F = b->F, nm = b->nmax;
+    CU(cudaMemcpyAsync(b->h_out, b->d_mu, F * BASE * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (h_feat && nm) CU(cudaMemcpyAsync(b->h_out + F * BASE, b->d_feat, F * nm * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h_mu) memcpy(h_mu, b->h_out, F * BASE * sizeof(double));
+    if (h_feat && nm) memcpy(h_feat, b->h_out + F * BASE, F * nm * 3 * sizeof(double));
+    return 0;
+}
+
+}  // extern "C"

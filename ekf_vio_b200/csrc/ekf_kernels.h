@@ -1,0 +1,31 @@
+// Internal interface between the C-ABI layer (ekf_api.cu) and the EKF kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace ekfvio {
+
+// Plain device-pointer bundle passed by value to every EKF kernel.
+struct EkfPtrs {
+    double* mu; double* feat; int* nfeat; double* cache; uint8_t* dflags; double* klt_last; int* status;
+    int* idx; double* y; int* m; double* K; double* W;
+    int F, nmax, Nmax, ldP, ldK, mmax;
+    uint32_t flags;
+    double depth, depth_var, uv_var;
+    size_t gain_smem_doubles;
+};
+
+// general path (ekf_general.cu)
+cudaError_t launch_process_general(const EkfPtrs& p, const double* Pin, double* Pout, const double* dts, int mode, double* F_out, cudaStream_t st);
+cudaError_t launch_update_general(const EkfPtrs& p, const double* Pin, double* Pout, const double* z, const double* R, const uint8_t* pass,
+                                  double* Sg, cudaStream_t st);
+size_t gain_general_smem_doubles(int mmax);
+cudaError_t launch_reset(const EkfPtrs& p, double* P0, cudaStream_t st);
+cudaError_t launch_add_features(const EkfPtrs& p, double* P0, const int* ks, const double* uv, int kmax, cudaStream_t st);
+cudaError_t launch_check_sigma(const EkfPtrs& p, const double* P0, int* neg, double* asym, cudaStream_t st);
+cudaError_t launch_fill_dt(double* dts, double dt, int F, cudaStream_t st);
+cudaError_t launch_pack_P(const double* P0, double* dense, int ld, int Nmax, int F, int to_dense, cudaStream_t st);
+cudaError_t launch_accumulate_errors(const EkfPtrs& p, const double* truth, double* acc, cudaStream_t st);
+
+}  // namespace ekfvio

@@ -1,0 +1,206 @@
+// C-ABI layer for the batched pyramidal KLT tracker (include/ekfvio_c.h, klt section).
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "klt_common.cuh"
+#include "klt_kernels.h"
+
+namespace ekfvio {
+extern thread_local std::string g_last_error;
+int fail(const char* what, cudaError_t e);
+int fail_msg(const std::string& msg);
+}  // namespace ekfvio
+
+using namespace kltdev;
+using ekfvio::fail_msg;
+
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return ekfvio::fail(#x, e_); } while (0)
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" {
+
+void ekfvio_klt_default_params(ekfvio_klt_params* p) {
+    p->window_size = 21;        // Params.h:104
+    p->max_pyramid_level = 3;   // Params.h:103
+    p->max_iterations = 30;     // KLTTracker.cpp:63
+    p->epsilon = 0.01;          // KLTTracker.cpp:63
+    p->min_eigen = 1e-4;        // Params.h:36
+    p->kill_pad = 11;           // Params.h:33
+    p->use_initial_flow = 1;    // KLTTracker.cpp:64
+}
+
+int ekfvio_klt_destroy(ekfvio_klt* k) {
+    if (!k) return 0;
+    cudaSetDevice(k->device);
+    cudaFree(k->d_slots); cudaFree(k->d_prev_pts); cudaFree(k->d_next_pts); cudaFree(k->d_status); cudaFree(k->d_err); cudaFree(k->d_npts);
+    cudaFreeHost(k->h_img); cudaFreeHost(k->h_pts);
+    delete[] k->slot_has_derivs; delete[] k->slot_batch;
+    delete k;
+    return 0;
+}
+
+int ekfvio_klt_create(ekfvio_klt** out, int device, int width, int height, int max_batch, int max_points, int num_slots,
+                      const ekfvio_klt_params* params) {
+    if (!out || width <= 0 || height <= 0 || max_batch <= 0 || max_points <= 0 || num_slots < 2) return fail_msg("ekfvio_klt_create: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail_msg("ekfvio_klt_create: no CUDA device (this library has no CPU path)");
+    CU(cudaSetDevice(device));
+    ekfvio_klt* k = new (std::nothrow) ekfvio_klt();
+    if (!k) return fail_msg("out of host memory");
+    k->device = device; k->width = width; k->height = height; k->max_batch = max_batch; k->max_points = max_points; k->num_slots = num_slots;
+    if (params) k->prm = *params; else ekfvio_klt_default_params(&k->prm);
+    const int win = k->prm.window_size;
+    if (win < 3 || win > 31 || (win & 1) == 0) { delete k; return fail_msg("ekfvio_klt_create: window_size must be odd and within 3..31"); }
+    if (k->prm.max_pyramid_level < 0 || k->prm.max_pyramid_level >= KLT_MAX_LEVELS) { delete k; return fail_msg("ekfvio_klt_create: max_pyramid_level out of range"); }
+    // level sizes as cv::buildOpticalFlowPyramid: stop when the next level would be <= window
+    Pyr& P = k->pyr;
+    int w = width, h = height, lv = 0;
+    size_t off = 0;
+    for (;;) {
+        Level& L = P.lv[lv];
+        L.w = w; L.h = h;
+        L.pitch = (int)align_up((size_t)w, 16);
+        L.dpitch = (int)align_up((size_t)w, 4);
+        L.img_stride = align_up((size_t)L.pitch * h, 256);
+        L.der_stride = align_up((size_t)L.dpitch * h * sizeof(short2), 256);
+        L.img_off = off; off += L.img_stride * max_batch;
+        L.der_off = off; off += L.der_stride * max_batch;
+        ++lv;
+        if (lv > k->prm.max_pyramid_level) break;
+        int nw = (w + 1) / 2, nh = (h + 1) / 2;
+        if (nw <= win || nh <= win) break;
+        w = nw; h = nh;
+    }
+    P.levels = lv;
+    k->slot_bytes = align_up(off, 256);
+    k->slot_has_derivs = new bool[num_slots]();
+    k->slot_batch = new int[num_slots]();
+    size_t npt = (size_t)max_batch * max_points;
+    cudaError_t e = cudaMalloc((void**)&k->d_slots, k->slot_bytes * num_slots);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&k->d_prev_pts, npt * 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&k->d_next_pts, npt * 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&k->d_status, npt);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&k->d_err, npt * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&k->d_npts, max_batch * sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&k->h_img, 2 * P.lv[0].img_stride * max_batch);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&k->h_pts, npt * 6 * sizeof(float) + max_batch * sizeof(int));
+    if (e != cudaSuccess) { ekfvio_klt_destroy(k); return ekfvio::fail("ekfvio_klt_create alloc", e); }
+    size_t smem = track_smem_bytes(win);
+    (void)smem;
+    *out = k;
+    return 0;
+}
+
+int ekfvio_klt_num_levels(const ekfvio_klt* k) { return k ? k->pyr.levels : 0; }
+long long ekfvio_klt_launch_count(const ekfvio_klt* k) { return k ? k->launches : 0; }
+
+int ekfvio_klt_build_pyramid(ekfvio_klt* k, int slot, const uint8_t* d_imgs, int pitch, int batch, int with_derivs, void* stream) {
+    if (slot < 0 || slot >= k->num_slots || batch <= 0 || batch > k->max_batch) return fail_msg("ekfvio_klt_build_pyramid: bad slot or batch");
+    CU(cudaSetDevice(k->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* base = k->d_slots + (size_t)slot * k->slot_bytes;
+    const Pyr& P = k->pyr;
+    for (int l = 0; l < P.levels; ++l) {
+        const Level& L = P.lv[l];
+        const uint8_t* src; int spitch; size_t sstride;
+        uint8_t* copy_dst = nullptr;
+        if (l == 0 && d_imgs) { src = d_imgs; spitch = pitch; sstride = (size_t)pitch * k->height; copy_dst = base + L.img_off; }
+        else { src = base + L.img_off; spitch = L.pitch; sstride = L.img_stride; }
+        short2* der = with_derivs ? reinterpret_cast<short2*>(base + L.der_off) : nullptr;
+        uint8_t* down = nullptr; int npitch = 0; size_t nstride = 0;
+        if (l + 1 < P.levels) { down = base + P.lv[l + 1].img_off; npitch = P.lv[l + 1].pitch; nstride = P.lv[l + 1].img_stride; }
+        if (!copy_dst && !der && !down) continue;
+        CU(launch_level(src, spitch, sstride, L.w, L.h, copy_dst, L.pitch, L.img_stride, der, L.dpitch, L.der_stride / sizeof(short2), down,
+                        npitch, nstride, batch, st));
+        k->launches += 1;
+    }
+    k->slot_has_derivs[slot] = with_derivs != 0;
+    k->slot_batch[slot] = batch;
+    return 0;
+}
+
+int ekfvio_klt_track(ekfvio_klt* k, int prev_slot, int next_slot, const float* d_prev_pts, float* d_next_pts, uint8_t* d_status, float* d_err,
+                     const int* d_npts, int batch, void* stream) {
+    if (prev_slot < 0 || prev_slot >= k->num_slots || next_slot < 0 || next_slot >= k->num_slots) return fail_msg("ekfvio_klt_track: bad slot");
+    if (!k->slot_has_derivs[prev_slot]) return fail_msg("ekfvio_klt_track: prev slot was built without derivatives");
+    if (batch <= 0 || batch > k->slot_batch[prev_slot] || batch > k->slot_batch[next_slot]) return fail_msg("ekfvio_klt_track: batch exceeds the built pyramids");
+    CU(cudaSetDevice(k->device));
+    CU(launch_track(k->pyr, k->d_slots + (size_t)prev_slot * k->slot_bytes, k->d_slots + (size_t)next_slot * k->slot_bytes, d_prev_pts, d_next_pts,
+                    d_status, d_err, d_npts, k->max_points, batch, k->prm, (cudaStream_t)stream));
+    k->launches += 1;
+    return 0;
+}
+
+int ekfvio_klt_postprocess(ekfvio_klt* k, const float* d_next_pts, const uint8_t* d_status, const int* d_npts, const float* d_K9, int batch,
+                           float* d_measured, float* d_cov, uint8_t* d_passed, void* stream) {
+    CU(cudaSetDevice(k->device));
+    CU(launch_postprocess(d_next_pts, d_status, d_npts, d_K9, k->max_points, batch, k->width, k->height, k->prm.kill_pad, d_measured, d_cov,
+                          d_passed, (cudaStream_t)stream));
+    k->launches += 1;
+    return 0;
+}
+
+int ekfvio_klt_track_pair_h(ekfvio_klt* k, const uint8_t* h_prev, const uint8_t* h_next, int pitch, int batch, const float* h_prev_pts,
+                            float* h_next_pts, uint8_t* h_status, float* h_err, const int* h_npts, void* stream) {
+    if (batch <= 0 || batch > k->max_batch) return fail_msg("ekfvio_klt_track_pair_h: bad batch");
+    CU(cudaSetDevice(k->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Level& L0 = k->pyr.lv[0];
+    uint8_t* s0 = k->d_slots;                   // slot 0 <- prev
+    uint8_t* s1 = k->d_slots + k->slot_bytes;   // slot 1 <- next
+    // frames go straight into level 0 of the slots (no staging copy on the device)
+    for (int which = 0; which < 2; ++which) {
+        const uint8_t* h = which ? h_next : h_prev;
+        uint8_t* stage = k->h_img + (size_t)which * L0.img_stride * k->max_batch;
+        for (int b = 0; b < batch; ++b)
+            for (int y = 0; y < k->height; ++y)
+                memcpy(stage + (size_t)b * L0.img_stride + (size_t)y * L0.pitch, h + ((size_t)b * k->height + y) * pitch, (size_t)k->width);
+        CU(cudaMemcpyAsync((which ? s1 : s0) + L0.img_off, stage, L0.img_stride * batch, cudaMemcpyHostToDevice, st));
+    }
+    size_t npt = (size_t)batch * k->max_points;
+    float* hp = k->h_pts;
+    memcpy(hp, h_prev_pts, npt * 2 * sizeof(float));
+    memcpy(hp + npt * 2, h_next_pts, npt * 2 * sizeof(float));
+    int* hn = reinterpret_cast<int*>(hp + (size_t)k->max_batch * k->max_points * 6);
+    memcpy(hn, h_npts, batch * sizeof(int));
+    CU(cudaMemcpyAsync(k->d_prev_pts, hp, npt * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(k->d_next_pts, hp + npt * 2, npt * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(k->d_npts, hn, batch * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(k->d_status, 0, npt, st));
+    CU(cudaMemsetAsync(k->d_err, 0, npt * sizeof(float), st));
+    int rc = ekfvio_klt_build_pyramid(k, 0, nullptr, 0, batch, 1, stream);
+    if (rc) return rc;
+    rc = ekfvio_klt_build_pyramid(k, 1, nullptr, 0, batch, 0, stream);
+    if (rc) return rc;
+    rc = ekfvio_klt_track(k, 0, 1, k->d_prev_pts, k->d_next_pts, k->d_status, k->d_err, k->d_npts, batch, stream);
+    if (rc) return rc;
+    float* ho = hp + npt * 2;  // reuse: next pts | err | status
+    CU(cudaMemcpyAsync(ho, k->d_next_pts, npt * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ho + npt * 2, k->d_err, npt * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ho + npt * 3, k->d_status, npt, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(h_next_pts, ho, npt * 2 * sizeof(float));
+    if (h_err) memcpy(h_err, ho + npt * 2, npt * sizeof(float));
+    memcpy(h_status, ho + npt * 3, npt);
+    return 0;
+}
+
+int ekfvio_klt_read_level(ekfvio_klt* k, int slot, int img, int level, uint8_t* h_img, int16_t* h_deriv, int* w_out, int* h_out) {
+    if (slot < 0 || slot >= k->num_slots || level < 0 || level >= k->pyr.levels || img < 0 || img >= k->max_batch) return fail_msg("ekfvio_klt_read_level: bad index");
+    CU(cudaSetDevice(k->device));
+    const Level& L = k->pyr.lv[level];
+    if (w_out) *w_out = L.w;
+    if (h_out) *h_out = L.h;
+    CU(cudaDeviceSynchronize());
+    uint8_t* base = k->d_slots + (size_t)slot * k->slot_bytes;
+    if (h_img) CU(cudaMemcpy2D(h_img, L.w, base + L.img_off + (size_t)img * L.img_stride, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    if (h_deriv) {
+        if (!k->slot_has_derivs[slot]) return fail_msg("ekfvio_klt_read_level: slot has no derivatives");
+        CU(cudaMemcpy2D(h_deriv, (size_t)L.w * 4, base + L.der_off + (size_t)img * L.der_stride, (size_t)L.dpitch * 4, (size_t)L.w * 4, L.h, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+// Shared definitions for the KLT kernels (sm_100a).  Arithmetic follows OpenCV's
+// calcOpticalFlowPyrLK operation by operation (oracle/klt_oracle.c), which is
+// what KLTTracker::findNewFeaturePositionsOpenCV calls (reference KLTTracker.cpp:61-64).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ekfvio_c.h"
+
+#define KLT_MAX_LEVELS 8
+
+namespace kltdev {
+
+struct Level {
+    int w, h;
+    int pitch;        // bytes per row of the u8 image (multiple of 16)
+    int dpitch;       // short2 elements per row of the derivative image (multiple of 4)
+    size_t img_off;   // byte offset of image 0 of this level inside the slot
+    size_t der_off;   // byte offset of derivative image 0
+    size_t img_stride;  // bytes between consecutive images of the batch
+    size_t der_stride;
+};
+
+struct Pyr {
+    int levels;  // number of levels (effective max level + 1)
+    Level lv[KLT_MAX_LEVELS];
+};
+
+// cv::borderInterpolate(p, len, BORDER_REFLECT_101)
+__host__ __device__ __forceinline__ int reflect101(int p, int len) {
+    if ((unsigned)p < (unsigned)len) return p;
+    if (len == 1) return 0;
+    do {
+        p = p < 0 ? -p : 2 * (len - 1) - p;
+    } while ((unsigned)p >= (unsigned)len);
+    return p;
+}
+
+}  // namespace kltdev
+
+struct ekfvio_klt {
+    int device = 0;
+    int width = 0, height = 0, max_batch = 0, max_points = 0, num_slots = 0;
+    ekfvio_klt_params prm{};
+    kltdev::Pyr pyr{};
+    size_t slot_bytes = 0;
+    uint8_t* d_slots = nullptr;       // num_slots * slot_bytes
+    bool* slot_has_derivs = nullptr;  // host
+    int* slot_batch = nullptr;        // host
+    // staging for the *_h entry point
+    float* d_prev_pts = nullptr; float* d_next_pts = nullptr; uint8_t* d_status = nullptr; float* d_err = nullptr; int* d_npts = nullptr;
+    uint8_t* h_img = nullptr;         // pinned: 2 * max_batch * height * level0 pitch
+    float* h_pts = nullptr;           // pinned: max_batch*max_points*(2+2+1) floats + status bytes
+    long long launches = 0;
+};

@@ -1,0 +1,192 @@
+/* ekfvio_c.h — C ABI of the B200-native (sm_100a) EKF + KLT hot paths of k-sheridan/ekf_vio.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ / torch types, no exceptions.
+ * Each entry point cites the reference interface it replaces (paths relative to the reference
+ * repository root).  Host code (the C++ facade in include/ekf_vio/, the Python binding in
+ * ekf_vio_b200/capi.py, or a maintainer's own binding — see INTEGRATION.md) calls only this.
+ *
+ * Conventions
+ *   - Every function returns 0 on success, non-zero on failure; ekfvio_last_error() gives the
+ *     message of the last failure on the calling thread.  (The reference's own convention is
+ *     void + ROS_ASSERT/ROS_ERROR; contract violations are reported as errors.)
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous
+ *     on that stream unless stated otherwise.
+ *   - Pointers named d_* are DEVICE pointers, h_* are HOST pointers.
+ *   - There is no CPU fallback: if no CUDA device is usable the create calls fail.
+ *
+ * Batch layout (F filters, capacity nmax features each, Nmax = 22 + 3*nmax):
+ *   mu    [F][22]            base state: p(0-2) q wxyz(3-6) body vel(7-9) omega(10-12)
+ *                            body accel(13-15) acc bias(16-18) gyro bias(19-21)
+ *                            (include/ekf_vio/TightlyCoupledEKF.h:11,29)
+ *   feat  [F][nmax][3]       Feature::mu = [u, v, 1/depth]          (Feature.h:41)
+ *   P     [F][Nmax][Nmax]    Sigma, dense row-major                  (TightlyCoupledEKF.h:34)
+ *   nfeat [F]                features.size()
+ *   cache [F][7]             convolveFeature's static cache (omega xyz, dq_inv wxyz), one
+ *                            private copy per filter                 (TightlyCoupledEKF.cpp:400-403)
+ *   flags [F][nmax]          Feature::delete_flag                    (Feature.h:46)
+ *   klt_last [F][nmax][2]    Feature::last_result_from_klt_tracker   (Feature.h:43)
+ *   status[F]                bit0: zero pivot in the S factorisation (TightlyCoupledEKF.cpp:579)
+ *                            bit1: non-finite state after an update
+ */
+#ifndef EKFVIO_C_H_
+#define EKFVIO_C_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EKFVIO_BASE_STATE_SIZE 22 /* TightlyCoupledEKF.h:12 */
+
+/* Flags in ekfvio_params.flags.  0 = reference behaviour, including the reference's errors
+ * (SURVEY.md §8a E1..E6).  Each fix is opt-in. */
+#define EKFVIO_FLAG_FORCE_GENERAL_PATH 0x1u /* always use the general (non-tiled) kernels */
+#define EKFVIO_FLAG_FRESH_DQ_CACHE 0x2u     /* fix E2: never reuse a dq_inv computed for another dt */
+
+typedef struct ekfvio_params {
+    double default_point_depth;               /* Params.h:83   DEFAULT_POINT_DEPTH = 0.5 */
+    double default_point_depth_variance;      /* Params.h:84   DEFAULT_POINT_DEPTH_VARIANCE = 100 */
+    double default_point_homogenous_variance; /* Params.h:86   DEFAULT_POINT_HOMOGENOUS_VARIANCE = 1e-5 */
+    uint32_t flags;
+} ekfvio_params;
+
+typedef struct ekfvio_batch ekfvio_batch;
+
+const char* ekfvio_last_error(void);
+/* Fills *p with the reference defaults (Params.h:83-86). */
+void ekfvio_default_params(ekfvio_params* p);
+
+/* ---- batched filter: TightlyCoupledEKF (include/ekf_vio/TightlyCoupledEKF.h:25-70) ---------- */
+
+/* TightlyCoupledEKF::TightlyCoupledEKF + initializeBaseState (TightlyCoupledEKF.cpp:10-56) for
+ * num_filters independent filters with room for max_features features each. */
+int ekfvio_batch_create(ekfvio_batch** out, int device, int num_filters, int max_features, const ekfvio_params* params);
+int ekfvio_batch_destroy(ekfvio_batch* b);
+int ekfvio_batch_num_filters(const ekfvio_batch* b);
+int ekfvio_batch_max_features(const ekfvio_batch* b);
+
+/* initializeBaseState (TightlyCoupledEKF.cpp:23-56) on every filter; drops all features. */
+int ekfvio_batch_reset(ekfvio_batch* b, void* stream);
+
+/* addNewFeatures (TightlyCoupledEKF.cpp:58-94): filter f appends d_k[f] features whose metric
+ * (u,v) are d_uv[f][0..k-1][0..1] (row stride kmax*2).  Exceeding max_features is an error
+ * reported through status bit2 for that filter (nothing is appended to it). */
+int ekfvio_batch_add_features(ekfvio_batch* b, const int* d_k, const double* d_uv, int kmax, void* stream);
+
+/* process(dt) (TightlyCoupledEKF.cpp:96-121): numericallyLinearizeProcess, convolveFeature on
+ * every feature, convolveBaseState, Sigma = F Sigma F' + Q, prune.  d_dt[F]. */
+int ekfvio_batch_process(ekfvio_batch* b, const double* d_dt, void* stream);
+/* Same with one dt for all filters. */
+int ekfvio_batch_process_dt(ekfvio_batch* b, double dt, void* stream);
+
+/* updateWithFeaturePositions (TightlyCoupledEKF.cpp:475-628).  d_z[F][nmax][2] metric
+ * measurements, d_R[F][nmax][4] row-major 2x2 covariances, d_pass[F][nmax] (0/1).  Entries of
+ * features >= nfeat[f] are ignored. */
+int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, const uint8_t* d_pass, void* stream);
+
+/* numericallyLinearizeProcess (TightlyCoupledEKF.cpp:176-325): writes the dense N x N Jacobian
+ * of filter f to d_F[f][Nmax][Nmax] (row-major, leading dimension Nmax) without changing the
+ * state — except the convolveFeature cache, exactly as in the reference. */
+int ekfvio_batch_linearize(ekfvio_batch* b, const double* d_dt, double* d_F, void* stream);
+
+/* checkSigma (TightlyCoupledEKF.cpp:699-714): number of negative diagonal entries and
+ * max |Sigma_ij - Sigma_ji| per filter.  Device outputs. */
+int ekfvio_batch_check_sigma(ekfvio_batch* b, int* d_neg_diag, double* d_max_asym, void* stream);
+
+/* State access (also the checkpoint/restore hook).  HOST pointers, any may be NULL.  Synchronous.
+ * Layouts as in the header comment; P has leading dimension Nmax = 22 + 3*max_features. */
+int ekfvio_batch_get_state(ekfvio_batch* b, double* h_mu, double* h_feat, double* h_P, int* h_nfeat, double* h_cache,
+                           uint8_t* h_flags, double* h_klt_last, int* h_status);
+int ekfvio_batch_set_state(ekfvio_batch* b, const double* h_mu, const double* h_feat, const double* h_P, const int* h_nfeat,
+                           const double* h_cache, const uint8_t* h_flags, const double* h_klt_last);
+
+/* Host-buffer convenience wrappers (the calls the C++ facade and the e2e benchmark use): inputs
+ * are staged through pinned memory, copied on `stream`, and the call returns after the work is
+ * enqueued (inputs are consumed before return). */
+int ekfvio_batch_add_features_h(ekfvio_batch* b, const int* h_k, const double* h_uv, int kmax, void* stream);
+int ekfvio_batch_update_h(ekfvio_batch* b, const double* h_z, const double* h_R, const uint8_t* h_pass, void* stream);
+/* Copies mu (F x 22) and feat (F x nmax x 3) to host after the enqueued work; synchronises. */
+int ekfvio_batch_read_mu_h(ekfvio_batch* b, double* h_mu, double* h_feat, void* stream);
+
+/* Device pointers of the live state, for zero-copy consumers (valid until destroy; P points at
+ * the current buffer and may change after each process/update — query again). */
+typedef struct ekfvio_batch_view {
+    double* d_mu;       /* [F][22] */
+    double* d_feat;     /* [F][nmax][3] */
+    double* d_P;        /* [F][ldP][ldP] */
+    int* d_nfeat;       /* [F] */
+    int* d_status;      /* [F] */
+    int ldP;            /* leading dimension of P (>= Nmax, multiple of 8) */
+    int num_filters, max_features;
+} ekfvio_batch_view;
+int ekfvio_batch_get_view(ekfvio_batch* b, ekfvio_batch_view* view);
+
+/* Number of kernel launches this library has issued on behalf of `b` since creation. */
+long long ekfvio_batch_launch_count(const ekfvio_batch* b);
+
+/* Monte-Carlo error statistics (no reference counterpart; north_star): per-filter squared
+ * position / velocity error against ground truth accumulated on device into d_acc[8] =
+ * {sum_e2_pos, sum_e2_vel, sum_e2_quat, count, max_e2_pos, 0, 0, 0}; the caller reduces d_acc
+ * across ranks with one NCCL all-reduce (sum for 0-3). */
+int ekfvio_batch_accumulate_errors(ekfvio_batch* b, const double* d_truth_mu /*[F][22]*/, double* d_acc, void* stream);
+
+/* ---- pyramidal KLT tracker: KLTTracker (include/ekf_vio/KLTTracker.h:25-99) ----------------- */
+
+typedef struct ekfvio_klt_params {
+    int window_size;      /* Params.h:104  WINDOW_SIZE = 21  (odd, <= 31) */
+    int max_pyramid_level;/* Params.h:103  MAX_PYRAMID_LEVEL = 3 */
+    int max_iterations;   /* KLTTracker.cpp:63   30 */
+    double epsilon;       /* KLTTracker.cpp:63   0.01 */
+    double min_eigen;     /* Params.h:36   KLT_MIN_EIGEN = 1e-4 */
+    int kill_pad;         /* Params.h:33   KILL_PAD = 11 */
+    int use_initial_flow; /* KLTTracker.cpp:64   OPTFLOW_USE_INITIAL_FLOW -> 1 */
+} ekfvio_klt_params;
+
+typedef struct ekfvio_klt ekfvio_klt;
+
+void ekfvio_klt_default_params(ekfvio_klt_params* p);
+
+/* A tracker for up to max_batch image pairs of width x height 8-bit pixels and up to max_points
+ * points per pair.  It owns `num_slots` pyramid slots, each holding max_batch pyramids. */
+int ekfvio_klt_create(ekfvio_klt** out, int device, int width, int height, int max_batch, int max_points, int num_slots,
+                      const ekfvio_klt_params* params);
+int ekfvio_klt_destroy(ekfvio_klt* k);
+/* Number of pyramid levels actually used (OpenCV stops when the next level would be <= window). */
+int ekfvio_klt_num_levels(const ekfvio_klt* k);
+
+/* cv::buildOpticalFlowPyramid (+ calcScharrDeriv when with_derivs) as called inside
+ * cv::calcOpticalFlowPyrLK (KLTTracker.cpp:61): d_imgs[batch][height][pitch] 8-bit gray.
+ * Fills pyramid slot `slot`. */
+int ekfvio_klt_build_pyramid(ekfvio_klt* k, int slot, const uint8_t* d_imgs, int pitch, int batch, int with_derivs, void* stream);
+
+/* LKTrackerInvoker over all levels (cv::calcOpticalFlowPyrLK, KLTTracker.cpp:61-64) between
+ * pyramid slots prev_slot (needs derivatives) and next_slot.  d_prev_pts[batch][max_points][2]
+ * pixel coordinates, d_next_pts same shape: in = initial flow (if use_initial_flow), out =
+ * result.  d_status[batch][max_points] (1 = tracked), d_err[batch][max_points] (may be NULL),
+ * d_npts[batch] points per image pair. */
+int ekfvio_klt_track(ekfvio_klt* k, int prev_slot, int next_slot, const float* d_prev_pts, float* d_next_pts, uint8_t* d_status,
+                     float* d_err, const int* d_npts, int batch, void* stream);
+
+/* KLTTracker.cpp:72-92 epilogue + Feature::pixel2Metric (Feature.h:60-62, with the reference's
+ * linear-index use of K — E1): passed = status==1 && inside kill-pad; cov = 1e-5*I scaled by
+ * 1/fx^2, 1/fy^2; measured = ((x-K(2))/K(0), (y-K(5))/K(4)).  d_K9[batch][9] column-major float
+ * 3x3.  d_measured entries of failed points are left untouched, as in the reference. */
+int ekfvio_klt_postprocess(ekfvio_klt* k, const float* d_next_pts, const uint8_t* d_status, const int* d_npts, const float* d_K9,
+                           int batch, float* d_measured, float* d_cov, uint8_t* d_passed, void* stream);
+
+/* Host-buffer convenience: build both pyramids from host images, track, post-process, copy the
+ * results back; synchronous.  The KLTTracker facade's findNewFeaturePositions is this call. */
+int ekfvio_klt_track_pair_h(ekfvio_klt* k, const uint8_t* h_prev, const uint8_t* h_next, int pitch, int batch, const float* h_prev_pts,
+                            float* h_next_pts, uint8_t* h_status, float* h_err, const int* h_npts, void* stream);
+
+/* Reads back level `level` of image `img` in slot `slot` (tests): h_img[h_l][w_l] and, if not
+ * NULL and the slot has derivatives, h_deriv[h_l][w_l][2] int16.  Synchronous. */
+int ekfvio_klt_read_level(ekfvio_klt* k, int slot, int img, int level, uint8_t* h_img, int16_t* h_deriv, int* w_out, int* h_out);
+
+long long ekfvio_klt_launch_count(const ekfvio_klt* k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EKFVIO_C_H_ */

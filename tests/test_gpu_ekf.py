@@ -1,0 +1,269 @@
+"""GPU parity tests of the batched EKF against the FP64 oracle, through the C ABI.
+
+Tolerance (north_star / SURVEY.md §8d): max|delta| / max|ref| <= 1e-9 per step for the state
+vector and for Sigma.  Scenarios are the reference's own (test/analyzeEKFSimulation.cpp:233-244,
+test/test_ekf.cpp, test/jacobian_test.cpp).
+"""
+import numpy as np
+import pytest
+
+from tests import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def rel(a, b):
+    d = np.max(np.abs(a - b)) if a.size else 0.0
+    s = np.max(np.abs(b)) if b.size else 1.0
+    return d / (s if s > 0 else 1.0)
+
+
+def gpu_state(batch, f=0):
+    s = batch.get_state()
+    n = int(s["nfeat"][f]); N = 22 + 3 * n
+    return dict(mu=s["mu"][f], feat=s["feat"][f, :n], P=s["P"][f, :N, :N], cache=s["cache"][f], flags=s["flags"][f, :n],
+                klt_last=s["klt_last"][f, :n], status=int(s["status"][f]), n=n)
+
+
+def assert_close(g, o, tol=TOL, what=""):
+    assert g["n"] == len(o["feat"]), what
+    full_g = np.concatenate([g["mu"], g["feat"].ravel()])
+    full_o = np.concatenate([o["mu"], o["feat"].ravel()])
+    assert rel(full_g, full_o) <= tol, f"{what}: state rel {rel(full_g, full_o):.3e}"
+    assert rel(g["P"], o["P"]) <= tol, f"{what}: P rel {rel(g['P'], o['P']):.3e}"
+
+
+def make_batch(F, nmax, flags=0):
+    from ekf_vio_b200 import capi
+    return capi.EkfBatch(F, nmax, params=capi.default_params(flags))
+
+
+def torch_inputs(z, R, passed):
+    import torch
+    return (torch.from_numpy(np.ascontiguousarray(z, np.float64)).cuda(), torch.from_numpy(np.ascontiguousarray(R, np.float64)).cuda(),
+            torch.from_numpy(np.ascontiguousarray(passed, np.uint8)).cuda())
+
+
+PATHS = [pytest.param(0, id="default"), pytest.param(1, id="general")]
+
+
+@pytest.mark.parametrize("flags", PATHS)
+@pytest.mark.parametrize("sid", range(6))
+def test_simulation_scenarios_free_running(cuda, sid, flags):
+    """simulateAndVisualizeEKF restated: process + update every step, compared after every call."""
+    sc = O.SCENARIOS[sid]
+    steps, uv, meas = O.scenario(**sc)
+    n = sc["n"]
+    orc = O.OracleFilter()
+    orc.add_features(uv)
+    b = make_batch(1, n, flags)
+    b.add_features_h(np.array([n], np.int32), uv.astype(np.float64)[None])
+    assert_close(gpu_state(b), orc.state(), what="after addNewFeatures")
+    dt = float(np.float32(sc["dt"]))
+    R = np.tile(np.array([1e-5, 0, 0, 1e-5]), (1, n, 1))
+    passed = np.ones((1, n), np.uint8)
+    worst = 0.0
+    for s in range(steps):
+        orc.process(dt)
+        b.process(dt)
+        g, o = gpu_state(b), orc.state()
+        assert_close(g, o, what=f"scenario {sid} step {s} process")
+        z = meas[s].astype(np.float64)[None]
+        orc.update(z[0], R[0], passed[0])
+        b.update(*torch_inputs(z, R, passed))
+        g, o = gpu_state(b), orc.state()
+        assert_close(g, o, what=f"scenario {sid} step {s} update")
+        worst = max(worst, rel(g["P"], o["P"]))
+        assert g["status"] == 0
+        np.testing.assert_array_equal(g["klt_last"], o["klt_last"])
+    neg, asym = orc.check_sigma()
+    assert neg == 0 and asym <= 1e-3          # the reference's own pass criterion (checkSigma)
+    import torch
+    dneg = torch.zeros(1, dtype=torch.int32, device="cuda"); dasym = torch.zeros(1, dtype=torch.float64, device="cuda")
+    b.check_sigma(dneg, dasym)
+    assert int(dneg[0]) == 0 and float(dasym[0]) <= 1e-3
+    print(f"scenario {sid}: worst P rel diff over {steps} steps = {worst:.3e}")
+
+
+@pytest.mark.parametrize("flags", PATHS)
+def test_resync_every_step(cuda, flags):
+    """Per-step parity with the GPU state re-seeded from the oracle before each step."""
+    sc = O.SCENARIOS[4]
+    steps, uv, meas = O.scenario(**sc)
+    n = sc["n"]
+    orc = O.OracleFilter(); orc.add_features(uv)
+    b = make_batch(1, n, flags)
+    b.add_features_h(np.array([n], np.int32), uv.astype(np.float64)[None])
+    dt = float(np.float32(sc["dt"]))
+    R = np.tile(np.array([1e-5, 0, 0, 1e-5]), (1, n, 1)); passed = np.ones((1, n), np.uint8)
+    for s in range(min(steps, 25)):
+        o = orc.state()
+        b.set_state(mu=o["mu"][None], feat=o["feat"][None], P=o["P"][None], cache=o["cache"][None])
+        orc.process(dt); b.process(dt)
+        assert_close(gpu_state(b), orc.state(), tol=1e-11, what=f"resync step {s} process")
+        o = orc.state()
+        b.set_state(mu=o["mu"][None], feat=o["feat"][None], P=o["P"][None], cache=o["cache"][None])
+        z = meas[s].astype(np.float64)[None]
+        orc.update(z[0], R[0], passed[0]); b.update(*torch_inputs(z, R, passed))
+        assert_close(gpu_state(b), orc.state(), what=f"resync step {s} update")
+
+
+@pytest.mark.parametrize("flags", PATHS)
+def test_test_ekf_update_case(cuda, flags):
+    """test/test_ekf.cpp:41-82: 3 features, measured {T,F,T}, cov 1e-3 I, update without process."""
+    feats = np.array([[0.1, 0.1], [-0.1, -0.1], [0.1, -0.1]])
+    orc = O.OracleFilter(); orc.add_features(feats)
+    b = make_batch(1, 3, flags)
+    b.add_features_h(np.array([3], np.int32), feats[None])
+    R = np.tile(np.array([1e-3, 0, 0, 1e-3]), (1, 3, 1)); passed = np.array([[1, 0, 1]], np.uint8)
+    for _ in range(2):
+        orc.update(feats, R[0], passed[0]); b.update(*torch_inputs(feats[None], R, passed))
+        g, o = gpu_state(b), orc.state()
+        assert_close(g, o, what="test_ekf update")
+        np.testing.assert_array_equal(g["flags"], o["flags"])       # feature 1 flagged for deletion
+        assert list(g["flags"]) == [0, 1, 0]
+
+
+@pytest.mark.parametrize("n,frac", [(103, 1.0), (103, 0.5)])
+def test_medium_state_update(cuda, n, frac):
+    """test/test_ekf.cpp:97-111 sized case (n=103) after two process steps so Sigma is dense."""
+    rng = np.random.default_rng(5)
+    uv = rng.uniform(-0.8, 0.8, (n, 2))
+    orc = O.OracleFilter(); orc.add_features(uv)
+    b = make_batch(1, n)
+    b.add_features_h(np.array([n], np.int32), uv[None])
+    mu = orc.state()["mu"]; mu[7:10] = [0.2, -0.1, 0.05]; mu[10:13] = [0.02, 0.1, -0.05]
+    st = orc.state(); orc.set_state(mu=mu, feat=st["feat"], Pm=st["P"])
+    b.set_state(mu=mu[None])
+    passed = (rng.uniform(size=(1, n)) < frac).astype(np.uint8)
+    R = np.tile(np.array([1e-5, 0, 0, 1e-5]), (1, n, 1))
+    for s in range(2):
+        orc.process(0.05); b.process(0.05)
+        assert_close(gpu_state(b), orc.state(), what=f"n={n} process {s}")
+        z = (orc.state()["feat"][:, :2] + rng.normal(0, 1e-3, (n, 2)))[None]
+        orc.update(z[0], R[0], passed[0]); b.update(*torch_inputs(z, R, passed))
+        assert_close(gpu_state(b), orc.state(), what=f"n={n} update {s}")
+
+
+@pytest.mark.parametrize("flags", PATHS)
+def test_heterogeneous_batch_and_edge_cases(cuda, flags):
+    """Filters with 0, 1, 7, 30 features in one batch; no measurements; asymmetric R; staged feature addition."""
+    rng = np.random.default_rng(11)
+    counts = [0, 1, 7, 30, 30, 12]
+    F, nmax = len(counts), 30
+    b = make_batch(F, nmax, flags)
+    orcs = [O.OracleFilter() for _ in counts]
+    uv = np.zeros((F, nmax, 2))
+    for f, c in enumerate(counts):
+        uv[f, :c] = rng.uniform(-1, 1, (c, 2))
+    # staged addition: first half, then the rest (addNewFeatures twice)
+    k1 = np.array([c // 2 for c in counts], np.int32)
+    b.add_features_h(k1, uv)
+    rest = np.zeros_like(uv)
+    k2 = np.array([c - c // 2 for c in counts], np.int32)
+    for f, c in enumerate(counts):
+        rest[f, :k2[f]] = uv[f, c // 2:c]
+        if c // 2: orcs[f].add_features(uv[f, :c // 2])
+        if k2[f]: orcs[f].add_features(uv[f, c // 2:c])
+    b.add_features_h(k2, rest)
+    mus = np.zeros((F, 22))
+    for f, o in enumerate(orcs):
+        st = o.state(); mu = st["mu"]
+        mu[7:10] = rng.uniform(-0.3, 0.3, 3); mu[10:13] = rng.uniform(-0.3, 0.3, 3); mu[13:16] = rng.uniform(-0.1, 0.1, 3)
+        o.set_state(mu=mu, feat=st["feat"], Pm=st["P"]); mus[f] = mu
+    b.set_state(mu=mus)
+    import torch
+    dts = np.array([0.05, 0.02, 0.1, 0.05, 0.033, 0.05])
+    for step in range(4):
+        for f, o in enumerate(orcs):
+            o.process(dts[f])
+        b.process(torch.from_numpy(dts).cuda())
+        for f, o in enumerate(orcs):
+            assert_close(gpu_state(b, f), o.state(), what=f"het filter {f} process {step}")
+        z = np.zeros((F, nmax, 2)); R = np.zeros((F, nmax, 4)); passed = np.zeros((F, nmax), np.uint8)
+        for f, o in enumerate(orcs):
+            c = counts[f]
+            ft = o.state()["feat"]
+            z[f, :c] = ft[:, :2] + rng.normal(0, 2e-3, (c, 2))
+            R[f, :c] = [1e-5, 0, 0, 1e-5]
+            passed[f, :c] = rng.uniform(size=c) < 0.7
+        if step == 1:
+            passed[3, :] = 0                       # no measurements at all for filter 3
+            R[4, :counts[4]] = [2e-5, 3e-6, 1e-6, 1e-5]   # asymmetric 2x2 blocks (E6 made visible)
+        for f, o in enumerate(orcs):
+            c = counts[f]
+            o.update(z[f, :c], R[f, :c], passed[f, :c])
+        b.update(*torch_inputs(z, R, passed))
+        for f, o in enumerate(orcs):
+            g, os_ = gpu_state(b, f), o.state()
+            assert_close(g, os_, what=f"het filter {f} update {step}")
+            np.testing.assert_array_equal(g["flags"], os_["flags"])
+            np.testing.assert_array_equal(g["klt_last"], os_["klt_last"])
+
+
+def test_linearize_jacobian_test_cases(cuda):
+    """test/jacobian_test.cpp:25-47, including the stale dq_inv cache (E2) at :45-47."""
+    import torch
+    feats = np.array([[0.1, 0.1], [-0.1, -0.1], [0.1, -0.1]])
+    orc = O.OracleFilter(depth_var=0.0, uv_var=0.0); orc.add_features(feats)
+    b = make_batch(1, 3)
+    b.add_features_h(np.array([3], np.int32), feats[None])
+    Fg = torch.zeros(1, 31, 31, dtype=torch.float64, device="cuda")
+
+    def both(dt, tol=1e-9):
+        Fo = orc.linearize(dt)
+        b.linearize(torch.tensor([dt], dtype=torch.float64, device="cuda"), Fg)
+        torch.cuda.synchronize()
+        assert rel(Fg[0].cpu().numpy(), Fo) <= tol
+        np.testing.assert_allclose(gpu_state(b)["cache"], orc.state()["cache"], rtol=0, atol=1e-15)
+
+    both(0.1); both(0.0)
+    mu = orc.state()["mu"]; mu[10] = 3.1415
+    st = orc.state(); orc.set_state(mu=mu, feat=st["feat"], Pm=st["P"]); b.set_state(mu=mu[None])
+    both(0.1)
+    mu[7] = 1.0
+    orc.set_state(mu=mu, feat=st["feat"], Pm=st["P"]); b.set_state(mu=mu[None])
+    both(0.1)
+    both(0.0)   # columns 7-9 are computed with the dq_inv cached for dt = 0.1 (E2; invisible at dt = 0)
+    both(0.1)
+    both(0.2)   # here the stale dq_inv (dt = 0.1) is visible in columns 7-9
+    # and the fix flag really changes that
+    from ekf_vio_b200 import capi
+    b2 = make_batch(1, 3, capi.FLAG_FRESH_DQ_CACHE)
+    b2.add_features_h(np.array([3], np.int32), feats[None]); b2.set_state(mu=mu[None])
+    dt1 = torch.tensor([0.1], dtype=torch.float64, device="cuda"); dt0 = torch.tensor([0.2], dtype=torch.float64, device="cuda")
+    b2.linearize(dt1, Fg); b2.linearize(dt0, Fg); torch.cuda.synchronize()
+    F_fixed = Fg[0].cpu().numpy().copy()
+    b.linearize(dt1, Fg); b.linearize(dt0, Fg); torch.cuda.synchronize()
+    assert np.max(np.abs(F_fixed - Fg[0].cpu().numpy())) > 1e-3
+
+
+def test_checkpoint_roundtrip(cuda):
+    """get_state/set_state is the checkpoint hook: a restored batch continues bit-identically."""
+    sc = O.SCENARIOS[1]
+    steps, uv, meas = O.scenario(**sc)
+    n = sc["n"]
+    a = make_batch(2, n); c = make_batch(2, n)
+    uv2 = np.stack([uv, uv * 0.9]).astype(np.float64)
+    a.add_features_h(np.array([n, n], np.int32), uv2)
+    R = np.tile(np.array([1e-5, 0, 0, 1e-5]), (2, n, 1)); passed = np.ones((2, n), np.uint8)
+    for s in range(5):
+        a.process(0.05); a.update(*torch_inputs(np.stack([meas[s], meas[s]]).astype(np.float64), R, passed))
+    s0 = a.get_state()
+    c.set_state(mu=s0["mu"], feat=s0["feat"], P=s0["P"], nfeat=s0["nfeat"], cache=s0["cache"], flags=s0["flags"], klt_last=s0["klt_last"])
+    for s in range(5, 8):
+        zz = torch_inputs(np.stack([meas[s], meas[s]]).astype(np.float64), R, passed)
+        a.process(0.05); a.update(*zz); c.process(0.05); c.update(*zz)
+    sa, sc_ = a.get_state(), c.get_state()
+    for key in ("mu", "feat", "P", "cache"):
+        np.testing.assert_array_equal(sa[key], sc_[key])
+
+
+def test_capacity_overflow_is_flagged(cuda):
+    b = make_batch(1, 4)
+    b.add_features_h(np.array([3], np.int32), np.zeros((1, 3, 2)))
+    b.add_features_h(np.array([3], np.int32), np.zeros((1, 3, 2)))
+    s = b.get_state(want_P=False)
+    assert int(s["nfeat"][0]) == 3 and int(s["status"][0]) & 4
