@@ -97,6 +97,11 @@ SIGNATURES = {
     "ekfvio_klt_track_pair_h": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ekfvio_klt_read_level": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, C.POINTER(c_int), C.POINTER(c_int)]),
     "ekfvio_klt_launch_count": (C.c_longlong, [c_void_p]),
+    "ekfvio_batch_enable_timing": (c_int, [c_void_p, c_int]),
+    "ekfvio_batch_get_timing": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "ekfvio_measure_fp64_peak": (c_int, [c_int, C.POINTER(c_double), C.POINTER(c_double)]),
+    "ekfvio_klt_enable_timing": (c_int, [c_void_p, c_int]),
+    "ekfvio_klt_get_timing": (c_int, [c_void_p, c_void_p, c_void_p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():
@@ -221,6 +226,22 @@ class EkfBatch:
     def launches(self) -> int:
         return int(lib.ekfvio_batch_launch_count(self._h))
 
+    def enable_timing(self, on: bool = True):
+        _check(lib.ekfvio_batch_enable_timing(self._h, int(on)))
+
+    def timing(self):
+        """(ms[8], count[8]) accumulated per kernel slot: 0 process, 1 gain, 2 covariance update."""
+        ms = np.zeros(8, np.float64); cnt = np.zeros(8, np.int64)
+        _check(lib.ekfvio_batch_get_timing(self._h, _ptr(ms), _ptr(cnt)))
+        return ms, cnt
+
+
+def measure_fp64_peak(device: int = 0):
+    """(DMMA TFLOP/s, DFMA TFLOP/s) measured on this GPU by register-resident loops."""
+    a, b = c_double(), c_double()
+    _check(lib.ekfvio_measure_fp64_peak(device, C.byref(a), C.byref(b)))
+    return a.value, b.value
+
 
 def default_klt_params() -> KltParams:
     p = KltParams()
@@ -287,3 +308,12 @@ class KltTracker:
     @property
     def launches(self) -> int:
         return int(lib.ekfvio_klt_launch_count(self._h))
+
+    def enable_timing(self, on: bool = True):
+        _check(lib.ekfvio_klt_enable_timing(self._h, int(on)))
+
+    def timing(self):
+        """(ms[8], count[8]): 0..3 pyramid level kernels, 4 track, 5 post-process."""
+        ms = np.zeros(8, np.float64); cnt = np.zeros(8, np.int64)
+        _check(lib.ekfvio_klt_get_timing(self._h, _ptr(ms), _ptr(cnt)))
+        return ms, cnt

@@ -126,7 +126,9 @@ int ekfvio_batch_add_features(ekfvio_batch* b, const int* d_k, const double* d_u
 
 int ekfvio_batch_process(ekfvio_batch* b, const double* d_dt, void* stream) {
     CU(cudaSetDevice(b->device));
+    b->timer.begin(0, (cudaStream_t)stream);
     CU(launch_process_general(ptrs(b), b->d_P[b->cur], b->d_P[b->cur ^ 1], d_dt, 0, nullptr, (cudaStream_t)stream));
+    b->timer.end((cudaStream_t)stream);
     b->cur ^= 1;
     b->launches += 1;
     return 0;
@@ -148,7 +150,13 @@ int ekfvio_batch_linearize(ekfvio_batch* b, const double* d_dt, double* d_F, voi
 
 int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, const uint8_t* d_pass, void* stream) {
     CU(cudaSetDevice(b->device));
-    CU(launch_update_general(ptrs(b), b->d_P[b->cur], b->d_P[b->cur ^ 1], d_z, d_R, d_pass, b->d_S, (cudaStream_t)stream));
+    cudaStream_t st = (cudaStream_t)stream;
+    b->timer.begin(1, st);
+    CU(launch_gain_general(ptrs(b), b->d_P[b->cur], d_z, d_R, d_pass, b->d_S, st));
+    b->timer.end(st);
+    b->timer.begin(2, st);
+    CU(launch_joseph_general(ptrs(b), b->d_P[b->cur], b->d_P[b->cur ^ 1], st));
+    b->timer.end(st);
     b->cur ^= 1;
     b->launches += 2;
     return 0;
@@ -165,6 +173,26 @@ int ekfvio_batch_accumulate_errors(ekfvio_batch* b, const double* d_truth_mu, do
     CU(cudaSetDevice(b->device));
     CU(launch_accumulate_errors(ptrs(b), d_truth_mu, d_acc, (cudaStream_t)stream));
     b->launches += 1;
+    return 0;
+}
+
+int ekfvio_batch_enable_timing(ekfvio_batch* b, int on) {
+    CU(cudaSetDevice(b->device));
+    b->timer.reset();
+    b->timer.on = on != 0;
+    return 0;
+}
+
+int ekfvio_batch_get_timing(ekfvio_batch* b, double* ms8, long long* count8) {
+    CU(cudaSetDevice(b->device));
+    b->timer.resolve();
+    for (int i = 0; i < KernelTimer::SLOTS; ++i) { if (ms8) ms8[i] = b->timer.ms[i]; if (count8) count8[i] = b->timer.cnt[i]; }
+    return 0;
+}
+
+int ekfvio_measure_fp64_peak(int device, double* dmma_tflops, double* dfma_tflops) {
+    CU(cudaSetDevice(device));
+    CU(measure_fp64_peak(dmma_tflops, dfma_tflops));
     return 0;
 }
 

@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include "../../include/ekfvio_c.h"
+#include "timing.h"
 
 namespace ekfvio {
 
@@ -145,4 +146,5 @@ struct ekfvio_batch {
     double* dd_z = nullptr; double* dd_R = nullptr; uint8_t* dd_pass = nullptr;
     double* h_out = nullptr;
     long long launches = 0;
+    KernelTimer timer;
 };

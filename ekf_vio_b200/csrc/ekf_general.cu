@@ -564,8 +564,8 @@ size_t gain_general_smem_doubles(int mmax) {
     return (need * sizeof(double) <= 200 * 1024) ? need : 0;
 }
 
-cudaError_t launch_update_general(const EkfPtrs& p, const double* Pin, double* Pout, const double* z, const double* R, const uint8_t* pass,
-                                  double* Sg, cudaStream_t st) {
+cudaError_t launch_gain_general(const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, double* Sg,
+                                cudaStream_t st) {
     size_t sm = p.gain_smem_doubles * sizeof(double);
     static size_t configured = 0;
     if (sm > 48 * 1024 && sm > configured) {
@@ -574,8 +574,10 @@ cudaError_t launch_update_general(const EkfPtrs& p, const double* Pin, double* P
         configured = sm;
     }
     ekf_gain_general<<<p.F, PT, sm, st>>>(p, Pin, z, R, pass, Sg);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_joseph_general(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st) {
     int tiles = (p.Nmax + 31) / 32;
     dim3 grid(tiles, tiles, p.F);
     ekf_joseph_general<<<grid, 256, 0, st>>>(p, Pin, Pout);

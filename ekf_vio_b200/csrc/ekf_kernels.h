@@ -18,8 +18,9 @@ struct EkfPtrs {
 
 // general path (ekf_general.cu)
 cudaError_t launch_process_general(const EkfPtrs& p, const double* Pin, double* Pout, const double* dts, int mode, double* F_out, cudaStream_t st);
-cudaError_t launch_update_general(const EkfPtrs& p, const double* Pin, double* Pout, const double* z, const double* R, const uint8_t* pass,
-                                  double* Sg, cudaStream_t st);
+cudaError_t launch_gain_general(const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, double* Sg,
+                                cudaStream_t st);
+cudaError_t launch_joseph_general(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st);
 size_t gain_general_smem_doubles(int mmax);
 cudaError_t launch_reset(const EkfPtrs& p, double* P0, cudaStream_t st);
 cudaError_t launch_add_features(const EkfPtrs& p, double* P0, const int* ks, const double* uv, int kmax, cudaStream_t st);
@@ -27,5 +28,8 @@ cudaError_t launch_check_sigma(const EkfPtrs& p, const double* P0, int* neg, dou
 cudaError_t launch_fill_dt(double* dts, double dt, int F, cudaStream_t st);
 cudaError_t launch_pack_P(const double* P0, double* dense, int ld, int Nmax, int F, int to_dense, cudaStream_t st);
 cudaError_t launch_accumulate_errors(const EkfPtrs& p, const double* truth, double* acc, cudaStream_t st);
+
+// FP64 peak probe (fp64_peak.cu)
+cudaError_t measure_fp64_peak(double* dmma_tflops, double* dfma_tflops);
 
 }  // namespace ekfvio

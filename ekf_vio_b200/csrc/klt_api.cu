@@ -93,6 +93,20 @@ int ekfvio_klt_create(ekfvio_klt** out, int device, int width, int height, int m
     return 0;
 }
 
+int ekfvio_klt_enable_timing(ekfvio_klt* k, int on) {
+    CU(cudaSetDevice(k->device));
+    k->timer.reset();
+    k->timer.on = on != 0;
+    return 0;
+}
+
+int ekfvio_klt_get_timing(ekfvio_klt* k, double* ms8, long long* count8) {
+    CU(cudaSetDevice(k->device));
+    k->timer.resolve();
+    for (int i = 0; i < KernelTimer::SLOTS; ++i) { if (ms8) ms8[i] = k->timer.ms[i]; if (count8) count8[i] = k->timer.cnt[i]; }
+    return 0;
+}
+
 int ekfvio_klt_num_levels(const ekfvio_klt* k) { return k ? k->pyr.levels : 0; }
 long long ekfvio_klt_launch_count(const ekfvio_klt* k) { return k ? k->launches : 0; }
 
@@ -112,8 +126,10 @@ int ekfvio_klt_build_pyramid(ekfvio_klt* k, int slot, const uint8_t* d_imgs, int
         uint8_t* down = nullptr; int npitch = 0; size_t nstride = 0;
         if (l + 1 < P.levels) { down = base + P.lv[l + 1].img_off; npitch = P.lv[l + 1].pitch; nstride = P.lv[l + 1].img_stride; }
         if (!copy_dst && !der && !down) continue;
+        k->timer.begin(l < 3 ? l : 3, st);
         CU(launch_level(src, spitch, sstride, L.w, L.h, copy_dst, L.pitch, L.img_stride, der, L.dpitch, L.der_stride / sizeof(short2), down,
                         npitch, nstride, batch, st));
+        k->timer.end(st);
         k->launches += 1;
     }
     k->slot_has_derivs[slot] = with_derivs != 0;
@@ -127,8 +143,10 @@ int ekfvio_klt_track(ekfvio_klt* k, int prev_slot, int next_slot, const float* d
     if (!k->slot_has_derivs[prev_slot]) return fail_msg("ekfvio_klt_track: prev slot was built without derivatives");
     if (batch <= 0 || batch > k->slot_batch[prev_slot] || batch > k->slot_batch[next_slot]) return fail_msg("ekfvio_klt_track: batch exceeds the built pyramids");
     CU(cudaSetDevice(k->device));
+    k->timer.begin(4, (cudaStream_t)stream);
     CU(launch_track(k->pyr, k->d_slots + (size_t)prev_slot * k->slot_bytes, k->d_slots + (size_t)next_slot * k->slot_bytes, d_prev_pts, d_next_pts,
                     d_status, d_err, d_npts, k->max_points, batch, k->prm, (cudaStream_t)stream));
+    k->timer.end((cudaStream_t)stream);
     k->launches += 1;
     return 0;
 }

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include "../../include/ekfvio_c.h"
+#include "timing.h"
 
 #define KLT_MAX_LEVELS 8
 
@@ -52,4 +53,5 @@ struct ekfvio_klt {
     uint8_t* h_img = nullptr;         // pinned: 2 * max_batch * height * level0 pitch
     float* h_pts = nullptr;           // pinned: max_batch*max_points*(2+2+1) floats + status bytes
     long long launches = 0;
+    KernelTimer timer;
 };

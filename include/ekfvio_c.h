@@ -125,6 +125,16 @@ int ekfvio_batch_get_view(ekfvio_batch* b, ekfvio_batch_view* view);
 /* Number of kernel launches this library has issued on behalf of `b` since creation. */
 long long ekfvio_batch_launch_count(const ekfvio_batch* b);
 
+/* Per-kernel device timing (CUDA events on the launching stream) for the roofline report.
+ * Slots: 0 process, 1 gain (S, factorisation, K, W, state), 2 covariance (Joseph) update.
+ * get_timing synchronises, then returns accumulated milliseconds and launch counts (8 slots). */
+int ekfvio_batch_enable_timing(ekfvio_batch* b, int on);
+int ekfvio_batch_get_timing(ekfvio_batch* b, double* ms8, long long* count8);
+
+/* Measures this GPU's FP64 peak with register-resident loops (about 50 ms each): the
+ * DMMA.8x8x4 rate and the DFMA rate, in TFLOP/s.  The roofline denominator for the EKF. */
+int ekfvio_measure_fp64_peak(int device, double* dmma_tflops, double* dfma_tflops);
+
 /* Monte-Carlo error statistics (no reference counterpart; north_star): per-filter squared
  * position / velocity error against ground truth accumulated on device into d_acc[8] =
  * {sum_e2_pos, sum_e2_vel, sum_e2_quat, count, max_e2_pos, 0, 0, 0}; the caller reduces d_acc
@@ -185,6 +195,10 @@ int ekfvio_klt_track_pair_h(ekfvio_klt* k, const uint8_t* h_prev, const uint8_t*
 int ekfvio_klt_read_level(ekfvio_klt* k, int slot, int img, int level, uint8_t* h_img, int16_t* h_deriv, int* w_out, int* h_out);
 
 long long ekfvio_klt_launch_count(const ekfvio_klt* k);
+/* Timing slots: 0..3 pyramid/Scharr kernel of level 0..3 (slot 3 also collects deeper levels),
+ * 4 track kernel, 5 post-process. */
+int ekfvio_klt_enable_timing(ekfvio_klt* k, int on);
+int ekfvio_klt_get_timing(ekfvio_klt* k, double* ms8, long long* count8);
 
 #ifdef __cplusplus
 }
