@@ -152,10 +152,18 @@ int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, c
     CU(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
     b->timer.begin(1, st);
-    CU(launch_gain_general(ptrs(b), b->d_P[b->cur], d_z, d_R, d_pass, b->d_S, st));
+    {
+        EkfPtrs pp = ptrs(b);
+        if (!(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | 0x100u)) && gain_tiled_supported(pp)) CU(launch_gain_tiled(pp, b->d_P[b->cur], d_z, d_R, d_pass, st));
+        else CU(launch_gain_general(pp, b->d_P[b->cur], d_z, d_R, d_pass, b->d_S, st));
+    }
     b->timer.end(st);
     b->timer.begin(2, st);
-    CU(launch_joseph_general(ptrs(b), b->d_P[b->cur], b->d_P[b->cur ^ 1], st));
+    {
+        EkfPtrs pp = ptrs(b);
+        if (!(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | 0x200u)) && joseph_tiled_supported(pp)) CU(launch_joseph_tiled(pp, b->d_P[b->cur], b->d_P[b->cur ^ 1], st));
+        else CU(launch_joseph_general(pp, b->d_P[b->cur], b->d_P[b->cur ^ 1], st));
+    }
     b->timer.end(st);
     b->cur ^= 1;
     b->launches += 2;

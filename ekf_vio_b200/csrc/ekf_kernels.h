@@ -29,6 +29,12 @@ cudaError_t launch_fill_dt(double* dts, double dt, int F, cudaStream_t st);
 cudaError_t launch_pack_P(const double* P0, double* dense, int ld, int Nmax, int F, int to_dense, cudaStream_t st);
 cudaError_t launch_accumulate_errors(const EkfPtrs& p, const double* truth, double* acc, cudaStream_t st);
 
+// tiled DMMA fast path (ekf_tiled.cu)
+bool joseph_tiled_supported(const EkfPtrs& p);
+bool gain_tiled_supported(const EkfPtrs& p);
+cudaError_t launch_gain_tiled(const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, cudaStream_t st);
+cudaError_t launch_joseph_tiled(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st);
+
 // FP64 peak probe (fp64_peak.cu)
 cudaError_t measure_fp64_peak(double* dmma_tflops, double* dfma_tflops);
 

@@ -1,0 +1,518 @@
+// Tiled FP64 tensor-core (DMMA.8x8x4) kernels for the EKF measurement update on sm_100a — the
+// fast path for feature-augmented states up to N = 22 + 3n <= 256.
+//
+//   ekf_joseph_tiled : Sigma' = Sigma - K Sigma(idx,:) - W K'     (TightlyCoupledEKF.cpp:586-596,
+//                      625 in selection form; W = Sigma(:,idx) - K S is the Joseph residual panel)
+//
+// One CTA per filter, one warp per 16-row strip of Sigma'; the strip's accumulators stay in
+// registers (2 x 11 DMMA tiles per pass), the B operands stream through shared memory in 8-deep
+// k-chunks with cp.async double buffering, the A operands come straight from global memory one
+// chunk ahead.  Shared-memory leading dimensions are == 4 (mod 8) doubles so every fragment load
+// is bank-conflict free.
+#include "ekf_common.cuh"
+#include "ekf_kernels.h"
+
+using namespace ekfvio;
+
+namespace {
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int JT = 11;              // column tiles per pass
+constexpr int KC = 8;               // k-chunk depth
+constexpr int LDG = JT * 8 + 4;     // G-phase chunk: [KC][LDG]
+constexpr int LDK = 12;             // K-phase chunk: [JT*8][LDK]
+constexpr int BS_DOUBLES = (JT * 8 * LDK > KC * LDG) ? JT * 8 * LDK : KC * LDG;
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const double* __restrict__ Pin, double* __restrict__ Pout) {
+    __shared__ __align__(16) double Bs[2][BS_DOUBLES];
+    __shared__ int s_idx[256];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = p.nfeat[f], N = BASE + 3 * n, m = p.m[f];
+    const int ld = p.ldP, ldK = p.ldK;
+    const double* Pi = Pin + (size_t)f * ld * ld;
+    double* Po = Pout + (size_t)f * ld * ld;
+    const double* Kf = p.K + (size_t)f * ld * ldK;
+    const double* Wf = p.W + (size_t)f * ld * ldK;
+    const int* idx = p.idx + (size_t)f * p.mmax;
+    for (int i = tid; i < m; i += NW * 32) s_idx[i] = idx[i];
+    __syncthreads();
+
+    const int r = lane >> 2, q = lane & 3;
+    const int i0 = warp * 16;
+    const bool active = i0 < N;
+    const int nct = (N + 7) >> 3, npass = (nct + JT - 1) / JT, nch = (m + KC - 1) / KC;
+
+    for (int pass = 0; pass < npass; ++pass) {
+        const int j0 = pass * JT * 8;
+        double c0[2][JT], c1[2][JT];
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+            for (int t = 0; t < JT; ++t) {
+                int row = i0 + rt * 8 + r, col = j0 + t * 8 + 2 * q;
+                double2 v = make_double2(0.0, 0.0);
+                if (active && row < ld && col < ld) v = *reinterpret_cast<const double2*>(Pi + (size_t)row * ld + col);
+                c0[rt][t] = v.x; c1[rt][t] = v.y;
+            }
+        for (int phase = 0; phase < 2; ++phase) {
+            const double* Am = phase == 0 ? Kf : Wf;
+            auto stage = [&](int c, int buf) {
+                const int k0 = c * KC;
+                if (phase == 0) {   // rows idx[k] of Sigma, columns j0 .. j0 + 87
+                    for (int t = tid; t < KC * (JT * 4); t += NW * 32) {
+                        int k = t / (JT * 4), seg = t % (JT * 4);
+                        double* dst = &Bs[buf][k * LDG + seg * 2];
+                        int col = j0 + seg * 2;
+                        if (k0 + k < m && col < ld) cp_async16(dst, Pi + (size_t)s_idx[k0 + k] * ld + col);
+                        else { dst[0] = 0.0; dst[1] = 0.0; }
+                    }
+                } else {            // rows j0 .. j0 + 87 of K, columns k0 .. k0 + 7
+                    for (int t = tid; t < JT * 8 * 4; t += NW * 32) {
+                        int col = t >> 2, seg = t & 3;
+                        double* dst = &Bs[buf][col * LDK + seg * 2];
+                        if (j0 + col < ld) cp_async16(dst, Kf + (size_t)(j0 + col) * ldK + k0 + seg * 2);
+                        else { dst[0] = 0.0; dst[1] = 0.0; }
+                    }
+                }
+                cp_async_commit();
+            };
+            auto load_a = [&](int c, double (&a)[2][2]) {
+                const int k0 = c * KC;
+#pragma unroll
+                for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        int row = i0 + rt * 8 + r;
+                        a[rt][kk] = (active && row < ld) ? -Am[(size_t)row * ldK + k0 + kk * 4 + q] : 0.0;
+                    }
+            };
+            double a_cur[2][2], a_nxt[2][2] = {{0, 0}, {0, 0}};
+            if (nch > 0) { stage(0, 0); load_a(0, a_cur); }
+            for (int c = 0; c < nch; ++c) {
+                const int buf = c & 1;
+                if (c + 1 < nch) { stage(c + 1, buf ^ 1); load_a(c + 1, a_nxt); cp_async_wait<1>(); }
+                else cp_async_wait<0>();
+                __syncthreads();
+                if (active) {
+                    const double* B = Bs[buf];
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+                        for (int t = 0; t < JT; ++t) {
+                            double b = (phase == 0) ? B[(kk * 4 + q) * LDG + t * 8 + r] : B[(t * 8 + r) * LDK + kk * 4 + q];
+                            dmma884(c0[0][t], c1[0][t], a_cur[0][kk], b);
+                            dmma884(c0[1][t], c1[1][t], a_cur[1][kk], b);
+                        }
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) a_cur[rt][kk] = a_nxt[rt][kk];
+            }
+        }
+        if (active) {
+#pragma unroll
+            for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+                for (int t = 0; t < JT; ++t) {
+                    int row = i0 + rt * 8 + r, col = j0 + t * 8 + 2 * q;
+                    if (row < N) {
+                        double* o = Po + (size_t)row * ld + col;
+                        if (col + 1 < N) *reinterpret_cast<double2*>(o) = make_double2(prune(c0[rt][t]), prune(c1[rt][t]));
+                        else if (col < N) o[0] = prune(c0[rt][t]);
+                    }
+                }
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// ekf_gain_tiled: measurement map, residual, S, Cholesky, K, W, state update — the DMMA version
+// of ekf_gain_general (TightlyCoupledEKF.cpp:475-580, 600-620).
+//
+// S (m x m, padded to 8*nb with an identity tail) lives in shared memory as 8x8 tiles, twice: Ss,
+// the full S kept for W = Sigma(:,idx) - K S (no symmetry assumed: the Joseph form only cancels
+// rounding errors of K if W is the residual against the very S that Sigma(idx,:) and Sigma(:,idx)
+// define), and Ls, the lower triangle taken from upper(S) as the reference's LDLT does, factored
+// in place (L L' = S).
+// Tile element (r, c) sits at r*8 + (c ^ 4*((r>>1)&1)) so that both the row-fragment access
+// (lane -> [lane/4][lane%4 + 4kk]) and the column-fragment access ([lane%4 + 4kk][lane/4]) hit 16
+// distinct banks per half-warp.  Each warp then owns a 16-row strip of Sigma(:,idx) and carries it
+// through both triangular solves entirely in registers (right-looking, 8-wide column blocks,
+// diagonal blocks applied through their explicit 8x8 inverses).
+__device__ __forceinline__ int tsw(int r, int c) { return r * 8 + (c ^ (((r >> 1) & 1) << 2)); }
+__device__ __forceinline__ int tile_of(int ib, int jb) { return (ib * (ib + 1) / 2 + jb) * 64; }
+
+// C-fragment (row = lane/4, cols 2q,2q+1) -> the two A-fragments (row = lane/4, k = q + 4kk)
+__device__ __forceinline__ void cfrag_to_afrag(double c0, double c1, int lane, double& a0, double& a1) {
+    const int q = lane & 3, base = lane & ~3;
+    double v0 = __shfl_sync(0xffffffffu, c0, base | (q >> 1));
+    double v1 = __shfl_sync(0xffffffffu, c1, base | (q >> 1));
+    a0 = (q & 1) ? v1 : v0;
+    v0 = __shfl_sync(0xffffffffu, c0, base | 2 | (q >> 1));
+    v1 = __shfl_sync(0xffffffffu, c1, base | 2 | (q >> 1));
+    a1 = (q & 1) ? v1 : v0;
+}
+
+template <int NW, int NB>
+__global__ void __launch_bounds__(NW * 32, 1) ekf_gain_tiled(EkfPtrs p, const double* __restrict__ Pin, const double* __restrict__ z,
+                                                             const double* __restrict__ Rin, const uint8_t* __restrict__ pass) {
+    extern __shared__ __align__(16) double smg[];
+    constexpr int NT = NB * (NB + 1) / 2;
+    double* Ls = smg;                      // NT tiles
+    double* Ss = Ls + NT * 64;             // NB*NB tiles: the full (possibly asymmetric) S
+    double* Li = Ss + NB * NB * 64;        // NB inverse diagonal tiles
+    double* s_y = Li + NB * 64;            // NB*8
+    int* s_idx = reinterpret_cast<int*>(s_y + NB * 8);   // NB*8
+    __shared__ int s_m, s_bad;
+
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = p.nfeat[f], N = BASE + 3 * n;
+    const int ld = p.ldP, ldK = p.ldK, nmax = p.nmax;
+    const double* Pi = Pin + (size_t)f * ld * ld;
+    const double* zf = z + (size_t)f * nmax * 2;
+    const double* Rf = Rin + (size_t)f * nmax * 4;
+    const uint8_t* pf = pass + (size_t)f * nmax;
+    double* Kf = p.K + (size_t)f * ld * ldK;
+    double* Wf = p.W + (size_t)f * ld * ldK;
+    double* mu_g = p.mu + (size_t)f * BASE;
+    double* feat_g = p.feat + (size_t)f * nmax * 3;
+    int* idx_g = p.idx + (size_t)f * p.mmax;
+
+    if (tid == 0) {  // formFeatureMeasurementMap (:634-661) + bookkeeping of :506-529
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            if (pf[i]) {
+                s_idx[m] = BASE + 3 * i; s_idx[m + 1] = BASE + 3 * i + 1;
+                idx_g[m] = BASE + 3 * i; idx_g[m + 1] = BASE + 3 * i + 1;
+                s_y[m] = zf[2 * i] - feat_g[3 * i];
+                s_y[m + 1] = zf[2 * i + 1] - feat_g[3 * i + 1];
+                p.klt_last[((size_t)f * nmax + i) * 2] = zf[2 * i];
+                p.klt_last[((size_t)f * nmax + i) * 2 + 1] = zf[2 * i + 1];
+                m += 2;
+            } else {
+                p.dflags[(size_t)f * nmax + i] = 1;
+            }
+        }
+        for (int a = m; a < NB * 8; ++a) { s_idx[a] = 0; s_y[a] = 0.0; }
+        s_m = m; s_bad = 0;
+        p.m[f] = m;
+    }
+    __syncthreads();
+    const int m = s_m;
+    if (m == 0) {
+        if (tid == 0) {
+            double qn = sqrt(mu_g[3] * mu_g[3] + mu_g[4] * mu_g[4] + mu_g[5] * mu_g[5] + mu_g[6] * mu_g[6]);
+            mu_g[3] /= qn; mu_g[4] /= qn; mu_g[5] /= qn; mu_g[6] /= qn;
+        }
+        return;
+    }
+    const int nb = (m + 7) >> 3;
+    const int r = lane >> 2, q = lane & 3;
+
+    // ---- Ss: full S = Sigma(idx,idx) + R as NB x NB tiles (identity tail); no symmetry assumed
+    for (int e = tid; e < nb * nb * 64; e += NW * 32) {
+        int t = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
+        int ta = t / nb, tb = t - ta * nb;
+        int a = ta * 8 + rr, b = tb * 8 + cc;
+        double v;
+        if (a < m && b < m) {
+            v = Pi[(size_t)s_idx[a] * ld + s_idx[b]];
+            if ((a >> 1) == (b >> 1)) v += Rf[4 * ((s_idx[a] - BASE) / 3) + (a & 1) * 2 + (b & 1)];
+        } else {
+            v = (a == b) ? 1.0 : 0.0;
+        }
+        Ss[(ta * NB + tb) * 64 + tsw(rr, cc)] = v;
+    }
+    __syncthreads();
+    // ---- Ls: lower(a,b), a >= b  <-  upper(S)(b,a)  (SimplicialLDLT::compute(S') reads upper(S), :578)
+    for (int e = tid; e < nb * (nb + 1) / 2 * 64; e += NW * 32) {
+        int t = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
+        int ib = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
+        while (ib * (ib + 1) / 2 > t) --ib;
+        while ((ib + 1) * (ib + 2) / 2 <= t) ++ib;
+        int jb = t - ib * (ib + 1) / 2;
+        Ls[t * 64 + tsw(rr, cc)] = Ss[(jb * NB + ib) * 64 + tsw(cc, rr)];
+    }
+    __syncthreads();
+
+    // ---- blocked right-looking Cholesky of Ls, 8x8 tiles
+    for (int jb = 0; jb < nb; ++jb) {
+        if (warp == 0) {   // diagonal tile: lane rr (< 8) owns row rr
+            double* T = Ls + tile_of(jb, jb);
+            const int rr = lane & 7;
+            double a[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a[c] = T[tsw(rr, c)];
+            bool bad = false;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                double dcc = __shfl_sync(0xffffffffu, a[c], c);
+                if (!(dcc > 0.0)) bad = true;
+                double piv = sqrt(dcc);
+                if (rr == c) a[c] = piv; else if (rr > c) a[c] = a[c] / piv;
+#pragma unroll
+                for (int c2 = c + 1; c2 < 8; ++c2) {
+                    double l = __shfl_sync(0xffffffffu, a[c], c2);
+                    if (rr >= c2) a[c2] -= a[c] * l;
+                }
+            }
+            // column j = rr of inv(L): forward substitution with rows fetched by shuffle
+            double x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                double sacc = (i == rr) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < i; ++k) sacc -= __shfl_sync(0xffffffffu, a[k], i) * x[k];
+                x[i] = sacc / __shfl_sync(0xffffffffu, a[i], i);
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) T[tsw(rr, c)] = (c <= rr) ? a[c] : 0.0;
+                double* I8 = Li + jb * 64;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) I8[tsw(i, rr)] = (i >= rr) ? x[i] : 0.0;
+                if (bad && lane == 0) s_bad = 1;
+            }
+        }
+        __syncthreads();
+        // panel: L(ib,jb) = A(ib,jb) * inv(Ljj)'
+        {
+            const double* I8 = Li + jb * 64;
+            double b0 = I8[tsw(r, q)], b1 = I8[tsw(r, 4 + q)];
+            for (int ib = jb + 1 + warp; ib < nb; ib += NW) {
+                double* T = Ls + tile_of(ib, jb);
+                double a0 = T[tsw(r, q)], a1 = T[tsw(r, 4 + q)];
+                double c0 = 0.0, c1 = 0.0;
+                dmma884(c0, c1, a0, b0);
+                dmma884(c0, c1, a1, b1);
+                __syncwarp();
+                *reinterpret_cast<double2*>(&T[tsw(r, 2 * q)]) = make_double2(c0, c1);
+            }
+        }
+        __syncthreads();
+        // trailing update: A(ib,kb) -= L(ib,jb) L(kb,jb)'  for ib >= kb > jb
+        {
+            const int t = nb - 1 - jb;
+            for (int e = warp; e < t * (t + 1) / 2; e += NW) {
+                int ii = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
+                while (ii * (ii + 1) / 2 > e) --ii;
+                while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
+                int kk2 = e - ii * (ii + 1) / 2;
+                int ib = jb + 1 + ii, kb = jb + 1 + kk2;
+                const double* TA = Ls + tile_of(ib, jb);
+                const double* TB = Ls + tile_of(kb, jb);
+                double* TC = Ls + tile_of(ib, kb);
+                double2 c = *reinterpret_cast<double2*>(&TC[tsw(r, 2 * q)]);
+                dmma884(c.x, c.y, -TA[tsw(r, q)], TB[tsw(r, q)]);
+                dmma884(c.x, c.y, -TA[tsw(r, 4 + q)], TB[tsw(r, 4 + q)]);
+                *reinterpret_cast<double2*>(&TC[tsw(r, 2 * q)]) = c;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && s_bad) atomicOr(&p.status[f], 1);
+
+    // ---- per-warp 16-row strips: K = Sigma(:,idx) inv(L)' inv(L), all in registers
+    const int i0 = warp * 16;
+    if (i0 < N) {
+        double k0[2][NB], k1[2][NB];
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt) {
+            const int row = i0 + rt * 8 + r;
+#pragma unroll
+            for (int jb = 0; jb < NB; ++jb) {
+                int a = jb * 8 + 2 * q;
+                bool ok = row < N && a < m && jb < nb;
+                k0[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a]] : 0.0;
+                k1[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a + 1]] : 0.0;
+            }
+        }
+        // forward: Z L' = C
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) {
+            if (jb < nb) {
+                const double* I8 = Li + jb * 64;
+                const double b0 = I8[tsw(r, q)], b1 = I8[tsw(r, 4 + q)];   // B[k][col] = inv(L)[col][k]
+                double za[2][2];
+#pragma unroll
+                for (int rt = 0; rt < 2; ++rt) {
+                    double a0, a1;
+                    cfrag_to_afrag(k0[rt][jb], k1[rt][jb], lane, a0, a1);
+                    double t0 = 0.0, t1 = 0.0;
+                    dmma884(t0, t1, a0, b0);
+                    dmma884(t0, t1, a1, b1);
+                    k0[rt][jb] = t0; k1[rt][jb] = t1;
+                    cfrag_to_afrag(t0, t1, lane, a0, a1);
+                    za[rt][0] = -a0; za[rt][1] = -a1;
+                }
+#pragma unroll
+                for (int j2 = 0; j2 < NB; ++j2) {
+                    if (j2 > jb && j2 < nb) {
+                        const double* T = Ls + tile_of(j2, jb);          // B[k][col] = L(j2,jb)[col][k]
+                        const double l0 = T[tsw(r, q)], l1 = T[tsw(r, 4 + q)];
+#pragma unroll
+                        for (int rt = 0; rt < 2; ++rt) {
+                            dmma884(k0[rt][j2], k1[rt][j2], za[rt][0], l0);
+                            dmma884(k0[rt][j2], k1[rt][j2], za[rt][1], l1);
+                        }
+                    }
+                }
+            }
+        }
+        // backward: K L = Z
+#pragma unroll
+        for (int jr = 0; jr < NB; ++jr) {
+            const int jb = NB - 1 - jr;
+            if (jb < nb) {
+                const double* I8 = Li + jb * 64;
+                const double b0 = I8[tsw(q, r)], b1 = I8[tsw(4 + q, r)];   // B[k][col] = inv(L)[k][col]
+                double ka[2][2];
+#pragma unroll
+                for (int rt = 0; rt < 2; ++rt) {
+                    double a0, a1;
+                    cfrag_to_afrag(k0[rt][jb], k1[rt][jb], lane, a0, a1);
+                    double t0 = 0.0, t1 = 0.0;
+                    dmma884(t0, t1, a0, b0);
+                    dmma884(t0, t1, a1, b1);
+                    k0[rt][jb] = t0; k1[rt][jb] = t1;
+                    cfrag_to_afrag(t0, t1, lane, a0, a1);
+                    ka[rt][0] = -a0; ka[rt][1] = -a1;
+                }
+#pragma unroll
+                for (int j2 = 0; j2 < NB; ++j2) {
+                    if (j2 < jb) {
+                        const double* T = Ls + tile_of(jb, j2);              // B[k][col] = L(jb,j2)[k][col]
+                        const double l0 = T[tsw(q, r)], l1 = T[tsw(4 + q, r)];
+#pragma unroll
+                        for (int rt = 0; rt < 2; ++rt) {
+                            dmma884(k0[rt][j2], k1[rt][j2], ka[rt][0], l0);
+                            dmma884(k0[rt][j2], k1[rt][j2], ka[rt][1], l1);
+                        }
+                    }
+                }
+            }
+        }
+        // sparseView (:580), mu += K y (:600), K to global
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt) {
+            const int row = i0 + rt * 8 + r;
+            double dot = 0.0;
+#pragma unroll
+            for (int jb = 0; jb < NB; ++jb) {
+                if (jb < nb) {
+                    double a = prune(k0[rt][jb]), b = prune(k1[rt][jb]);
+                    k0[rt][jb] = a; k1[rt][jb] = b;
+                    dot += a * s_y[jb * 8 + 2 * q] + b * s_y[jb * 8 + 2 * q + 1];
+                    if (row < ld) *reinterpret_cast<double2*>(Kf + (size_t)row * ldK + jb * 8 + 2 * q) = make_double2(a, b);
+                }
+            }
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            if (q == 0 && row < N) { if (row < BASE) mu_g[row] += dot; else feat_g[row - BASE] += dot; }
+        }
+        __syncwarp();
+        // W = Sigma(:,idx) - K S  (S = Ss, symmetric from upper(S)) - K E  (E: asymmetric part of the R blocks)
+        double w0[2][NB], w1[2][NB];
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt) {
+            const int row = i0 + rt * 8 + r;
+#pragma unroll
+            for (int jb = 0; jb < NB; ++jb) {
+                int a = jb * 8 + 2 * q;
+                bool ok = row < N && a < m && jb < nb;
+                double c0 = ok ? Pi[(size_t)row * ld + s_idx[a]] : 0.0;
+                double c1 = ok ? Pi[(size_t)row * ld + s_idx[a + 1]] : 0.0;
+                w0[rt][jb] = c0;
+                w1[rt][jb] = c1;
+            }
+        }
+        for (int kb = 0; kb < nb; ++kb) {
+            double ka[2][2];
+#pragma unroll
+            for (int rt = 0; rt < 2; ++rt) {
+                const int row = i0 + rt * 8 + r;
+                const double* kr = Kf + (size_t)row * ldK + kb * 8 + q;
+                ka[rt][0] = row < ld ? -kr[0] : 0.0;
+                ka[rt][1] = row < ld ? -kr[4] : 0.0;
+            }
+#pragma unroll
+            for (int j2 = 0; j2 < NB; ++j2) {
+                if (j2 < nb) {
+                    const double* T = Ss + (kb * NB + j2) * 64;   // B[k][col] = S(kb*8+k, j2*8+col)
+                    const double s0 = T[tsw(q, r)], s1 = T[tsw(4 + q, r)];
+#pragma unroll
+                    for (int rt = 0; rt < 2; ++rt) {
+                        dmma884(w0[rt][j2], w1[rt][j2], ka[rt][0], s0);
+                        dmma884(w0[rt][j2], w1[rt][j2], ka[rt][1], s1);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt) {
+            const int row = i0 + rt * 8 + r;
+#pragma unroll
+            for (int jb = 0; jb < NB; ++jb)
+                if (jb < nb && row < ld) *reinterpret_cast<double2*>(Wf + (size_t)row * ldK + jb * 8 + 2 * q) = make_double2(w0[rt][jb], w1[rt][jb]);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {  // renormalise the quaternion (:605-609) and flag non-finite states
+        __threadfence_block();
+        double qn = sqrt(mu_g[3] * mu_g[3] + mu_g[4] * mu_g[4] + mu_g[5] * mu_g[5] + mu_g[6] * mu_g[6]);
+        mu_g[3] /= qn; mu_g[4] /= qn; mu_g[5] /= qn; mu_g[6] /= qn;
+        bool fin = true;
+        for (int i = 0; i < BASE; ++i) fin = fin && isfinite(mu_g[i]);
+        if (!fin) atomicOr(&p.status[f], 2);
+    }
+}
+
+template <int NW, int NB> size_t gain_tiled_smem() {
+    return (size_t)(NB * (NB + 1) / 2 * 64 + NB * NB * 64 + NB * 64 + NB * 8 + NB * 4) * sizeof(double) + NB * 8 * sizeof(int);
+}
+template <int NW, int NB>
+cudaError_t launch_gain_tiled_t(const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, cudaStream_t st) {
+    static bool configured = false;
+    size_t sm = gain_tiled_smem<NW, NB>();
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ekf_gain_tiled<NW, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    ekf_gain_tiled<NW, NB><<<p.F, NW * 32, sm, st>>>(p, Pin, z, R, pass);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+namespace ekfvio {
+
+bool joseph_tiled_supported(const EkfPtrs& p) { return p.Nmax <= 256 && p.mmax <= 256; }
+
+bool gain_tiled_supported(const EkfPtrs& p) { return p.Nmax <= 176 && p.mmax <= 104; }
+
+cudaError_t launch_gain_tiled(const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, cudaStream_t st) {
+    if (p.Nmax <= 128 && p.mmax <= 64) return launch_gain_tiled_t<8, 8>(p, Pin, z, R, pass, st);
+    return launch_gain_tiled_t<11, 13>(p, Pin, z, R, pass, st);
+}
+
+cudaError_t launch_joseph_tiled(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st) {
+    const int strips = (p.Nmax + 15) / 16;
+    if (strips <= 8) ekf_joseph_tiled<8><<<p.F, 8 * 32, 0, st>>>(p, Pin, Pout);
+    else if (strips <= 11) ekf_joseph_tiled<11><<<p.F, 11 * 32, 0, st>>>(p, Pin, Pout);
+    else ekf_joseph_tiled<16><<<p.F, 16 * 32, 0, st>>>(p, Pin, Pout);
+    return cudaGetLastError();
+}
+
+}  // namespace ekfvio
