@@ -24,7 +24,7 @@ int fail_msg(const std::string& msg) { g_last_error = msg; return 1; }
 static EkfPtrs ptrs(const ekfvio_batch* b) {
     EkfPtrs p;
     p.mu = b->d_mu; p.feat = b->d_feat; p.nfeat = b->d_nfeat; p.cache = b->d_cache; p.dflags = b->d_flags;
-    p.klt_last = b->d_klt_last; p.status = b->d_status; p.idx = b->d_idx; p.y = b->d_y; p.m = b->d_m; p.K = b->d_K; p.W = b->d_W;
+    p.klt_last = b->d_klt_last; p.status = b->d_status; p.idx = b->d_idx; p.y = b->d_y; p.m = b->d_m; p.K = b->d_K; p.W = b->d_W; p.L = b->d_L;
     p.F = b->F; p.nmax = b->nmax; p.Nmax = b->Nmax; p.ldP = b->ldP; p.ldK = b->ldK; p.mmax = b->mmax;
     p.flags = b->prm.flags;
     p.depth = b->prm.default_point_depth; p.depth_var = b->prm.default_point_depth_variance;
@@ -49,7 +49,7 @@ int ekfvio_batch_destroy(ekfvio_batch* b) {
     cudaSetDevice(b->device);
     cudaFree(b->d_mu); cudaFree(b->d_feat); cudaFree(b->d_P[0]); cudaFree(b->d_P[1]); cudaFree(b->d_nfeat); cudaFree(b->d_cache);
     cudaFree(b->d_flags); cudaFree(b->d_klt_last); cudaFree(b->d_status); cudaFree(b->d_dt); cudaFree(b->d_K); cudaFree(b->d_W);
-    cudaFree(b->d_S); cudaFree(b->d_y); cudaFree(b->d_idx); cudaFree(b->d_m); cudaFree(b->d_fjac);
+    cudaFree(b->d_S); cudaFree(b->d_L); cudaFree(b->d_y); cudaFree(b->d_idx); cudaFree(b->d_m); cudaFree(b->d_fjac);
     cudaFree(b->dd_z); cudaFree(b->dd_R); cudaFree(b->dd_pass);
     cudaFreeHost(b->h_z); cudaFreeHost(b->h_R); cudaFreeHost(b->h_pass); cudaFreeHost(b->h_out);
     delete b;
@@ -90,6 +90,7 @@ int ekfvio_batch_create(ekfvio_batch** out, int device, int num_filters, int max
     ALLOC(b->d_idx, F * b->mmax * sizeof(int));
     ALLOC(b->d_m, F * sizeof(int));
     if (gain_general_smem_doubles(b->mmax) == 0) ALLOC(b->d_S, F * ((size_t)b->mmax * b->mmax + b->mmax) * sizeof(double));
+    if (b->Nmax <= 176 && b->mmax <= 104) ALLOC(b->d_L, F * gain_tiled_scratch_doubles(b->mmax) * sizeof(double));
     ALLOC(b->dd_z, F * nm * 2 * sizeof(double));
     ALLOC(b->dd_R, F * nm * 4 * sizeof(double));
     ALLOC(b->dd_pass, F * nm);

@@ -137,6 +137,7 @@ struct ekfvio_batch {
     double* d_K = nullptr;         // [F][ldP][ldK]   gain
     double* d_W = nullptr;         // [F][ldP][ldK]   Joseph residual panel
     double* d_S = nullptr;         // [F][mmax][mmax] (general path only; lazily allocated)
+    double* d_L = nullptr;         // [F][tiles] Cholesky factor + inverse diagonal tiles (tiled path)
     double* d_y = nullptr;         // [F][mmax]
     int* d_idx = nullptr;          // [F][mmax]
     int* d_m = nullptr;            // [F]

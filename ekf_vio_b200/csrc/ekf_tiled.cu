@@ -24,14 +24,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 constexpr int JT = 11;              // column tiles per pass
-constexpr int KC = 8;               // k-chunk depth
+constexpr int KC = 16;              // k-chunk depth
+constexpr int NST = 3;              // cp.async stages
 constexpr int LDG = JT * 8 + 4;     // G-phase chunk: [KC][LDG]
-constexpr int LDK = 12;             // K-phase chunk: [JT*8][LDK]
+constexpr int LDK = KC + 4;         // K-phase chunk: [JT*8][LDK]
 constexpr int BS_DOUBLES = (JT * 8 * LDK > KC * LDG) ? JT * 8 * LDK : KC * LDG;
 
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const double* __restrict__ Pin, double* __restrict__ Pout) {
-    __shared__ __align__(16) double Bs[2][BS_DOUBLES];
+    extern __shared__ __align__(16) double Bs_all[];   // NST * BS_DOUBLES
     __shared__ int s_idx[256];
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = p.nfeat[f], N = BASE + 3 * n, m = p.m[f];
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const 
     const int i0 = warp * 16;
     const bool active = i0 < N;
     const int nct = (N + 7) >> 3, npass = (nct + JT - 1) / JT, nch = (m + KC - 1) / KC;
+    const int row0 = min(i0 + r, ld - 1), row1 = min(i0 + 8 + r, ld - 1);
 
     for (int pass = 0; pass < npass; ++pass) {
         const int j0 = pass * JT * 8;
@@ -56,68 +58,72 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const 
         for (int rt = 0; rt < 2; ++rt)
 #pragma unroll
             for (int t = 0; t < JT; ++t) {
-                int row = i0 + rt * 8 + r, col = j0 + t * 8 + 2 * q;
+                int row = rt ? row1 : row0, col = j0 + t * 8 + 2 * q;
                 double2 v = make_double2(0.0, 0.0);
-                if (active && row < ld && col < ld) v = *reinterpret_cast<const double2*>(Pi + (size_t)row * ld + col);
+                if (active && col < ld) v = *reinterpret_cast<const double2*>(Pi + (size_t)row * ld + col);
                 c0[rt][t] = v.x; c1[rt][t] = v.y;
             }
         for (int phase = 0; phase < 2; ++phase) {
             const double* Am = phase == 0 ? Kf : Wf;
-            auto stage = [&](int c, int buf) {
+            const double* A0 = Am + (size_t)row0 * ldK + q;
+            const double* A1 = Am + (size_t)row1 * ldK + q;
+            auto stage = [&](int c) {
+                double* B = Bs_all + (c % NST) * BS_DOUBLES;
                 const int k0 = c * KC;
-                if (phase == 0) {   // rows idx[k] of Sigma, columns j0 .. j0 + 87
-                    for (int t = tid; t < KC * (JT * 4); t += NW * 32) {
-                        int k = t / (JT * 4), seg = t % (JT * 4);
-                        double* dst = &Bs[buf][k * LDG + seg * 2];
-                        int col = j0 + seg * 2;
-                        if (k0 + k < m && col < ld) cp_async16(dst, Pi + (size_t)s_idx[k0 + k] * ld + col);
-                        else { dst[0] = 0.0; dst[1] = 0.0; }
-                    }
-                } else {            // rows j0 .. j0 + 87 of K, columns k0 .. k0 + 7
-                    for (int t = tid; t < JT * 8 * 4; t += NW * 32) {
-                        int col = t >> 2, seg = t & 3;
-                        double* dst = &Bs[buf][col * LDK + seg * 2];
-                        if (j0 + col < ld) cp_async16(dst, Kf + (size_t)(j0 + col) * ldK + k0 + seg * 2);
-                        else { dst[0] = 0.0; dst[1] = 0.0; }
-                    }
-                }
-                cp_async_commit();
-            };
-            auto load_a = [&](int c, double (&a)[2][2]) {
-                const int k0 = c * KC;
-#pragma unroll
-                for (int rt = 0; rt < 2; ++rt)
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        int row = i0 + rt * 8 + r;
-                        a[rt][kk] = (active && row < ld) ? -Am[(size_t)row * ldK + k0 + kk * 4 + q] : 0.0;
-                    }
-            };
-            double a_cur[2][2], a_nxt[2][2] = {{0, 0}, {0, 0}};
-            if (nch > 0) { stage(0, 0); load_a(0, a_cur); }
-            for (int c = 0; c < nch; ++c) {
-                const int buf = c & 1;
-                if (c + 1 < nch) { stage(c + 1, buf ^ 1); load_a(c + 1, a_nxt); cp_async_wait<1>(); }
-                else cp_async_wait<0>();
-                __syncthreads();
-                if (active) {
-                    const double* B = Bs[buf];
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-#pragma unroll
-                        for (int t = 0; t < JT; ++t) {
-                            double b = (phase == 0) ? B[(kk * 4 + q) * LDG + t * 8 + r] : B[(t * 8 + r) * LDK + kk * 4 + q];
-                            dmma884(c0[0][t], c1[0][t], a_cur[0][kk], b);
-                            dmma884(c0[1][t], c1[1][t], a_cur[1][kk], b);
+                if (c < nch) {
+                    if (phase == 0) {   // rows idx[k] of Sigma, columns j0 .. j0 + 87
+                        for (int t = tid; t < KC * (JT * 4); t += NW * 32) {
+                            int k = t / (JT * 4), seg = t % (JT * 4);
+                            double* dst = &B[k * LDG + seg * 2];
+                            int col = j0 + seg * 2;
+                            if (k0 + k < m && col < ld) cp_async16(dst, Pi + (size_t)s_idx[k0 + k] * ld + col);
+                            else { dst[0] = 0.0; dst[1] = 0.0; }
+                        }
+                    } else {            // rows j0 .. j0 + 87 of K, columns k0 .. k0 + KC-1
+                        for (int t = tid; t < JT * 8 * (KC / 2); t += NW * 32) {
+                            int col = t / (KC / 2), seg = t % (KC / 2);
+                            double* dst = &B[col * LDK + seg * 2];
+                            if (j0 + col < ld && k0 + seg * 2 < m) cp_async16(dst, Kf + (size_t)(j0 + col) * ldK + k0 + seg * 2);   // m is even; k >= m must read as zero
+                            else { dst[0] = 0.0; dst[1] = 0.0; }
                         }
                     }
                 }
-                __syncthreads();
+                cp_async_commit();   // one group per stage call, possibly empty: keeps the wait count uniform
+            };
+            auto load_a = [&](int c, double (&a)[2][KC / 4]) {
+                const int k0 = c * KC;
 #pragma unroll
-                for (int rt = 0; rt < 2; ++rt)
+                for (int kk = 0; kk < KC / 4; ++kk) {
+                    bool ok = active && c < nch && k0 + kk * 4 + q < ldK;
+                    a[0][kk] = ok ? A0[k0 + kk * 4] : 0.0;
+                    a[1][kk] = ok ? A1[k0 + kk * 4] : 0.0;
+                }
+            };
+            double a_cur[2][KC / 4], a_nxt[2][KC / 4];
+            stage(0); stage(1);
+            load_a(0, a_cur);
+            for (int c = 0; c < nch; ++c) {
+                cp_async_wait<NST - 2>();      // chunk c has landed (one younger group may be in flight)
+                __syncthreads();               // ... for everyone, and everyone is done with chunk c-1
+                stage(c + 2);                  // refills the buffer chunk c-1 used
+                load_a(c + 1, a_nxt);
+                if (active) {
+                    const double* B = Bs_all + (c % NST) * BS_DOUBLES;
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) a_cur[rt][kk] = a_nxt[rt][kk];
+                    for (int kk = 0; kk < KC / 4; ++kk) {
+#pragma unroll
+                        for (int t = 0; t < JT; ++t) {
+                            double b = (phase == 0) ? B[(kk * 4 + q) * LDG + t * 8 + r] : B[(t * 8 + r) * LDK + kk * 4 + q];
+                            dmma884(c0[0][t], c1[0][t], -a_cur[0][kk], b);
+                            dmma884(c0[1][t], c1[1][t], -a_cur[1][kk], b);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int kk = 0; kk < KC / 4; ++kk) { a_cur[0][kk] = a_nxt[0][kk]; a_cur[1][kk] = a_nxt[1][kk]; }
             }
+            cp_async_wait<0>();
+            __syncthreads();
         }
         if (active) {
 #pragma unroll
@@ -164,54 +170,60 @@ __device__ __forceinline__ void cfrag_to_afrag(double c0, double c1, int lane, d
     a1 = (q & 1) ? v1 : v0;
 }
 
-template <int NW, int NB>
-__global__ void __launch_bounds__(NW * 32, 1) ekf_gain_tiled(EkfPtrs p, const double* __restrict__ Pin, const double* __restrict__ z,
-                                                             const double* __restrict__ Rin, const uint8_t* __restrict__ pass) {
-    extern __shared__ __align__(16) double smg[];
+// Kernel 1 of 2: measurement map, residual vector, lower(S) from upper(S), blocked right-looking
+// Cholesky (8x8 tiles) and the explicit inverses of the diagonal tiles.  128 threads per filter
+// and ~54 KB of shared memory, so four filters share an SM and hide each other's serial
+// diagonal-tile steps.  L tiles and inverse tiles go to global scratch in their swizzled layout.
+template <int NB>
+__global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double* __restrict__ Pin, const double* __restrict__ z,
+                                                         const double* __restrict__ Rin, const uint8_t* __restrict__ pass) {
+    extern __shared__ __align__(16) double smc[];
     constexpr int NT = NB * (NB + 1) / 2;
-    double* Ls = smg;                      // NT tiles
-    double* Ss = Ls + NT * 64;             // NB*NB tiles: the full (possibly asymmetric) S
-    double* Li = Ss + NB * NB * 64;        // NB inverse diagonal tiles
-    double* s_y = Li + NB * 64;            // NB*8
-    int* s_idx = reinterpret_cast<int*>(s_y + NB * 8);   // NB*8
+    constexpr int NWC = 4;
+    double* Ls = smc;                      // NT tiles
+    double* Li = Ls + NT * 64;             // NB inverse diagonal tiles
+    int* s_idx = reinterpret_cast<int*>(Li + NB * 64);   // NB*8
     __shared__ int s_m, s_bad;
 
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = p.nfeat[f], N = BASE + 3 * n;
-    const int ld = p.ldP, ldK = p.ldK, nmax = p.nmax;
+    const int n = p.nfeat[f];
+    const int ld = p.ldP, nmax = p.nmax;
     const double* Pi = Pin + (size_t)f * ld * ld;
     const double* zf = z + (size_t)f * nmax * 2;
     const double* Rf = Rin + (size_t)f * nmax * 4;
     const uint8_t* pf = pass + (size_t)f * nmax;
-    double* Kf = p.K + (size_t)f * ld * ldK;
-    double* Wf = p.W + (size_t)f * ld * ldK;
     double* mu_g = p.mu + (size_t)f * BASE;
-    double* feat_g = p.feat + (size_t)f * nmax * 3;
+    const double* feat_g = p.feat + (size_t)f * nmax * 3;
     int* idx_g = p.idx + (size_t)f * p.mmax;
+    double* y_g = p.y + (size_t)f * p.mmax;
 
-    if (tid == 0) {  // formFeatureMeasurementMap (:634-661) + bookkeeping of :506-529
+    if (warp == 0) {  // formFeatureMeasurementMap (:634-661) + bookkeeping of :506-529, ballot-compacted
         int m = 0;
-        for (int i = 0; i < n; ++i) {
-            if (pf[i]) {
-                s_idx[m] = BASE + 3 * i; s_idx[m + 1] = BASE + 3 * i + 1;
-                idx_g[m] = BASE + 3 * i; idx_g[m + 1] = BASE + 3 * i + 1;
-                s_y[m] = zf[2 * i] - feat_g[3 * i];
-                s_y[m + 1] = zf[2 * i + 1] - feat_g[3 * i + 1];
-                p.klt_last[((size_t)f * nmax + i) * 2] = zf[2 * i];
-                p.klt_last[((size_t)f * nmax + i) * 2 + 1] = zf[2 * i + 1];
-                m += 2;
-            } else {
+        for (int base = 0; base < n; base += 32) {
+            int i = base + lane;
+            bool pr = i < n && pf[i] != 0;
+            unsigned mask = __ballot_sync(0xffffffffu, pr);
+            int pos = m + 2 * __popc(mask & ((1u << lane) - 1u));
+            if (pr) {
+                s_idx[pos] = BASE + 3 * i; s_idx[pos + 1] = BASE + 3 * i + 1;
+                idx_g[pos] = BASE + 3 * i; idx_g[pos + 1] = BASE + 3 * i + 1;
+                double zx = zf[2 * i], zy = zf[2 * i + 1];
+                y_g[pos] = zx - feat_g[3 * i];
+                y_g[pos + 1] = zy - feat_g[3 * i + 1];
+                p.klt_last[((size_t)f * nmax + i) * 2] = zx;
+                p.klt_last[((size_t)f * nmax + i) * 2 + 1] = zy;
+            } else if (i < n) {
                 p.dflags[(size_t)f * nmax + i] = 1;
             }
+            m += 2 * __popc(mask);
         }
-        for (int a = m; a < NB * 8; ++a) { s_idx[a] = 0; s_y[a] = 0.0; }
-        s_m = m; s_bad = 0;
-        p.m[f] = m;
+        for (int a = m + lane; a < NB * 8; a += 32) s_idx[a] = 0;
+        if (lane == 0) { s_m = m; s_bad = 0; p.m[f] = m; }
     }
     __syncthreads();
     const int m = s_m;
     if (m == 0) {
-        if (tid == 0) {
+        if (tid == 0) {  // K is N x 0: only the quaternion renormalisation of :605-609 acts
             double qn = sqrt(mu_g[3] * mu_g[3] + mu_g[4] * mu_g[4] + mu_g[5] * mu_g[5] + mu_g[6] * mu_g[6]);
             mu_g[3] /= qn; mu_g[4] /= qn; mu_g[5] /= qn; mu_g[6] /= qn;
         }
@@ -220,33 +232,28 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_gain_tiled(EkfPtrs p, const do
     const int nb = (m + 7) >> 3;
     const int r = lane >> 2, q = lane & 3;
 
-    // ---- Ss: full S = Sigma(idx,idx) + R as NB x NB tiles (identity tail); no symmetry assumed
-    for (int e = tid; e < nb * nb * 64; e += NW * 32) {
-        int t = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
-        int ta = t / nb, tb = t - ta * nb;
-        int a = ta * 8 + rr, b = tb * 8 + cc;
-        double v;
-        if (a < m && b < m) {
-            v = Pi[(size_t)s_idx[a] * ld + s_idx[b]];
-            if ((a >> 1) == (b >> 1)) v += Rf[4 * ((s_idx[a] - BASE) / 3) + (a & 1) * 2 + (b & 1)];
-        } else {
-            v = (a == b) ? 1.0 : 0.0;
-        }
-        Ss[(ta * NB + tb) * 64 + tsw(rr, cc)] = v;
-    }
-    __syncthreads();
-    // ---- Ls: lower(a,b), a >= b  <-  upper(S)(b,a)  (SimplicialLDLT::compute(S') reads upper(S), :578)
-    for (int e = tid; e < nb * (nb + 1) / 2 * 64; e += NW * 32) {
+    // lower(a,b), a >= b  <-  upper(S)(b,a) = Sigma(idx[b], idx[a]) + R(b,a)  (SimplicialLDLT::compute(S')
+    // reads upper(S), :578); identity tail
+    for (int e = tid; e < nb * (nb + 1) / 2 * 64; e += 128) {
         int t = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
         int ib = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
         while (ib * (ib + 1) / 2 > t) --ib;
         while ((ib + 1) * (ib + 2) / 2 <= t) ++ib;
         int jb = t - ib * (ib + 1) / 2;
-        Ls[t * 64 + tsw(rr, cc)] = Ss[(jb * NB + ib) * 64 + tsw(cc, rr)];
+        int a = ib * 8 + rr, b = jb * 8 + cc;
+        double v = 0.0;
+        if (a >= b) {
+            if (a < m) {
+                v = Pi[(size_t)s_idx[b] * ld + s_idx[a]];
+                if ((a >> 1) == (b >> 1)) v += Rf[4 * ((s_idx[a] - BASE) / 3) + (b & 1) * 2 + (a & 1)];
+            } else {
+                v = (a == b) ? 1.0 : 0.0;
+            }
+        }
+        Ls[t * 64 + tsw(rr, cc)] = v;
     }
     __syncthreads();
 
-    // ---- blocked right-looking Cholesky of Ls, 8x8 tiles
     for (int jb = 0; jb < nb; ++jb) {
         if (warp == 0) {   // diagonal tile: lane rr (< 8) owns row rr
             double* T = Ls + tile_of(jb, jb);
@@ -286,11 +293,10 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_gain_tiled(EkfPtrs p, const do
             }
         }
         __syncthreads();
-        // panel: L(ib,jb) = A(ib,jb) * inv(Ljj)'
-        {
+        {   // panel: L(ib,jb) = A(ib,jb) * inv(Ljj)'
             const double* I8 = Li + jb * 64;
             double b0 = I8[tsw(r, q)], b1 = I8[tsw(r, 4 + q)];
-            for (int ib = jb + 1 + warp; ib < nb; ib += NW) {
+            for (int ib = jb + 1 + warp; ib < nb; ib += NWC) {
                 double* T = Ls + tile_of(ib, jb);
                 double a0 = T[tsw(r, q)], a1 = T[tsw(r, 4 + q)];
                 double c0 = 0.0, c1 = 0.0;
@@ -301,10 +307,9 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_gain_tiled(EkfPtrs p, const do
             }
         }
         __syncthreads();
-        // trailing update: A(ib,kb) -= L(ib,jb) L(kb,jb)'  for ib >= kb > jb
-        {
+        {   // trailing update: A(ib,kb) -= L(ib,jb) L(kb,jb)'  for ib >= kb > jb
             const int t = nb - 1 - jb;
-            for (int e = warp; e < t * (t + 1) / 2; e += NW) {
+            for (int e = warp; e < t * (t + 1) / 2; e += NWC) {
                 int ii = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
                 while (ii * (ii + 1) / 2 > e) --ii;
                 while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
@@ -322,8 +327,82 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_gain_tiled(EkfPtrs p, const do
         __syncthreads();
     }
     if (tid == 0 && s_bad) atomicOr(&p.status[f], 1);
+    // factor and inverse tiles to global scratch (same swizzled layout)
+    double* Lg = p.L + (size_t)f * (NT + NB) * 64;
+    const int used = nb * (nb + 1) / 2 * 64;
+    for (int e = tid * 2; e < used; e += 256) *reinterpret_cast<double2*>(Lg + e) = *reinterpret_cast<const double2*>(Ls + e);
+    for (int e = tid * 2; e < nb * 64; e += 256) *reinterpret_cast<double2*>(Lg + NT * 64 + e) = *reinterpret_cast<const double2*>(Li + e);
+}
 
-    // ---- per-warp 16-row strips: K = Sigma(:,idx) inv(L)' inv(L), all in registers
+// Kernel 2 of 2: K = Sigma(:,idx) inv(L)' inv(L), sparseView, mu += K y, W = Sigma(:,idx) - K S,
+// quaternion renormalisation.  One warp per 16-row strip, the strip lives in registers through both
+// triangular solves (right-looking over 8-wide column blocks).
+template <int NW, int NB>
+__global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const double* __restrict__ Pin, const double* __restrict__ Rin) {
+    extern __shared__ __align__(16) double smg[];
+    constexpr int NT = NB * (NB + 1) / 2;
+    double* Ls = smg;                      // NT tiles
+    double* Li = Ls + NT * 64;             // NB inverse diagonal tiles (contiguous with Ls, as in scratch)
+    double* Ss = Li + NB * 64;             // NB*NB tiles: the full (possibly asymmetric) S
+    double* s_y = Ss + NB * NB * 64;       // NB*8
+    int* s_idx = reinterpret_cast<int*>(s_y + NB * 8);   // NB*8
+
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = p.m[f];
+    if (m == 0) return;
+    const int n = p.nfeat[f], N = BASE + 3 * n;
+    const int ld = p.ldP, ldK = p.ldK, nmax = p.nmax;
+    const double* Pi = Pin + (size_t)f * ld * ld;
+    const double* Rf = Rin + (size_t)f * nmax * 4;
+    double* Kf = p.K + (size_t)f * ld * ldK;
+    double* Wf = p.W + (size_t)f * ld * ldK;
+    double* mu_g = p.mu + (size_t)f * BASE;
+    double* feat_g = p.feat + (size_t)f * nmax * 3;
+    const int nb = (m + 7) >> 3;
+    const int r = lane >> 2, q = lane & 3;
+
+    {   // L and inverse tiles: straight copy from scratch
+        const double* Lg = p.L + (size_t)f * (NT + NB) * 64;
+        const int used = nb * (nb + 1) / 2 * 64;
+        for (int e = tid * 2; e < used; e += NW * 64) cp_async16(Ls + e, Lg + e);
+        for (int e = tid * 2; e < nb * 64; e += NW * 64) cp_async16(Li + e, Lg + NT * 64 + e);
+        cp_async_commit();
+        const int* idx_g = p.idx + (size_t)f * p.mmax;
+        const double* y_g = p.y + (size_t)f * p.mmax;
+        for (int a = tid; a < NB * 8; a += NW * 32) { s_idx[a] = a < m ? idx_g[a] : 0; s_y[a] = a < m ? y_g[a] : 0.0; }
+    }
+    __syncthreads();
+    // Ss: full S = Sigma(idx,idx) + R as NB x NB tiles (identity tail); no symmetry assumed
+    for (int e0 = tid; e0 < nb * nb * 64; e0 += NW * 32 * 4) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int e = e0 + u * NW * 32;
+            int t = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
+            int ta = t / nb, tb = t - ta * nb;
+            int a = ta * 8 + rr, b = tb * 8 + cc;
+            v[u] = 0.0;
+            if (e < nb * nb * 64) {
+                if (a < m && b < m) v[u] = Pi[(size_t)s_idx[a] * ld + s_idx[b]];
+                else v[u] = (a == b) ? 1.0 : 0.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int e = e0 + u * NW * 32;
+            if (e < nb * nb * 64) {
+                int t = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
+                int ta = t / nb, tb = t - ta * nb;
+                int a = ta * 8 + rr, b = tb * 8 + cc;
+                double x = v[u];
+                if (a < m && b < m && (a >> 1) == (b >> 1)) x += Rf[4 * ((s_idx[a] - BASE) / 3) + (a & 1) * 2 + (b & 1)];
+                Ss[(ta * NB + tb) * 64 + tsw(rr, cc)] = x;
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
     const int i0 = warp * 16;
     if (i0 < N) {
         double k0[2][NB], k1[2][NB];
@@ -353,8 +432,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_gain_tiled(EkfPtrs p, const do
                     dmma884(t0, t1, a0, b0);
                     dmma884(t0, t1, a1, b1);
                     k0[rt][jb] = t0; k1[rt][jb] = t1;
-                    cfrag_to_afrag(t0, t1, lane, a0, a1);
-                    za[rt][0] = -a0; za[rt][1] = -a1;
+                    cfrag_to_afrag(t0, t1, lane, za[rt][0], za[rt][1]);
                 }
 #pragma unroll
                 for (int j2 = 0; j2 < NB; ++j2) {
@@ -363,8 +441,8 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_gain_tiled(EkfPtrs p, const do
                         const double l0 = T[tsw(r, q)], l1 = T[tsw(r, 4 + q)];
 #pragma unroll
                         for (int rt = 0; rt < 2; ++rt) {
-                            dmma884(k0[rt][j2], k1[rt][j2], za[rt][0], l0);
-                            dmma884(k0[rt][j2], k1[rt][j2], za[rt][1], l1);
+                            dmma884(k0[rt][j2], k1[rt][j2], -za[rt][0], l0);
+                            dmma884(k0[rt][j2], k1[rt][j2], -za[rt][1], l1);
                         }
                     }
                 }
@@ -386,8 +464,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_gain_tiled(EkfPtrs p, const do
                     dmma884(t0, t1, a0, b0);
                     dmma884(t0, t1, a1, b1);
                     k0[rt][jb] = t0; k1[rt][jb] = t1;
-                    cfrag_to_afrag(t0, t1, lane, a0, a1);
-                    ka[rt][0] = -a0; ka[rt][1] = -a1;
+                    cfrag_to_afrag(t0, t1, lane, ka[rt][0], ka[rt][1]);
                 }
 #pragma unroll
                 for (int j2 = 0; j2 < NB; ++j2) {
@@ -396,8 +473,8 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_gain_tiled(EkfPtrs p, const do
                         const double l0 = T[tsw(q, r)], l1 = T[tsw(4 + q, r)];
 #pragma unroll
                         for (int rt = 0; rt < 2; ++rt) {
-                            dmma884(k0[rt][j2], k1[rt][j2], ka[rt][0], l0);
-                            dmma884(k0[rt][j2], k1[rt][j2], ka[rt][1], l1);
+                            dmma884(k0[rt][j2], k1[rt][j2], -ka[rt][0], l0);
+                            dmma884(k0[rt][j2], k1[rt][j2], -ka[rt][1], l1);
                         }
                     }
                 }
@@ -412,7 +489,6 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_gain_tiled(EkfPtrs p, const do
             for (int jb = 0; jb < NB; ++jb) {
                 if (jb < nb) {
                     double a = prune(k0[rt][jb]), b = prune(k1[rt][jb]);
-                    k0[rt][jb] = a; k1[rt][jb] = b;
                     dot += a * s_y[jb * 8 + 2 * q] + b * s_y[jb * 8 + 2 * q + 1];
                     if (row < ld) *reinterpret_cast<double2*>(Kf + (size_t)row * ldK + jb * 8 + 2 * q) = make_double2(a, b);
                 }
@@ -422,7 +498,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_gain_tiled(EkfPtrs p, const do
             if (q == 0 && row < N) { if (row < BASE) mu_g[row] += dot; else feat_g[row - BASE] += dot; }
         }
         __syncwarp();
-        // W = Sigma(:,idx) - K S  (S = Ss, symmetric from upper(S)) - K E  (E: asymmetric part of the R blocks)
+        // W = Sigma(:,idx) - K S with the full S
         double w0[2][NB], w1[2][NB];
 #pragma unroll
         for (int rt = 0; rt < 2; ++rt) {
@@ -431,21 +507,17 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_gain_tiled(EkfPtrs p, const do
             for (int jb = 0; jb < NB; ++jb) {
                 int a = jb * 8 + 2 * q;
                 bool ok = row < N && a < m && jb < nb;
-                double c0 = ok ? Pi[(size_t)row * ld + s_idx[a]] : 0.0;
-                double c1 = ok ? Pi[(size_t)row * ld + s_idx[a + 1]] : 0.0;
-                w0[rt][jb] = c0;
-                w1[rt][jb] = c1;
+                w0[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a]] : 0.0;
+                w1[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a + 1]] : 0.0;
             }
         }
+        const int rowa = min(i0 + r, ld - 1), rowb = min(i0 + 8 + r, ld - 1);
+        const double* kra = Kf + (size_t)rowa * ldK + q;
+        const double* krb = Kf + (size_t)rowb * ldK + q;
+        double ka[2][2] = {{kra[0], kra[4]}, {krb[0], krb[4]}};
         for (int kb = 0; kb < nb; ++kb) {
-            double ka[2][2];
-#pragma unroll
-            for (int rt = 0; rt < 2; ++rt) {
-                const int row = i0 + rt * 8 + r;
-                const double* kr = Kf + (size_t)row * ldK + kb * 8 + q;
-                ka[rt][0] = row < ld ? -kr[0] : 0.0;
-                ka[rt][1] = row < ld ? -kr[4] : 0.0;
-            }
+            double kn[2][2] = {{0, 0}, {0, 0}};
+            if (kb + 1 < nb) { kn[0][0] = kra[(kb + 1) * 8]; kn[0][1] = kra[(kb + 1) * 8 + 4]; kn[1][0] = krb[(kb + 1) * 8]; kn[1][1] = krb[(kb + 1) * 8 + 4]; }
 #pragma unroll
             for (int j2 = 0; j2 < NB; ++j2) {
                 if (j2 < nb) {
@@ -453,11 +525,12 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_gain_tiled(EkfPtrs p, const do
                     const double s0 = T[tsw(q, r)], s1 = T[tsw(4 + q, r)];
 #pragma unroll
                     for (int rt = 0; rt < 2; ++rt) {
-                        dmma884(w0[rt][j2], w1[rt][j2], ka[rt][0], s0);
-                        dmma884(w0[rt][j2], w1[rt][j2], ka[rt][1], s1);
+                        dmma884(w0[rt][j2], w1[rt][j2], -ka[rt][0], s0);
+                        dmma884(w0[rt][j2], w1[rt][j2], -ka[rt][1], s1);
                     }
                 }
             }
+            ka[0][0] = kn[0][0]; ka[0][1] = kn[0][1]; ka[1][0] = kn[1][0]; ka[1][1] = kn[1][1];
         }
 #pragma unroll
         for (int rt = 0; rt < 2; ++rt) {
@@ -469,7 +542,6 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_gain_tiled(EkfPtrs p, const do
     }
     __syncthreads();
     if (tid == 0) {  // renormalise the quaternion (:605-609) and flag non-finite states
-        __threadfence_block();
         double qn = sqrt(mu_g[3] * mu_g[3] + mu_g[4] * mu_g[4] + mu_g[5] * mu_g[5] + mu_g[6] * mu_g[6]);
         mu_g[3] /= qn; mu_g[4] /= qn; mu_g[5] /= qn; mu_g[6] /= qn;
         bool fin = true;
@@ -478,19 +550,22 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_gain_tiled(EkfPtrs p, const do
     }
 }
 
-template <int NW, int NB> size_t gain_tiled_smem() {
-    return (size_t)(NB * (NB + 1) / 2 * 64 + NB * NB * 64 + NB * 64 + NB * 8 + NB * 4) * sizeof(double) + NB * 8 * sizeof(int);
-}
 template <int NW, int NB>
 cudaError_t launch_gain_tiled_t(const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, cudaStream_t st) {
     static bool configured = false;
-    size_t sm = gain_tiled_smem<NW, NB>();
+    constexpr int NT = NB * (NB + 1) / 2;
+    const size_t sm_c = (size_t)(NT + NB) * 64 * sizeof(double) + NB * 8 * sizeof(int);
+    const size_t sm_s = (size_t)((NT + NB) * 64 + NB * NB * 64 + NB * 8) * sizeof(double) + NB * 8 * sizeof(int);
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(ekf_gain_tiled<NW, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaError_t e = cudaFuncSetAttribute(ekf_chol_tiled<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_solve_tiled<NW, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_s);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    ekf_gain_tiled<NW, NB><<<p.F, NW * 32, sm, st>>>(p, Pin, z, R, pass);
+    ekf_chol_tiled<NB><<<p.F, 128, sm_c, st>>>(p, Pin, z, R, pass);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    ekf_solve_tiled<NW, NB><<<p.F, NW * 32, sm_s, st>>>(p, Pin, R);
     return cudaGetLastError();
 }
 
@@ -500,7 +575,8 @@ namespace ekfvio {
 
 bool joseph_tiled_supported(const EkfPtrs& p) { return p.Nmax <= 256 && p.mmax <= 256; }
 
-bool gain_tiled_supported(const EkfPtrs& p) { return p.Nmax <= 176 && p.mmax <= 104; }
+bool gain_tiled_supported(const EkfPtrs& p) { return p.Nmax <= 176 && p.mmax <= 104 && p.L != nullptr; }
+size_t gain_tiled_scratch_doubles(int mmax) { int NB = mmax <= 64 ? 8 : 13; return (size_t)(NB * (NB + 1) / 2 + NB) * 64; }
 
 cudaError_t launch_gain_tiled(const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, cudaStream_t st) {
     if (p.Nmax <= 128 && p.mmax <= 64) return launch_gain_tiled_t<8, 8>(p, Pin, z, R, pass, st);
@@ -509,9 +585,18 @@ cudaError_t launch_gain_tiled(const EkfPtrs& p, const double* Pin, const double*
 
 cudaError_t launch_joseph_tiled(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st) {
     const int strips = (p.Nmax + 15) / 16;
-    if (strips <= 8) ekf_joseph_tiled<8><<<p.F, 8 * 32, 0, st>>>(p, Pin, Pout);
-    else if (strips <= 11) ekf_joseph_tiled<11><<<p.F, 11 * 32, 0, st>>>(p, Pin, Pout);
-    else ekf_joseph_tiled<16><<<p.F, 16 * 32, 0, st>>>(p, Pin, Pout);
+    const size_t sm = (size_t)NST * BS_DOUBLES * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ekf_joseph_tiled<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_joseph_tiled<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_joseph_tiled<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (strips <= 8) ekf_joseph_tiled<8><<<p.F, 8 * 32, sm, st>>>(p, Pin, Pout);
+    else if (strips <= 11) ekf_joseph_tiled<11><<<p.F, 11 * 32, sm, st>>>(p, Pin, Pout);
+    else ekf_joseph_tiled<16><<<p.F, 16 * 32, sm, st>>>(p, Pin, Pout);
     return cudaGetLastError();
 }
 
