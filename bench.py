@@ -210,8 +210,9 @@ def bench_ekf(args, rank, world, local):
     res = {
         "value": value, "ms_per_step": ms_total / K, "launches": int(launches), "clocks": clocks,
         "e2e": {"value": total_filters * K / e2e_s, "unit": "filter-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-        "kernel_ms": {"process": kms[0] / max(kcnt[0], 1), "gain": kms[1] / max(kcnt[1], 1), "cov_update": kms[2] / max(kcnt[2], 1)},
-        "kernel_share": {k: float(v) for k, v in zip(("process", "gain", "cov_update"), kms[:3] / max(kms[:3].sum(), 1e-12))},
+        "kernel_ms": {"process": kms[0] / max(kcnt[0], 1), "gain_chol": kms[1] / max(kcnt[1], 1), "gain_solve": kms[3] / max(kcnt[3], 1),
+                      "cov_update": kms[2] / max(kcnt[2], 1)},
+        "kernel_share": {k: float(v) for k, v in zip(("process", "gain_chol", "cov_update", "gain_solve"), kms[:4] / max(kms[:4].sum(), 1e-12))},
         "status_nonzero": bad, "finite": finite, "arms_agree": arms_agree, "gen_s": gen_s,
         "mc_stats": {"rmse_pos": float(np.sqrt(acc[0] / max(acc[3], 1))), "rmse_vel": float(np.sqrt(acc[1] / max(acc[3], 1))), "count": float(acc[3])},
     }

@@ -4,6 +4,9 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
+#include <algorithm>
+#include <cmath>
 
 #include "ekf_common.cuh"
 #include "ekf_kernels.h"
@@ -24,7 +27,7 @@ int fail_msg(const std::string& msg) { g_last_error = msg; return 1; }
 static EkfPtrs ptrs(const ekfvio_batch* b) {
     EkfPtrs p;
     p.mu = b->d_mu; p.feat = b->d_feat; p.nfeat = b->d_nfeat; p.cache = b->d_cache; p.dflags = b->d_flags;
-    p.klt_last = b->d_klt_last; p.status = b->d_status; p.idx = b->d_idx; p.y = b->d_y; p.m = b->d_m; p.K = b->d_K; p.W = b->d_W; p.L = b->d_L;
+    p.klt_last = b->d_klt_last; p.status = b->d_status; p.idx = b->d_idx; p.y = b->d_y; p.m = b->d_m; p.K = b->d_K; p.W = b->d_W; p.L = b->d_L; p.asym = b->d_asym;
     p.F = b->F; p.nmax = b->nmax; p.Nmax = b->Nmax; p.ldP = b->ldP; p.ldK = b->ldK; p.mmax = b->mmax;
     p.flags = b->prm.flags;
     p.depth = b->prm.default_point_depth; p.depth_var = b->prm.default_point_depth_variance;
@@ -49,7 +52,7 @@ int ekfvio_batch_destroy(ekfvio_batch* b) {
     cudaSetDevice(b->device);
     cudaFree(b->d_mu); cudaFree(b->d_feat); cudaFree(b->d_P[0]); cudaFree(b->d_P[1]); cudaFree(b->d_nfeat); cudaFree(b->d_cache);
     cudaFree(b->d_flags); cudaFree(b->d_klt_last); cudaFree(b->d_status); cudaFree(b->d_dt); cudaFree(b->d_K); cudaFree(b->d_W);
-    cudaFree(b->d_S); cudaFree(b->d_L); cudaFree(b->d_y); cudaFree(b->d_idx); cudaFree(b->d_m); cudaFree(b->d_fjac);
+    cudaFree(b->d_S); cudaFree(b->d_L); cudaFree(b->d_asym); cudaFree(b->d_y); cudaFree(b->d_idx); cudaFree(b->d_m); cudaFree(b->d_fjac);
     cudaFree(b->dd_z); cudaFree(b->dd_R); cudaFree(b->dd_pass);
     cudaFreeHost(b->h_z); cudaFreeHost(b->h_R); cudaFreeHost(b->h_pass); cudaFreeHost(b->h_out);
     delete b;
@@ -89,6 +92,7 @@ int ekfvio_batch_create(ekfvio_batch** out, int device, int num_filters, int max
     ALLOC(b->d_y, F * b->mmax * sizeof(double));
     ALLOC(b->d_idx, F * b->mmax * sizeof(int));
     ALLOC(b->d_m, F * sizeof(int));
+    ALLOC(b->d_asym, F * sizeof(int));
     if (gain_general_smem_doubles(b->mmax) == 0) ALLOC(b->d_S, F * ((size_t)b->mmax * b->mmax + b->mmax) * sizeof(double));
     if (b->Nmax <= 176 && b->mmax <= 104) ALLOC(b->d_L, F * gain_tiled_scratch_doubles(b->mmax) * sizeof(double));
     ALLOC(b->dd_z, F * nm * 2 * sizeof(double));
@@ -152,17 +156,32 @@ int ekfvio_batch_linearize(ekfvio_batch* b, const double* d_dt, double* d_F, voi
 int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, const uint8_t* d_pass, void* stream) {
     CU(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
-    b->timer.begin(1, st);
     {
         EkfPtrs pp = ptrs(b);
-        if (!(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | 0x100u)) && gain_tiled_supported(pp)) CU(launch_gain_tiled(pp, b->d_P[b->cur], d_z, d_R, d_pass, st));
-        else CU(launch_gain_general(pp, b->d_P[b->cur], d_z, d_R, d_pass, b->d_S, st));
+        if (!(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | 0x100u)) && gain_tiled_supported(pp)) {
+            b->timer.begin(1, st);
+            CU(launch_gain_tiled(0, pp, b->d_P[b->cur], d_z, d_R, d_pass, st));
+            b->timer.end(st);
+            b->timer.begin(3, st);
+            CU(launch_gain_tiled(1, pp, b->d_P[b->cur], d_z, d_R, d_pass, st));
+            b->timer.end(st);
+            b->launches += 1;
+        } else {
+            b->timer.begin(1, st);
+            CU(launch_gain_general(pp, b->d_P[b->cur], d_z, d_R, d_pass, b->d_S, st));
+            b->timer.end(st);
+        }
     }
-    b->timer.end(st);
     b->timer.begin(2, st);
     {
         EkfPtrs pp = ptrs(b);
-        if (!(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | 0x200u)) && joseph_tiled_supported(pp)) CU(launch_joseph_tiled(pp, b->d_P[b->cur], b->d_P[b->cur ^ 1], st));
+        const bool tiled = !(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | 0x200u)) && joseph_tiled_supported(pp);
+        const bool sym = tiled && !(b->prm.flags & 0x400u) && joseph_sym_supported(pp);
+        if (sym) {   // symmetric filters: lower-triangle kernel; the (rare) asymmetric ones: full kernel
+            CU(launch_joseph_sym(pp, b->d_P[b->cur], b->d_P[b->cur ^ 1], st));
+            CU(launch_joseph_tiled(pp, b->d_P[b->cur], b->d_P[b->cur ^ 1], 1, st));
+            b->launches += 1;
+        } else if (tiled) CU(launch_joseph_tiled(pp, b->d_P[b->cur], b->d_P[b->cur ^ 1], 0, st));
         else CU(launch_joseph_general(pp, b->d_P[b->cur], b->d_P[b->cur ^ 1], st));
     }
     b->timer.end(st);
@@ -251,6 +270,27 @@ int ekfvio_batch_set_state(ekfvio_batch* b, const double* h_mu, const double* h_
     if (h_flags && nm) CU(cudaMemcpy(b->d_flags, h_flags, F * nm, cudaMemcpyHostToDevice));
     if (h_klt_last && nm) CU(cudaMemcpy(b->d_klt_last, h_klt_last, F * nm * 2 * sizeof(double), cudaMemcpyHostToDevice));
     if (h_P) {
+        // filters whose Sigma is not symmetric (beyond rounding) are marked so that the update
+        // takes the kernels that make no symmetry assumption
+        {
+            std::vector<int> asym(F, 0), nf(F, 0);
+            CU(cudaMemcpy(nf.data(), b->d_nfeat, F * sizeof(int), cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(asym.data(), b->d_asym, F * sizeof(int), cudaMemcpyDeviceToHost));
+            const size_t Nm = b->Nmax;
+            for (size_t f = 0; f < F; ++f) {
+                const double* P = h_P + f * Nm * Nm;
+                const int N = BASE + 3 * nf[f];
+                double mx = 0, ma = 0;
+                for (int i = 0; i < N; ++i)
+                    for (int j = 0; j <= i; ++j) {
+                        double a = P[i * Nm + j], c = P[j * Nm + i];
+                        mx = std::max(mx, std::max(std::fabs(a), std::fabs(c)));
+                        ma = std::max(ma, std::fabs(a - c));
+                    }
+                if (ma > 1e-13 * mx) asym[f] = 1;
+            }
+            CU(cudaMemcpy(b->d_asym, asym.data(), F * sizeof(int), cudaMemcpyHostToDevice));
+        }
         double* tmp = nullptr;
         size_t bytes = F * (size_t)b->Nmax * b->Nmax * sizeof(double);
         CU(cudaMalloc((void**)&tmp, bytes));

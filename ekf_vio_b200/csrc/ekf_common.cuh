@@ -141,6 +141,7 @@ struct ekfvio_batch {
     double* d_y = nullptr;         // [F][mmax]
     int* d_idx = nullptr;          // [F][mmax]
     int* d_m = nullptr;            // [F]
+    int* d_asym = nullptr;         // [F] sticky: Sigma or an R block of this filter is not symmetric
     double* d_fjac = nullptr;      // [F][(22*22 + nmax*27 + nmax*9)] A | B | D
     // pinned staging + device input buffers for the *_h entry points
     double* h_z = nullptr; double* h_R = nullptr; uint8_t* h_pass = nullptr;

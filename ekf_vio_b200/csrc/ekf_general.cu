@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(PT) ekf_gain_general(EkfPtrs p, const double* 
                 y[m + 1] = zf[2 * i + 1] - feat_g[3 * i + 1];
                 p.klt_last[((size_t)f * nmax + i) * 2] = zf[2 * i];
                 p.klt_last[((size_t)f * nmax + i) * 2 + 1] = zf[2 * i + 1];
+                if (Rf[4 * i + 1] != Rf[4 * i + 2]) p.asym[f] = 1;
                 m += 2;
             } else {
                 p.dflags[(size_t)f * nmax + i] = 1;
@@ -439,7 +440,7 @@ __global__ void ekf_reset_kernel(EkfPtrs p, double* P0) {  // initializeBaseStat
     }
     if (tid < BASE) p.mu[(size_t)f * BASE + tid] = (tid == 3) ? 1.0 : 0.0;
     if (tid == 0) {
-        p.nfeat[f] = 0; p.status[f] = 0; p.m[f] = 0;
+        p.nfeat[f] = 0; p.status[f] = 0; p.m[f] = 0; p.asym[f] = 0;
         double* c = p.cache + (size_t)f * 7;
         c[0] = c[1] = c[2] = 0.0; c[3] = 1.0; c[4] = c[5] = c[6] = 0.0;
     }

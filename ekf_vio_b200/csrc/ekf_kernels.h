@@ -9,7 +9,7 @@ namespace ekfvio {
 // Plain device-pointer bundle passed by value to every EKF kernel.
 struct EkfPtrs {
     double* mu; double* feat; int* nfeat; double* cache; uint8_t* dflags; double* klt_last; int* status;
-    int* idx; double* y; int* m; double* K; double* W; double* L;
+    int* idx; double* y; int* m; double* K; double* W; double* L; int* asym;
     int F, nmax, Nmax, ldP, ldK, mmax;
     uint32_t flags;
     double depth, depth_var, uv_var;
@@ -33,8 +33,10 @@ cudaError_t launch_accumulate_errors(const EkfPtrs& p, const double* truth, doub
 bool joseph_tiled_supported(const EkfPtrs& p);
 bool gain_tiled_supported(const EkfPtrs& p);
 size_t gain_tiled_scratch_doubles(int mmax);
-cudaError_t launch_gain_tiled(const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, cudaStream_t st);
-cudaError_t launch_joseph_tiled(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st);
+cudaError_t launch_gain_tiled(int which, const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, cudaStream_t st);
+cudaError_t launch_joseph_tiled(const EkfPtrs& p, const double* Pin, double* Pout, int only_asym, cudaStream_t st);
+bool joseph_sym_supported(const EkfPtrs& p);
+cudaError_t launch_joseph_sym(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st);
 
 // FP64 peak probe (fp64_peak.cu)
 cudaError_t measure_fp64_peak(double* dmma_tflops, double* dfma_tflops);

@@ -31,10 +31,11 @@ constexpr int LDK = KC + 4;         // K-phase chunk: [JT*8][LDK]
 constexpr int BS_DOUBLES = (JT * 8 * LDK > KC * LDG) ? JT * 8 * LDK : KC * LDG;
 
 template <int NW>
-__global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const double* __restrict__ Pin, double* __restrict__ Pout) {
+__global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const double* __restrict__ Pin, double* __restrict__ Pout, int only_asym) {
     extern __shared__ __align__(16) double Bs_all[];   // NST * BS_DOUBLES
     __shared__ int s_idx[256];
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (only_asym && p.asym[f] == 0) return;              // symmetric filters went to ekf_joseph_sym
     const int n = p.nfeat[f], N = BASE + 3 * n, m = p.m[f];
     const int ld = p.ldP, ldK = p.ldK;
     const double* Pi = Pin + (size_t)f * ld * ld;
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
                 y_g[pos + 1] = zy - feat_g[3 * i + 1];
                 p.klt_last[((size_t)f * nmax + i) * 2] = zx;
                 p.klt_last[((size_t)f * nmax + i) * 2 + 1] = zy;
+                if (Rf[4 * i + 1] != Rf[4 * i + 2]) p.asym[f] = 1;   // sticky: Sigma turns asymmetric with this update
             } else if (i < n) {
                 p.dflags[(size_t)f * nmax + i] = 1;
             }
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
 }
 
 template <int NW, int NB>
-cudaError_t launch_gain_tiled_t(const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, cudaStream_t st) {
+cudaError_t launch_gain_tiled_t(int which, const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, cudaStream_t st) {
     static bool configured = false;
     constexpr int NT = NB * (NB + 1) / 2;
     const size_t sm_c = (size_t)(NT + NB) * 64 * sizeof(double) + NB * 8 * sizeof(int);
@@ -562,10 +564,167 @@ cudaError_t launch_gain_tiled_t(const EkfPtrs& p, const double* Pin, const doubl
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    ekf_chol_tiled<NB><<<p.F, 128, sm_c, st>>>(p, Pin, z, R, pass);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    ekf_solve_tiled<NW, NB><<<p.F, NW * 32, sm_s, st>>>(p, Pin, R);
+    if (which == 0) ekf_chol_tiled<NB><<<p.F, 128, sm_c, st>>>(p, Pin, z, R, pass);
+    else ekf_solve_tiled<NW, NB><<<p.F, NW * 32, sm_s, st>>>(p, Pin, R);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// ekf_joseph_sym: the covariance update for filters whose Sigma and R are symmetric (the normal
+// case; p.asym[f] == 0).  Only the 16x16 blocks on or below the diagonal are computed —
+//   Sigma'(I,J) = Sigma(I,J) - K(I,:) Sigma(idx,J) - W(I,:) K(J,:)'     for J <= I
+// and written together with their mirror image, so Sigma' is exactly symmetric (the reference's
+// Sigma' is symmetric up to rounding; its fixSigma() is a no-op, TightlyCoupledEKF.cpp:716-718).
+// Both operands of every DMMA come from shared memory: per k-chunk the A panel (K or W, all rows)
+// and the B panel (rows idx[k] of Sigma, or K) are staged with cp.async, three stages deep.  The
+// lower-triangular block list is dealt round-robin to the warps, IPW blocks of 2x2 tiles each.
+constexpr int SKC = 16;             // k-chunk depth
+constexpr int SLDA = SKC + 4;       // A panel / K-as-B panel: [rows][SLDA]
+constexpr int SNST = 3;
+
+template <int NW, int NBLK, int IPW>
+__global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const double* __restrict__ Pin, double* __restrict__ Pout) {
+    constexpr int ROWS = NBLK * 16;
+    constexpr int SLDB = ROWS + 4;                       // G panel: [SKC][SLDB]
+    constexpr int A_DOUBLES = ROWS * SLDA;
+    constexpr int B_DOUBLES = (SKC * SLDB > A_DOUBLES) ? SKC * SLDB : A_DOUBLES;
+    constexpr int STAGE = A_DOUBLES + B_DOUBLES;
+    extern __shared__ __align__(16) double sms[];
+    __shared__ int s_idx[2 * 104];
+    const int f = blockIdx.x;
+    if (p.asym[f] != 0) return;                           // handled by ekf_joseph_tiled
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = p.nfeat[f], N = BASE + 3 * n, m = p.m[f];
+    const int ld = p.ldP, ldK = p.ldK;
+    const double* Pi = Pin + (size_t)f * ld * ld;
+    double* Po = Pout + (size_t)f * ld * ld;
+    const double* Kf = p.K + (size_t)f * ld * ldK;
+    const double* Wf = p.W + (size_t)f * ld * ldK;
+    const int* idx = p.idx + (size_t)f * p.mmax;
+    for (int i = tid; i < m; i += NW * 32) s_idx[i] = idx[i];
+    __syncthreads();
+
+    const int r = lane >> 2, q = lane & 3;
+    const int nblk = (N + 15) >> 4, nitems = nblk * (nblk + 1) / 2, nch = (m + SKC - 1) / SKC;
+    int bi[IPW], bj[IPW];
+    double c0[IPW][4], c1[IPW][4];                        // tile t = rt*2 + ct of the 16x16 block
+#pragma unroll
+    for (int it = 0; it < IPW; ++it) {
+        int e = warp + it * NW;
+        bool ok = e < nitems;
+        int i = 0, j = 0;
+        if (ok) {
+            i = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
+            while (i * (i + 1) / 2 > e) --i;
+            while ((i + 1) * (i + 2) / 2 <= e) ++i;
+            j = e - i * (i + 1) / 2;
+        }
+        bi[it] = ok ? i : -1; bj[it] = j;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            double2 v = make_double2(0.0, 0.0);
+            int row = i * 16 + (t >> 1) * 8 + r, col = j * 16 + (t & 1) * 8 + 2 * q;
+            if (ok && row < ld && col < ld) v = *reinterpret_cast<const double2*>(Pi + (size_t)row * ld + col);
+            c0[it][t] = v.x; c1[it][t] = v.y;
+        }
+    }
+
+#pragma unroll
+    for (int phase = 0; phase < 2; ++phase) {
+        const double* Am = phase == 0 ? Kf : Wf;
+        auto stage = [&](int c) {
+            if (c < nch) {
+                double* A = sms + (c % SNST) * STAGE;
+                double* B = A + A_DOUBLES;
+                const int k0 = c * SKC;
+                for (int t = tid; t < ROWS * (SKC / 2); t += NW * 32) {   // A panel: rows of K or W
+                    int row = t / (SKC / 2), seg = t % (SKC / 2);
+                    double* dst = &A[row * SLDA + seg * 2];
+                    if (row < ld && k0 + seg * 2 < m) cp_async16(dst, Am + (size_t)row * ldK + k0 + seg * 2);
+                    else { dst[0] = 0.0; dst[1] = 0.0; }
+                }
+                if (phase == 0) {                                         // B panel: rows idx[k] of Sigma
+                    for (int t = tid; t < SKC * (ROWS / 2); t += NW * 32) {
+                        int k = t / (ROWS / 2), seg = t % (ROWS / 2);
+                        double* dst = &B[k * SLDB + seg * 2];
+                        if (k0 + k < m && seg * 2 < ld) cp_async16(dst, Pi + (size_t)s_idx[k0 + k] * ld + seg * 2);
+                        else { dst[0] = 0.0; dst[1] = 0.0; }
+                    }
+                } else {                                                  // B panel: rows of K
+                    for (int t = tid; t < ROWS * (SKC / 2); t += NW * 32) {
+                        int row = t / (SKC / 2), seg = t % (SKC / 2);
+                        double* dst = &B[row * SLDA + seg * 2];
+                        if (row < ld && k0 + seg * 2 < m) cp_async16(dst, Kf + (size_t)row * ldK + k0 + seg * 2);
+                        else { dst[0] = 0.0; dst[1] = 0.0; }
+                    }
+                }
+            }
+            cp_async_commit();
+        };
+        stage(0); stage(1);
+        for (int c = 0; c < nch; ++c) {
+            cp_async_wait<SNST - 2>();
+            __syncthreads();
+            stage(c + 2);
+            const double* A = sms + (c % SNST) * STAGE;
+            const double* B = A + A_DOUBLES;
+#pragma unroll
+            for (int kk = 0; kk < SKC / 4; ++kk) {
+#pragma unroll
+                for (int it = 0; it < IPW; ++it) {
+                    if (bi[it] >= 0) {
+                        const double a0 = A[(bi[it] * 16 + r) * SLDA + kk * 4 + q];
+                        const double a1 = A[(bi[it] * 16 + 8 + r) * SLDA + kk * 4 + q];
+                        double b0, b1;
+                        if (phase == 0) { b0 = B[(kk * 4 + q) * SLDB + bj[it] * 16 + r]; b1 = B[(kk * 4 + q) * SLDB + bj[it] * 16 + 8 + r]; }
+                        else { b0 = B[(bj[it] * 16 + r) * SLDA + kk * 4 + q]; b1 = B[(bj[it] * 16 + 8 + r) * SLDA + kk * 4 + q]; }
+                        dmma884(c0[it][0], c1[it][0], -a0, b0);
+                        dmma884(c0[it][1], c1[it][1], -a0, b1);
+                        dmma884(c0[it][2], c1[it][2], -a1, b0);
+                        dmma884(c0[it][3], c1[it][3], -a1, b1);
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int it = 0; it < IPW; ++it) {
+        if (bi[it] < 0) continue;
+        const bool diag = bi[it] == bj[it];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int row = bi[it] * 16 + (t >> 1) * 8 + r, col = bj[it] * 16 + (t & 1) * 8 + 2 * q;
+            const double v0 = prune(c0[it][t]), v1 = prune(c1[it][t]);
+            if (row >= N) continue;
+            if (!diag) {
+                if (col + 1 < N) *reinterpret_cast<double2*>(Po + (size_t)row * ld + col) = make_double2(v0, v1);
+                else if (col < N) Po[(size_t)row * ld + col] = v0;
+                if (col < N) Po[(size_t)col * ld + row] = v0;
+                if (col + 1 < N) Po[(size_t)(col + 1) * ld + row] = v1;
+            } else {
+                if (col <= row) { Po[(size_t)row * ld + col] = v0; if (col != row) Po[(size_t)col * ld + row] = v0; }
+                if (col + 1 <= row) { Po[(size_t)row * ld + col + 1] = v1; if (col + 1 != row) Po[(size_t)(col + 1) * ld + row] = v1; }
+            }
+        }
+    }
+}
+
+template <int NW, int NBLK, int IPW>
+cudaError_t launch_joseph_sym_t(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st) {
+    constexpr int ROWS = NBLK * 16;
+    constexpr int A_DOUBLES = ROWS * SLDA;
+    constexpr int B_DOUBLES = (SKC * (ROWS + 4) > A_DOUBLES) ? SKC * (ROWS + 4) : A_DOUBLES;
+    const size_t sm = (size_t)SNST * (A_DOUBLES + B_DOUBLES) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ekf_joseph_sym<NW, NBLK, IPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    ekf_joseph_sym<NW, NBLK, IPW><<<p.F, NW * 32, sm, st>>>(p, Pin, Pout);
     return cudaGetLastError();
 }
 
@@ -574,16 +733,24 @@ cudaError_t launch_gain_tiled_t(const EkfPtrs& p, const double* Pin, const doubl
 namespace ekfvio {
 
 bool joseph_tiled_supported(const EkfPtrs& p) { return p.Nmax <= 256 && p.mmax <= 256; }
+bool joseph_sym_supported(const EkfPtrs& p) { return p.Nmax <= 176 && p.mmax <= 208; }
+
+// Symmetric filters only (p.asym[f] == 0); the others are left to launch_joseph_tiled.
+cudaError_t launch_joseph_sym(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st) {
+    if (p.Nmax <= 128) return launch_joseph_sym_t<9, 8, 4>(p, Pin, Pout, st);      // 36 blocks
+    return launch_joseph_sym_t<11, 11, 6>(p, Pin, Pout, st);                       // 66 blocks
+}
 
 bool gain_tiled_supported(const EkfPtrs& p) { return p.Nmax <= 176 && p.mmax <= 104 && p.L != nullptr; }
 size_t gain_tiled_scratch_doubles(int mmax) { int NB = mmax <= 64 ? 8 : 13; return (size_t)(NB * (NB + 1) / 2 + NB) * 64; }
 
-cudaError_t launch_gain_tiled(const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, cudaStream_t st) {
-    if (p.Nmax <= 128 && p.mmax <= 64) return launch_gain_tiled_t<8, 8>(p, Pin, z, R, pass, st);
-    return launch_gain_tiled_t<11, 13>(p, Pin, z, R, pass, st);
+// which = 0: Cholesky kernel, 1: solve kernel (two launches so the API layer can time them apart)
+cudaError_t launch_gain_tiled(int which, const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, cudaStream_t st) {
+    if (p.Nmax <= 128 && p.mmax <= 64) return launch_gain_tiled_t<8, 8>(which, p, Pin, z, R, pass, st);
+    return launch_gain_tiled_t<11, 13>(which, p, Pin, z, R, pass, st);
 }
 
-cudaError_t launch_joseph_tiled(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st) {
+cudaError_t launch_joseph_tiled(const EkfPtrs& p, const double* Pin, double* Pout, int only_asym, cudaStream_t st) {
     const int strips = (p.Nmax + 15) / 16;
     const size_t sm = (size_t)NST * BS_DOUBLES * sizeof(double);
     static bool configured = false;
@@ -594,9 +761,9 @@ cudaError_t launch_joseph_tiled(const EkfPtrs& p, const double* Pin, double* Pou
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    if (strips <= 8) ekf_joseph_tiled<8><<<p.F, 8 * 32, sm, st>>>(p, Pin, Pout);
-    else if (strips <= 11) ekf_joseph_tiled<11><<<p.F, 11 * 32, sm, st>>>(p, Pin, Pout);
-    else ekf_joseph_tiled<16><<<p.F, 16 * 32, sm, st>>>(p, Pin, Pout);
+    if (strips <= 8) ekf_joseph_tiled<8><<<p.F, 8 * 32, sm, st>>>(p, Pin, Pout, only_asym);
+    else if (strips <= 11) ekf_joseph_tiled<11><<<p.F, 11 * 32, sm, st>>>(p, Pin, Pout, only_asym);
+    else ekf_joseph_tiled<16><<<p.F, 16 * 32, sm, st>>>(p, Pin, Pout, only_asym);
     return cudaGetLastError();
 }
 

@@ -126,7 +126,8 @@ int ekfvio_batch_get_view(ekfvio_batch* b, ekfvio_batch_view* view);
 long long ekfvio_batch_launch_count(const ekfvio_batch* b);
 
 /* Per-kernel device timing (CUDA events on the launching stream) for the roofline report.
- * Slots: 0 process, 1 gain (S, factorisation, K, W, state), 2 covariance (Joseph) update.
+ * Slots: 0 process, 1 gain part 1 (measurement map, S, factorisation; the whole gain on the
+ * general path), 2 covariance (Joseph) update, 3 gain part 2 (K, W, state update; tiled path).
  * get_timing synchronises, then returns accumulated milliseconds and launch counts (8 slots). */
 int ekfvio_batch_enable_timing(ekfvio_batch* b, int on);
 int ekfvio_batch_get_timing(ekfvio_batch* b, double* ms8, long long* count8);
