@@ -114,8 +114,8 @@ __device__ void linearize_block(const ProcSmem& s, int n, double dt, const doubl
 
 // process(dt) — TightlyCoupledEKF.cpp:96-121.  mode 0: full step (state + covariance).
 // mode 1: linearize only (dense F written to F_out, state untouched except the dq cache).
-__global__ void __launch_bounds__(PT) ekf_process_general(EkfPtrs p, const double* __restrict__ Pin, double* __restrict__ Pout,
-                                                          const double* __restrict__ dts, int mode, double* __restrict__ F_out) {
+__global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const double* __restrict__ Pin, double* __restrict__ Pout,
+                                                          const double* __restrict__ dts, int mode, double* __restrict__ F_out, int fused) {
     extern __shared__ double sm[];
     const int f = blockIdx.x, tid = threadIdx.x;
     const int n = p.nfeat[f], N = BASE + 3 * n;
@@ -165,9 +165,127 @@ __global__ void __launch_bounds__(PT) ekf_process_general(EkfPtrs p, const doubl
         for (int i = 0; i < 22; ++i) mu_g[i] = o[i];
     }
 
-    // Sigma' = F Sigma F' + Q, two passes through T = F Sigma held in Pout.
     const double* Pi = Pin + (size_t)f * ld * ld;
     double* Po = Pout + (size_t)f * ld * ld;
+    if (fused) {
+        // Sigma' = F Sigma F' + Q fused by row blocks: a warp takes three rows I of F, forms
+        // T = F(I,:) Sigma (3 x N) in its slice of shared memory, then Sigma'(I,:) = T F'.
+        // Sigma is read once and written once.  Rows 7..15 of Sigma (needed by every feature block)
+        // are staged once per CTA; a warp's own three rows arrive by cp.async one task ahead.
+        const int Np = (N + 3) & ~3;
+        const int Npm = ((BASE + 3 * p.nmax) + 3) & ~3;
+        double* Pb = sm + ProcSmem::doubles(p.nmax);          // [9][Np]: rows 7..15
+        const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+        double* Tw = Pb + 9 * (size_t)Npm + (size_t)warp * 6 * Npm;   // [3][Np]
+        double* Own = Tw + 3 * (size_t)Npm;                           // [3][Np]
+        for (int e = tid; e < 9 * N; e += blockDim.x) { int k = e / N, c = e - k * N; Pb[k * Np + c] = Pi[(size_t)(7 + k) * ld + c]; }
+        const int ntask = 8 + n;
+        auto prefetch = [&](int t) {
+            if (t >= 8 && t < ntask) {
+                const double* own = Pi + (size_t)(BASE + 3 * (t - 8)) * ld;
+                for (int e = lane; e < 3 * (Np / 2); e += 32) {
+                    int r = e / (Np / 2), c2 = (e - r * (Np / 2)) * 2;
+                    unsigned dst = (unsigned)__cvta_generic_to_shared(Own + r * Np + c2);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(own + (size_t)r * ld + c2) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        prefetch(warp + nw);            // tasks 0..7 are the base-row tasks, one per warp in the first round
+        __syncthreads();
+        for (int t = warp; t < ntask; t += nw) {
+            const bool base_task = t < 8;
+            const int fi = t - 8;
+            const int r0 = base_task ? 3 * t : BASE + 3 * fi;
+            const int nr = base_task ? min(3, BASE - r0) : 3;
+            // pass 1: T(r, c), lanes over columns
+            if (base_task) {
+                for (int c = lane; c < N; c += 32) {
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 22; ++k) {
+                        double pv = Pi[(size_t)k * ld + c];
+                        a0 += s.A[r0 * 23 + k] * pv;
+                        if (nr > 1) a1 += s.A[(r0 + 1) * 23 + k] * pv;
+                        if (nr > 2) a2 += s.A[(r0 + 2) * 23 + k] * pv;
+                    }
+                    Tw[c] = a0; Tw[Np + c] = a1; Tw[2 * Np + c] = a2;
+                }
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+                double bb[27], dd[9];
+#pragma unroll
+                for (int k = 0; k < 27; ++k) bb[k] = s.B[fi * 27 + k];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) dd[k] = s.D[fi * 9 + k];
+                for (int c = lane; c < N; c += 32) {
+                    double o0 = Own[c], o1 = Own[Np + c], o2 = Own[2 * Np + c];
+                    double a0 = dd[0] * o0 + dd[1] * o1 + dd[2] * o2;
+                    double a1 = dd[3] * o0 + dd[4] * o1 + dd[5] * o2;
+                    double a2 = dd[6] * o0 + dd[7] * o1 + dd[8] * o2;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        double pv = Pb[k * Np + c];
+                        a0 += bb[k] * pv; a1 += bb[9 + k] * pv; a2 += bb[18 + k] * pv;
+                    }
+                    Tw[c] = a0; Tw[Np + c] = a1; Tw[2 * Np + c] = a2;
+                }
+            }
+            __syncwarp();
+            if (!base_task) prefetch(t + nw);   // Own is free again; overlaps with pass 2
+            // pass 2: Sigma'(r, :) = T(r, :) F', lanes over base columns, then over feature blocks
+            if (lane < BASE) {
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 22; ++k) {
+                    double av = s.A[lane * 23 + k];
+                    a0 += Tw[k] * av; a1 += Tw[Np + k] * av; a2 += Tw[2 * Np + k] * av;
+                }
+                if (r0 == lane) a0 += process_noise_diag(lane, dt);
+                if (r0 + 1 == lane) a1 += process_noise_diag(lane, dt);
+                if (r0 + 2 == lane) a2 += process_noise_diag(lane, dt);
+                Po[(size_t)r0 * ld + lane] = prune(a0);
+                if (nr > 1) Po[(size_t)(r0 + 1) * ld + lane] = prune(a1);
+                if (nr > 2) Po[(size_t)(r0 + 2) * ld + lane] = prune(a2);
+            }
+            {
+                double tb[3][9];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) tb[r][k] = Tw[r * Np + 7 + k];
+                for (int fj = lane; fj < n; fj += 32) {
+                    double t3[3][3];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) t3[r][q] = Tw[r * Np + BASE + 3 * fj + q];
+#pragma unroll
+                    for (int c2 = 0; c2 < 3; ++c2) {
+                        const double* bj = s.B + (3 * fj + c2) * 9;
+                        const double* dj = s.D + fj * 9 + c2 * 3;
+                        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) { double bv = bj[k]; a0 += tb[0][k] * bv; a1 += tb[1][k] * bv; a2 += tb[2][k] * bv; }
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) { double dv = dj[q]; a0 += t3[0][q] * dv; a1 += t3[1][q] * dv; a2 += t3[2][q] * dv; }
+                        const int j = BASE + 3 * fj + c2;
+                        if (r0 == j) a0 += process_noise_diag(j, dt);
+                        if (r0 + 1 == j) a1 += process_noise_diag(j, dt);
+                        if (r0 + 2 == j) a2 += process_noise_diag(j, dt);
+                        Po[(size_t)r0 * ld + j] = prune(a0);
+                        if (nr > 1) Po[(size_t)(r0 + 1) * ld + j] = prune(a1);
+                        if (nr > 2) Po[(size_t)(r0 + 2) * ld + j] = prune(a2);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        return;
+    }
+    // large states: Sigma' = F Sigma F' + Q in two passes through T = F Sigma held in Pout.
     // pass 1: thread (column c, row group g) — the 22 base entries of column c stay in registers
     {
         const int CW = 64, G = PT / CW;
@@ -547,16 +665,23 @@ __global__ void ekf_accumulate_errors_kernel(EkfPtrs p, const double* __restrict
 namespace ekfvio {
 
 static size_t proc_smem_bytes(int nmax) { return ProcSmem::doubles(nmax) * sizeof(double); }
+// fused covariance pass: + rows 7..15 of Sigma + a 3-row T slice and a 3-row prefetch slice per warp
+static size_t proc_fused_smem_bytes(int nmax) {
+    size_t Np = ((size_t)(BASE + 3 * nmax) + 3) & ~(size_t)3;
+    return proc_smem_bytes(nmax) + (9 + 6 * (PT / 32)) * Np * sizeof(double);
+}
 
 cudaError_t launch_process_general(const EkfPtrs& p, const double* Pin, double* Pout, const double* dts, int mode, double* F_out, cudaStream_t st) {
     size_t sm = proc_smem_bytes(p.nmax);
+    const int fused = (mode == 0 && proc_fused_smem_bytes(p.nmax) <= 110 * 1024) ? 1 : 0;   // two CTAs per SM
+    if (fused) sm = proc_fused_smem_bytes(p.nmax);
     static size_t configured = 0;
     if (sm > 48 * 1024 && sm > configured) {
         cudaError_t e = cudaFuncSetAttribute(ekf_process_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
         configured = sm;
     }
-    ekf_process_general<<<p.F, PT, sm, st>>>(p, Pin, Pout, dts, mode, F_out);
+    ekf_process_general<<<p.F, PT, sm, st>>>(p, Pin, Pout, dts, mode, F_out, fused);
     return cudaGetLastError();
 }
 

@@ -21,6 +21,13 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// A global load the compiler may not sink below later volatile asm (the DMMAs): keeps software
+// prefetches one block ahead of their use.
+__device__ __forceinline__ double ldg_pinned(const double* p) {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 constexpr int JT = 11;              // column tiles per pass
@@ -235,24 +242,36 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
     const int r = lane >> 2, q = lane & 3;
 
     // lower(a,b), a >= b  <-  upper(S)(b,a) = Sigma(idx[b], idx[a]) + R(b,a)  (SimplicialLDLT::compute(S')
-    // reads upper(S), :578); identity tail
-    for (int e = tid; e < nb * (nb + 1) / 2 * 64; e += 128) {
-        int t = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
-        int ib = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
-        while (ib * (ib + 1) / 2 > t) --ib;
-        while ((ib + 1) * (ib + 2) / 2 <= t) ++ib;
-        int jb = t - ib * (ib + 1) / 2;
-        int a = ib * 8 + rr, b = jb * 8 + cc;
-        double v = 0.0;
-        if (a >= b) {
-            if (a < m) {
-                v = Pi[(size_t)s_idx[b] * ld + s_idx[a]];
-                if ((a >> 1) == (b >> 1)) v += Rf[4 * ((s_idx[a] - BASE) / 3) + (b & 1) * 2 + (a & 1)];
-            } else {
-                v = (a == b) ? 1.0 : 0.0;
+    // reads upper(S), :578); identity tail.  Four independent gathers in flight per thread.
+    {
+        const int total = nb * (nb + 1) / 2 * 64;
+        for (int e0 = tid; e0 < total; e0 += 128 * 4) {
+            double v[4]; int o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int e = e0 + u * 128;
+                v[u] = 0.0; o[u] = -1;
+                if (e < total) {
+                    int t = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
+                    int ib = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
+                    while (ib * (ib + 1) / 2 > t) --ib;
+                    while ((ib + 1) * (ib + 2) / 2 <= t) ++ib;
+                    int jb = t - ib * (ib + 1) / 2;
+                    int a = ib * 8 + rr, b = jb * 8 + cc;
+                    o[u] = t * 64 + tsw(rr, cc);
+                    if (a >= b) {
+                        if (a < m) {
+                            v[u] = Pi[(size_t)s_idx[b] * ld + s_idx[a]];
+                            if ((a >> 1) == (b >> 1)) v[u] += Rf[4 * ((s_idx[a] - BASE) / 3) + (b & 1) * 2 + (a & 1)];
+                        } else {
+                            v[u] = (a == b) ? 1.0 : 0.0;
+                        }
+                    }
+                }
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (o[u] >= 0) Ls[o[u]] = v[u];
         }
-        Ls[t * 64 + tsw(rr, cc)] = v;
     }
     __syncthreads();
 
@@ -264,12 +283,15 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
 #pragma unroll
             for (int c = 0; c < 8; ++c) a[c] = T[tsw(rr, c)];
             bool bad = false;
+            double rd[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 double dcc = __shfl_sync(0xffffffffu, a[c], c);
                 if (!(dcc > 0.0)) bad = true;
                 double piv = sqrt(dcc);
-                if (rr == c) a[c] = piv; else if (rr > c) a[c] = a[c] / piv;
+                double rpiv = 1.0 / piv;       // one reciprocal per column instead of a division per row
+                rd[c] = rpiv;
+                if (rr == c) a[c] = piv; else if (rr > c) a[c] = a[c] * rpiv;
 #pragma unroll
                 for (int c2 = c + 1; c2 < 8; ++c2) {
                     double l = __shfl_sync(0xffffffffu, a[c], c2);
@@ -283,7 +305,7 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
                 double sacc = (i == rr) ? 1.0 : 0.0;
 #pragma unroll
                 for (int k = 0; k < i; ++k) sacc -= __shfl_sync(0xffffffffu, a[k], i) * x[k];
-                x[i] = sacc / __shfl_sync(0xffffffffu, a[i], i);
+                x[i] = sacc * rd[i];
             }
             if (lane < 8) {
 #pragma unroll
@@ -348,6 +370,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
     double* Ss = Li + NB * 64;             // NB*NB tiles: the full (possibly asymmetric) S
     double* s_y = Ss + NB * NB * 64;       // NB*8
     int* s_idx = reinterpret_cast<int*>(s_y + NB * 8);   // NB*8
+    __shared__ short s_inv[NW * 16];
 
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m = p.m[f];
@@ -374,33 +397,13 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
         for (int a = tid; a < NB * 8; a += NW * 32) { s_idx[a] = a < m ? idx_g[a] : 0; s_y[a] = a < m ? y_g[a] : 0.0; }
     }
     __syncthreads();
-    // Ss: full S = Sigma(idx,idx) + R as NB x NB tiles (identity tail); no symmetry assumed
-    for (int e0 = tid; e0 < nb * nb * 64; e0 += NW * 32 * 4) {
-        double v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            int e = e0 + u * NW * 32;
-            int t = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
-            int ta = t / nb, tb = t - ta * nb;
-            int a = ta * 8 + rr, b = tb * 8 + cc;
-            v[u] = 0.0;
-            if (e < nb * nb * 64) {
-                if (a < m && b < m) v[u] = Pi[(size_t)s_idx[a] * ld + s_idx[b]];
-                else v[u] = (a == b) ? 1.0 : 0.0;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            int e = e0 + u * NW * 32;
-            if (e < nb * nb * 64) {
-                int t = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
-                int ta = t / nb, tb = t - ta * nb;
-                int a = ta * 8 + rr, b = tb * 8 + cc;
-                double x = v[u];
-                if (a < m && b < m && (a >> 1) == (b >> 1)) x += Rf[4 * ((s_idx[a] - BASE) / 3) + (a & 1) * 2 + (b & 1)];
-                Ss[(ta * NB + tb) * 64 + tsw(rr, cc)] = x;
-            }
-        }
+    // inverse measurement map: state row -> measurement index (or -1); identity tail rows of Ss
+    for (int i = tid; i < ld; i += NW * 32) s_inv[i] = -1;
+    __syncthreads();
+    for (int a = tid; a < m; a += NW * 32) s_inv[s_idx[a]] = a;
+    for (int e = tid; e < (nb * 8 - m) * nb * 8; e += NW * 32) {
+        int a = m + e / (nb * 8), b = e % (nb * 8);
+        Ss[((a >> 3) * NB + (b >> 3)) * 64 + tsw(a & 7, b & 7)] = (a == b) ? 1.0 : 0.0;
     }
     cp_async_wait<0>();
     __syncthreads();
@@ -417,6 +420,21 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
                 bool ok = row < N && a < m && jb < nb;
                 k0[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a]] : 0.0;
                 k1[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a + 1]] : 0.0;
+            }
+            // a measured state row of Sigma(:,idx) is a row of S = Sigma(idx,idx) + R: the full S (no
+            // symmetry assumed) is assembled from the strips instead of being gathered a second time
+            const int am = row < N ? s_inv[row] : -1;
+            if (am >= 0) {
+                const double* rr = Rf + 4 * ((row - BASE) / 3) + (am & 1) * 2;
+#pragma unroll
+                for (int jb = 0; jb < NB; ++jb) {
+                    if (jb < nb) {
+                        int b = jb * 8 + 2 * q;
+                        double v0 = k0[rt][jb], v1 = k1[rt][jb];
+                        if (b == (am & ~1)) { v0 += rr[0]; v1 += rr[1]; }
+                        *reinterpret_cast<double2*>(&Ss[((am >> 3) * NB + jb) * 64 + tsw(am & 7, 2 * q)]) = make_double2(v0, v1);
+                    }
+                }
             }
         }
         // forward: Z L' = C
@@ -499,7 +517,9 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
             dot += __shfl_xor_sync(0xffffffffu, dot, 2);
             if (q == 0 && row < N) { if (row < BASE) mu_g[row] += dot; else feat_g[row - BASE] += dot; }
         }
-        __syncwarp();
+    }
+    __syncthreads();   // every strip has contributed its rows of S, and K is in global memory
+    if (i0 < N) {
         // W = Sigma(:,idx) - K S with the full S
         double w0[2][NB], w1[2][NB];
 #pragma unroll
@@ -516,10 +536,13 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
         const int rowa = min(i0 + r, ld - 1), rowb = min(i0 + 8 + r, ld - 1);
         const double* kra = Kf + (size_t)rowa * ldK + q;
         const double* krb = Kf + (size_t)rowb * ldK + q;
-        double ka[2][2] = {{kra[0], kra[4]}, {krb[0], krb[4]}};
+        double ka[2][2] = {{ldg_pinned(kra), ldg_pinned(kra + 4)}, {ldg_pinned(krb), ldg_pinned(krb + 4)}};
         for (int kb = 0; kb < nb; ++kb) {
             double kn[2][2] = {{0, 0}, {0, 0}};
-            if (kb + 1 < nb) { kn[0][0] = kra[(kb + 1) * 8]; kn[0][1] = kra[(kb + 1) * 8 + 4]; kn[1][0] = krb[(kb + 1) * 8]; kn[1][1] = krb[(kb + 1) * 8 + 4]; }
+            if (kb + 1 < nb) {   // issued before this block's DMMAs (volatile asm keeps program order)
+                kn[0][0] = ldg_pinned(kra + (kb + 1) * 8); kn[0][1] = ldg_pinned(kra + (kb + 1) * 8 + 4);
+                kn[1][0] = ldg_pinned(krb + (kb + 1) * 8); kn[1][1] = ldg_pinned(krb + (kb + 1) * 8 + 4);
+            }
 #pragma unroll
             for (int j2 = 0; j2 < NB; ++j2) {
                 if (j2 < nb) {
