@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libekfvio_b200.so")
+LIB_PATH = os.environ.get("EKFVIO_LIB_PATH") or os.path.join(_HERE, "libekfvio_b200.so")   # override: kernel experiments only
 
 
 class EkfvioError(RuntimeError):

@@ -72,7 +72,7 @@ int ekfvio_batch_create(ekfvio_batch** out, int device, int num_filters, int max
     b->Nmax = BASE + 3 * max_features;
     b->ldP = (b->Nmax + 7) / 8 * 8;
     b->mmax = 2 * max_features > 0 ? 2 * max_features : 2;
-    b->ldK = (b->mmax + 7) / 8 * 8 + 4;   // == 4 (mod 8): conflict-free DMMA fragment loads from shared memory
+    b->ldK = (b->mmax + 15) / 16 * 16;    // K / W panels are chunk-major in 16-column chunks (kw_at)
     if (params) b->prm = *params; else ekfvio_default_params(&b->prm);
     size_t F = b->F, nm = b->nmax > 0 ? b->nmax : 1;
     size_t Pbytes = F * b->ldP * b->ldP * sizeof(double), Kbytes = F * b->ldP * b->ldK * sizeof(double);

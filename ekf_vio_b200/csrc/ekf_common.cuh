@@ -97,6 +97,13 @@ __device__ __forceinline__ void convolve_feature(const Q4& dqi, const V3& vel, c
     out3[2] = 1.0 / z;
 }
 
+// Gain (K) and Joseph residual (W) panels are stored chunk-major: element (row, k) of a filter sits
+// at (k/16) * ldP*16 + row*16 + k%16, i.e. each 16-column k-chunk of all rows is one contiguous
+// block — the unit the covariance update streams through shared memory.  ldK = 16 * #chunks.
+__host__ __device__ __forceinline__ size_t kw_at(int ldP, int row, int k) {
+    return (size_t)(k >> 4) * ldP * 16 + (size_t)row * 16 + (k & 15);
+}
+
 __device__ __forceinline__ double prune(double v) { return (fabs(v) > PRUNE_LIMIT) ? v : 0.0; }
 
 // Diagonal of Q*dt (generateProcessNoise, TightlyCoupledEKF.cpp:123-174).
@@ -111,7 +118,11 @@ __device__ __forceinline__ double process_noise_diag(int i, double dt) {
 // FP64 tensor-core tile: D(8x8) += A(8x4) * B(4x8).  Fragments (PTX ISA, mma.m8n8k4.f64):
 //   a : A[row = lane/4][k = lane%4]          b : B[k = lane%4][col = lane/4]
 //   c0,c1 : C[row = lane/4][col = 2*(lane%4) + {0,1}]
+// (not volatile: the scheduler is free to interleave fragment loads of the next tile with these)
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void dmma884_volatile(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
@@ -134,8 +145,8 @@ struct ekfvio_batch {
     int* d_status = nullptr;       // [F]
     // scratch
     double* d_dt = nullptr;        // [F]
-    double* d_K = nullptr;         // [F][ldP][ldK]   gain
-    double* d_W = nullptr;         // [F][ldP][ldK]   Joseph residual panel
+    double* d_K = nullptr;         // [F][ldK/16][ldP][16]   gain, chunk-major (kw_at)
+    double* d_W = nullptr;         // [F][ldK/16][ldP][16]   Joseph residual panel
     double* d_S = nullptr;         // [F][mmax][mmax] (general path only; lazily allocated)
     double* d_L = nullptr;         // [F][tiles] Cholesky factor + inverse diagonal tiles (tiled path)
     double* d_y = nullptr;         // [F][mmax]

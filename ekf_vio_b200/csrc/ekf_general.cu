@@ -440,24 +440,25 @@ __global__ void __launch_bounds__(PT) ekf_gain_general(EkfPtrs p, const double* 
     if (tid == 0 && s_bad) atomicOr(&p.status[f], 1);
     // K row by row: K(i,:) = S^-1 Sigma(i, idx)  (:580), entries <= 1e-13 dropped (sparseView)
     for (int i = tid; i < N; i += blockDim.x) {
-        double* w = Kf + (size_t)i * ldK;
+#define KROW(a) Kf[kw_at(ld, i, (a))]
         const double* prow = Pi + (size_t)i * ld;
-        for (int a = 0; a < m; ++a) w[a] = prow[idx[a]];
+        for (int a = 0; a < m; ++a) KROW(a) = prow[idx[a]];
         for (int a = 0; a < m; ++a) {
-            double v = w[a];
+            double v = KROW(a);
             const double* l = Lw + (size_t)a * m;
-            for (int k = 0; k < a; ++k) v -= l[k] * w[k];
-            w[a] = v;
+            for (int k = 0; k < a; ++k) v -= l[k] * KROW(k);
+            KROW(a) = v;
         }
-        for (int a = 0; a < m; ++a) w[a] /= Lw[(size_t)a * m + a];
+        for (int a = 0; a < m; ++a) KROW(a) /= Lw[(size_t)a * m + a];
         for (int a = m - 1; a >= 0; --a) {
-            double v = w[a];
-            for (int k = a + 1; k < m; ++k) v -= Lw[(size_t)k * m + a] * w[k];
-            w[a] = v;
+            double v = KROW(a);
+            for (int k = a + 1; k < m; ++k) v -= Lw[(size_t)k * m + a] * KROW(k);
+            KROW(a) = v;
         }
         double dot = 0.0;
-        for (int a = 0; a < m; ++a) { double k = prune(w[a]); w[a] = k; dot += k * y[a]; }
-        for (int a = m; a < ldK; ++a) w[a] = 0.0;
+        for (int a = 0; a < m; ++a) { double k = prune(KROW(a)); KROW(a) = k; dot += k * y[a]; }
+        for (int a = m; a < ldK; ++a) KROW(a) = 0.0;
+#undef KROW
         // mu += K y  (:600)
         if (i < BASE) mu_g[i] += dot; else feat_g[i - BASE] += dot;
     }
@@ -466,19 +467,17 @@ __global__ void __launch_bounds__(PT) ekf_gain_general(EkfPtrs p, const double* 
     {
         const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
         for (int i = warp; i < N; i += nw) {
-            const double* k = Kf + (size_t)i * ldK;
-            double* w = Wf + (size_t)i * ldK;
             for (int b = lane; b < ldK; b += 32) {
                 double acc = 0.0;
                 if (b < m) {
                     int jb = idx[b];
                     acc = Pi[(size_t)i * ld + jb];
-                    for (int a = 0; a < m; ++a) acc -= k[a] * Pi[(size_t)idx[a] * ld + jb];
+                    for (int a = 0; a < m; ++a) acc -= Kf[kw_at(ld, i, a)] * Pi[(size_t)idx[a] * ld + jb];
                     const double* r = Rf + 4 * ((jb - BASE) / 3);
                     int b0 = b & ~1;
-                    acc -= k[b0] * r[b & 1] + k[b0 + 1] * r[2 + (b & 1)];
+                    acc -= Kf[kw_at(ld, i, b0)] * r[b & 1] + Kf[kw_at(ld, i, b0 + 1)] * r[2 + (b & 1)];
                 }
-                w[b] = acc;
+                Wf[kw_at(ld, i, b)] = acc;
             }
         }
     }
@@ -514,7 +513,7 @@ __global__ void __launch_bounds__(256) ekf_joseph_general(EkfPtrs p, const doubl
         for (int k0 = 0; k0 < m; k0 += 16) {
             for (int e = tid; e < 32 * 16; e += 256) {
                 int r = e / 16, k = e % 16;
-                As[r][k] = (i0 + r < N && k0 + k < m) ? Am[(size_t)(i0 + r) * ldK + k0 + k] : 0.0;
+                As[r][k] = (i0 + r < N && k0 + k < m) ? Am[kw_at(ld, i0 + r, k0 + k)] : 0.0;
             }
             if (phase == 0) {  // B(k, j) = Sigma(idx[k], j)
                 for (int e = tid; e < 16 * 32; e += 256) {
@@ -524,7 +523,7 @@ __global__ void __launch_bounds__(256) ekf_joseph_general(EkfPtrs p, const doubl
             } else {           // B(k, j) = K(j, k)
                 for (int e = tid; e < 16 * 32; e += 256) {
                     int c = e / 16, k = e % 16;
-                    Bs[k][c] = (j0 + c < N && k0 + k < m) ? Kf[(size_t)(j0 + c) * ldK + k0 + k] : 0.0;
+                    Bs[k][c] = (j0 + c < N && k0 + k < m) ? Kf[kw_at(ld, j0 + c, k0 + k)] : 0.0;
                 }
             }
             __syncthreads();

@@ -73,8 +73,8 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const 
             }
         for (int phase = 0; phase < 2; ++phase) {
             const double* Am = phase == 0 ? Kf : Wf;
-            const double* A0 = Am + (size_t)row0 * ldK + q;
-            const double* A1 = Am + (size_t)row1 * ldK + q;
+            const double* A0 = Am + (size_t)row0 * 16 + q;   // + chunk * ld*16 (chunk-major panels, KC == 16)
+            const double* A1 = Am + (size_t)row1 * 16 + q;
             auto stage = [&](int c) {
                 double* B = Bs_all + (c % NST) * BS_DOUBLES;
                 const int k0 = c * KC;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const 
                         for (int t = tid; t < JT * 8 * (KC / 2); t += NW * 32) {
                             int col = t / (KC / 2), seg = t % (KC / 2);
                             double* dst = &B[col * LDK + seg * 2];
-                            if (j0 + col < ld && k0 + seg * 2 < m) cp_async16(dst, Kf + (size_t)(j0 + col) * ldK + k0 + seg * 2);   // m is even; k >= m must read as zero
+                            if (j0 + col < ld && k0 + seg * 2 < m) cp_async16(dst, Kf + kw_at(ld, j0 + col, k0 + seg * 2));   // m is even; k >= m must read as zero
                             else { dst[0] = 0.0; dst[1] = 0.0; }
                         }
                     }
@@ -103,8 +103,8 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const 
 #pragma unroll
                 for (int kk = 0; kk < KC / 4; ++kk) {
                     bool ok = active && c < nch && k0 + kk * 4 + q < ldK;
-                    a[0][kk] = ok ? A0[k0 + kk * 4] : 0.0;
-                    a[1][kk] = ok ? A1[k0 + kk * 4] : 0.0;
+                    a[0][kk] = ok ? A0[(size_t)c * ld * 16 + kk * 4] : 0.0;
+                    a[1][kk] = ok ? A1[(size_t)c * ld * 16 + kk * 4] : 0.0;
                 }
             };
             double a_cur[2][KC / 4], a_nxt[2][KC / 4];
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
                 if (jb < nb) {
                     double a = prune(k0[rt][jb]), b = prune(k1[rt][jb]);
                     dot += a * s_y[jb * 8 + 2 * q] + b * s_y[jb * 8 + 2 * q + 1];
-                    if (row < ld) *reinterpret_cast<double2*>(Kf + (size_t)row * ldK + jb * 8 + 2 * q) = make_double2(a, b);
+                    if (row < ld) *reinterpret_cast<double2*>(Kf + kw_at(ld, row, jb * 8 + 2 * q)) = make_double2(a, b);
                 }
             }
             dot += __shfl_xor_sync(0xffffffffu, dot, 1);
@@ -534,14 +534,16 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
             }
         }
         const int rowa = min(i0 + r, ld - 1), rowb = min(i0 + 8 + r, ld - 1);
-        const double* kra = Kf + (size_t)rowa * ldK + q;
-        const double* krb = Kf + (size_t)rowb * ldK + q;
+        const double* kra = Kf + (size_t)rowa * 16 + q;   // block kb: + (kb/2) * ld*16 + (kb%2) * 8
+        const double* krb = Kf + (size_t)rowb * 16 + q;
+        const size_t cst = (size_t)ld * 16;
         double ka[2][2] = {{ldg_pinned(kra), ldg_pinned(kra + 4)}, {ldg_pinned(krb), ldg_pinned(krb + 4)}};
         for (int kb = 0; kb < nb; ++kb) {
             double kn[2][2] = {{0, 0}, {0, 0}};
             if (kb + 1 < nb) {   // issued before this block's DMMAs (volatile asm keeps program order)
-                kn[0][0] = ldg_pinned(kra + (kb + 1) * 8); kn[0][1] = ldg_pinned(kra + (kb + 1) * 8 + 4);
-                kn[1][0] = ldg_pinned(krb + (kb + 1) * 8); kn[1][1] = ldg_pinned(krb + (kb + 1) * 8 + 4);
+                const size_t o = (size_t)((kb + 1) >> 1) * cst + ((kb + 1) & 1) * 8;
+                kn[0][0] = ldg_pinned(kra + o); kn[0][1] = ldg_pinned(kra + o + 4);
+                kn[1][0] = ldg_pinned(krb + o); kn[1][1] = ldg_pinned(krb + o + 4);
             }
 #pragma unroll
             for (int j2 = 0; j2 < NB; ++j2) {
@@ -562,7 +564,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
             const int row = i0 + rt * 8 + r;
 #pragma unroll
             for (int jb = 0; jb < NB; ++jb)
-                if (jb < nb && row < ld) *reinterpret_cast<double2*>(Wf + (size_t)row * ldK + jb * 8 + 2 * q) = make_double2(w0[rt][jb], w1[rt][jb]);
+                if (jb < nb && row < ld) *reinterpret_cast<double2*>(Wf + kw_at(ld, row, jb * 8 + 2 * q)) = make_double2(w0[rt][jb], w1[rt][jb]);
         }
     }
     __syncthreads();
@@ -592,6 +594,12 @@ cudaError_t launch_gain_tiled_t(int which, const EkfPtrs& p, const double* Pin, 
     return cudaGetLastError();
 }
 
+#ifdef EKFVIO_PROFILE_CLOCKS
+__device__ unsigned long long g_clk[8];
+#define CLK_MARK(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(&g_clk[i], (unsigned long long)(t_ - t_prev)); t_prev = t_; } } while (0)
+#else
+#define CLK_MARK(i) do {} while (0)
+#endif
 // ---------------------------------------------------------------------------------------------
 // ekf_joseph_sym: the covariance update for filters whose Sigma and R are symmetric (the normal
 // case; p.asym[f] == 0).  Only the 16x16 blocks on or below the diagonal are computed —
@@ -612,127 +620,183 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
     constexpr int A_DOUBLES = ROWS * SLDA;
     constexpr int B_DOUBLES = (SKC * SLDB > A_DOUBLES) ? SKC * SLDB : A_DOUBLES;
     constexpr int STAGE = A_DOUBLES + B_DOUBLES;
-    extern __shared__ __align__(16) double sms[];
-    __shared__ int s_idx[2 * 104];
-    const int f = blockIdx.x;
-    if (p.asym[f] != 0) return;                           // handled by ekf_joseph_tiled
+    constexpr int TLD = 10;                              // per-warp 8x8 transpose tile, padded
+    extern __shared__ __align__(16) double sms[];        // SNST stages | NW transpose tiles
+    __shared__ int s_idx[2][2 * 104];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = p.nfeat[f], N = BASE + 3 * n, m = p.m[f];
-    const int ld = p.ldP, ldK = p.ldK;
-    const double* Pi = Pin + (size_t)f * ld * ld;
-    double* Po = Pout + (size_t)f * ld * ld;
-    const double* Kf = p.K + (size_t)f * ld * ldK;
-    const double* Wf = p.W + (size_t)f * ld * ldK;
-    const int* idx = p.idx + (size_t)f * p.mmax;
-    for (int i = tid; i < m; i += NW * 32) s_idx[i] = idx[i];
-    __syncthreads();
-
     const int r = lane >> 2, q = lane & 3;
-    const int nblk = (N + 15) >> 4, nitems = nblk * (nblk + 1) / 2, nch = (m + SKC - 1) / SKC;
-    int bi[IPW], bj[IPW];
-    double c0[IPW][4], c1[IPW][4];                        // tile t = rt*2 + ct of the 16x16 block
-#pragma unroll
-    for (int it = 0; it < IPW; ++it) {
-        int e = warp + it * NW;
-        bool ok = e < nitems;
-        int i = 0, j = 0;
-        if (ok) {
-            i = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
-            while (i * (i + 1) / 2 > e) --i;
-            while ((i + 1) * (i + 2) / 2 <= e) ++i;
-            j = e - i * (i + 1) / 2;
-        }
-        bi[it] = ok ? i : -1; bj[it] = j;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            double2 v = make_double2(0.0, 0.0);
-            int row = i * 16 + (t >> 1) * 8 + r, col = j * 16 + (t & 1) * 8 + 2 * q;
-            if (ok && row < ld && col < ld) v = *reinterpret_cast<const double2*>(Pi + (size_t)row * ld + col);
-            c0[it][t] = v.x; c1[it][t] = v.y;
-        }
-    }
+    const int ld = p.ldP, ldK = p.ldK;
+    double* tw = sms + SNST * STAGE + warp * 8 * TLD;
 
-#pragma unroll
-    for (int phase = 0; phase < 2; ++phase) {
-        const double* Am = phase == 0 ? Kf : Wf;
-        auto stage = [&](int c) {
-            if (c < nch) {
-                double* A = sms + (c % SNST) * STAGE;
-                double* B = A + A_DOUBLES;
-                const int k0 = c * SKC;
-                for (int t = tid; t < ROWS * (SKC / 2); t += NW * 32) {   // A panel: rows of K or W
-                    int row = t / (SKC / 2), seg = t % (SKC / 2);
-                    double* dst = &A[row * SLDA + seg * 2];
-                    if (row < ld && k0 + seg * 2 < m) cp_async16(dst, Am + (size_t)row * ldK + k0 + seg * 2);
+    // Persistent CTA: filters f = blockIdx.x, blockIdx.x + gridDim.x, ...  The cp.async stage stream
+    // runs on across the two phases of a filter and into the next filter, so the pipeline never
+    // drains: while a filter's result is being stored, the first panels of the next one are in flight.
+    struct Meta { int f, N, m, nch, nv; const double* Pi; const double* Kf; const double* Wf; };
+    auto meta = [&](int f) {
+        Meta M; M.f = f;
+        if (f < p.F && p.asym[f] == 0) {
+            M.N = BASE + 3 * p.nfeat[f]; M.m = p.m[f];
+        } else { M.N = 0; M.m = 0; }                        // nothing to do (asymmetric filters: ekf_joseph_tiled)
+        M.nch = (M.m + SKC - 1) / SKC; M.nv = 2 * M.nch;
+        M.Pi = Pin + (size_t)f * ld * ld; M.Kf = p.K + (size_t)f * ld * ldK; M.Wf = p.W + (size_t)f * ld * ldK;
+        return M;
+    };
+    int gs = 0;                                            // stages issued so far -> buffer gs % SNST
+    auto issue = [&](const Meta& M, int v, const int* sidx) {
+        if (v < M.nv) {
+            double* A = sms + (gs % SNST) * STAGE;
+            double* B = A + A_DOUBLES;
+            const int phase = v >= M.nch, k0 = (phase ? v - M.nch : v) * SKC, m = M.m;
+            const double* Am = phase ? M.Wf : M.Kf;
+            for (int t = tid; t < ROWS * (SKC / 2); t += NW * 32) {   // A panel: rows of K or W
+                int row = t / (SKC / 2), seg = t % (SKC / 2);
+                double* dst = &A[row * SLDA + seg * 2];
+                if (row < ld && k0 + seg * 2 < m) cp_async16(dst, Am + kw_at(ld, row, k0 + seg * 2));
+                else { dst[0] = 0.0; dst[1] = 0.0; }
+            }
+            if (!phase) {                                             // B panel: rows idx[k] of Sigma
+                for (int t = tid; t < SKC * (ROWS / 2); t += NW * 32) {
+                    int k = t / (ROWS / 2), seg = t % (ROWS / 2);
+                    double* dst = &B[k * SLDB + seg * 2];
+                    if (k0 + k < m && seg * 2 < ld) cp_async16(dst, M.Pi + (size_t)sidx[k0 + k] * ld + seg * 2);
                     else { dst[0] = 0.0; dst[1] = 0.0; }
                 }
-                if (phase == 0) {                                         // B panel: rows idx[k] of Sigma
-                    for (int t = tid; t < SKC * (ROWS / 2); t += NW * 32) {
-                        int k = t / (ROWS / 2), seg = t % (ROWS / 2);
-                        double* dst = &B[k * SLDB + seg * 2];
-                        if (k0 + k < m && seg * 2 < ld) cp_async16(dst, Pi + (size_t)s_idx[k0 + k] * ld + seg * 2);
-                        else { dst[0] = 0.0; dst[1] = 0.0; }
-                    }
-                } else {                                                  // B panel: rows of K
-                    for (int t = tid; t < ROWS * (SKC / 2); t += NW * 32) {
-                        int row = t / (SKC / 2), seg = t % (SKC / 2);
-                        double* dst = &B[row * SLDA + seg * 2];
-                        if (row < ld && k0 + seg * 2 < m) cp_async16(dst, Kf + (size_t)row * ldK + k0 + seg * 2);
-                        else { dst[0] = 0.0; dst[1] = 0.0; }
-                    }
+            } else {                                                  // B panel: rows of K
+                for (int t = tid; t < ROWS * (SKC / 2); t += NW * 32) {
+                    int row = t / (SKC / 2), seg = t % (SKC / 2);
+                    double* dst = &B[row * SLDA + seg * 2];
+                    if (row < ld && k0 + seg * 2 < m) cp_async16(dst, M.Kf + kw_at(ld, row, k0 + seg * 2));
+                    else { dst[0] = 0.0; dst[1] = 0.0; }
                 }
             }
-            cp_async_commit();
-        };
-        stage(0); stage(1);
-        for (int c = 0; c < nch; ++c) {
+        }
+        cp_async_commit();   // exactly one group per call (possibly empty): keeps the wait arithmetic uniform
+        ++gs;
+    };
+
+    Meta cur = meta(blockIdx.x);
+    int ib = 0;
+    for (int i = tid; i < cur.m; i += NW * 32) s_idx[0][i] = p.idx[(size_t)cur.f * p.mmax + i];
+    __syncthreads();
+    issue(cur, 0, s_idx[0]); issue(cur, 1, s_idx[0]);
+    int gc = 0;                                            // stages consumed so far
+
+    while (cur.f < p.F) {
+        Meta nxt = meta(cur.f + gridDim.x);
+        for (int i = tid; i < nxt.m; i += NW * 32) s_idx[ib ^ 1][i] = p.idx[(size_t)nxt.f * p.mmax + i];
+        __syncthreads();
+        const int N = cur.N;
+        const int nblk = (N + 15) >> 4, nitems = nblk * (nblk + 1) / 2;
+        int bi[IPW], bj[IPW], aoff[IPW], boffg[IPW], boffk[IPW];
+        double c0[IPW][4], c1[IPW][4];                    // tile t = rt*2 + ct of the 16x16 block
+#pragma unroll
+        for (int it = 0; it < IPW; ++it) {
+            int e = warp + it * NW;
+            bool ok = e < nitems;
+            int i = 0, j = 0;
+            if (ok) {
+                i = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
+                while (i * (i + 1) / 2 > e) --i;
+                while ((i + 1) * (i + 2) / 2 <= e) ++i;
+                j = e - i * (i + 1) / 2;
+            }
+            bi[it] = ok ? i : -1; bj[it] = j;
+            aoff[it] = (i * 16 + r) * SLDA + q;
+            boffg[it] = q * SLDB + j * 16 + r;
+            boffk[it] = (j * 16 + r) * SLDA + q;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                double2 v = make_double2(0.0, 0.0);
+                int row = i * 16 + (t >> 1) * 8 + r, col = j * 16 + (t & 1) * 8 + 2 * q;
+                if (ok && row < ld && col < ld) v = *reinterpret_cast<const double2*>(cur.Pi + (size_t)row * ld + col);
+                c0[it][t] = v.x; c1[it][t] = v.y;
+            }
+        }
+        int issued_next = 0;
+        for (int v = 0; v < cur.nv; ++v) {
             cp_async_wait<SNST - 2>();
             __syncthreads();
-            stage(c + 2);
-            const double* A = sms + (c % SNST) * STAGE;
+#ifdef EXP_NO_STAGE
+            cp_async_commit(); ++gs; if (!(v + 2 < cur.nv)) ++issued_next;
+#else
+            if (v + 2 < cur.nv) issue(cur, v + 2, s_idx[ib]);
+            else { issue(nxt, issued_next, s_idx[ib ^ 1]); ++issued_next; }
+#endif
+            const double* A = sms + (gc % SNST) * STAGE;
             const double* B = A + A_DOUBLES;
+            ++gc;
+            const bool phase1 = v >= cur.nch;
 #pragma unroll
             for (int kk = 0; kk < SKC / 4; ++kk) {
+                double fa0[IPW], fa1[IPW], fb0[IPW], fb1[IPW];
+#pragma unroll
+                for (int it = 0; it < IPW; ++it) {   // idle slots (bi < 0) recompute block (0,0) and are never stored
+                    const double* Ai = A + aoff[it] + kk * 4;
+                    fa0[it] = Ai[0]; fa1[it] = Ai[8 * SLDA];
+                    if (!phase1) { const double* Bi = B + boffg[it] + kk * 4 * SLDB; fb0[it] = Bi[0]; fb1[it] = Bi[8]; }
+                    else { const double* Bi = B + boffk[it] + kk * 4; fb0[it] = Bi[0]; fb1[it] = Bi[8 * SLDA]; }
+                }
+#ifndef EXP_NO_MMA
 #pragma unroll
                 for (int it = 0; it < IPW; ++it) {
-                    if (bi[it] >= 0) {
-                        const double a0 = A[(bi[it] * 16 + r) * SLDA + kk * 4 + q];
-                        const double a1 = A[(bi[it] * 16 + 8 + r) * SLDA + kk * 4 + q];
-                        double b0, b1;
-                        if (phase == 0) { b0 = B[(kk * 4 + q) * SLDB + bj[it] * 16 + r]; b1 = B[(kk * 4 + q) * SLDB + bj[it] * 16 + 8 + r]; }
-                        else { b0 = B[(bj[it] * 16 + r) * SLDA + kk * 4 + q]; b1 = B[(bj[it] * 16 + 8 + r) * SLDA + kk * 4 + q]; }
-                        dmma884(c0[it][0], c1[it][0], -a0, b0);
-                        dmma884(c0[it][1], c1[it][1], -a0, b1);
-                        dmma884(c0[it][2], c1[it][2], -a1, b0);
-                        dmma884(c0[it][3], c1[it][3], -a1, b1);
+                    dmma884(c0[it][0], c1[it][0], -fa0[it], fb0[it]);
+                    dmma884(c0[it][1], c1[it][1], -fa0[it], fb1[it]);
+                    dmma884(c0[it][2], c1[it][2], -fa1[it], fb0[it]);
+                    dmma884(c0[it][3], c1[it][3], -fa1[it], fb1[it]);
+                }
+#else
+#pragma unroll
+                for (int it = 0; it < IPW; ++it) { c0[it][0] += fa0[it] * fb0[it]; c1[it][1] += fa1[it] * fb1[it]; }
+#endif
+            }
+        }
+        while (issued_next < 2) { issue(nxt, issued_next, s_idx[ib ^ 1]); ++issued_next; }   // short filters (nv < 2)
+
+        // epilogue: Sigma'(I,J) and its mirror Sigma'(J,I); the mirror goes through an 8x8 transpose in
+        // shared memory so that both stores are row-contiguous
+        if (N > 0) {
+            double* Po = Pout + (size_t)cur.f * ld * ld;
+#pragma unroll
+            for (int it = 0; it < IPW; ++it) {
+                if (bi[it] < 0) continue;
+                const bool diag = bi[it] == bj[it];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int rt = t >> 1, ct = t & 1;
+                    const int row = bi[it] * 16 + rt * 8 + r, col = bj[it] * 16 + ct * 8 + 2 * q;
+                    const double v0 = prune(c0[it][t]), v1 = prune(c1[it][t]);
+                    if (diag && ct > rt) continue;                       // upper tile of a diagonal block: mirrored from (ct,rt)
+                    const bool dtile = diag && ct == rt;                 // tile on the diagonal: keep col <= row, mirror the rest
+                    if (row < N) {
+                        if (!dtile) {
+                            if (col + 1 < N) *reinterpret_cast<double2*>(Po + (size_t)row * ld + col) = make_double2(v0, v1);
+                            else if (col < N) Po[(size_t)row * ld + col] = v0;
+                        } else {
+                            if (col <= row) Po[(size_t)row * ld + col] = v0;
+                            if (col + 1 <= row) Po[(size_t)row * ld + col + 1] = v1;
+                        }
+                    }
+                    __syncwarp();
+                    tw[r * TLD + 2 * q] = v0; tw[r * TLD + 2 * q + 1] = v1;
+                    __syncwarp();
+                    // lane (r, q) now writes row' = tile column r, columns' = tile rows 2q, 2q+1
+                    const double m0 = tw[(2 * q) * TLD + r], m1 = tw[(2 * q + 1) * TLD + r];
+                    const int mrow = bj[it] * 16 + ct * 8 + r, mcol = bi[it] * 16 + rt * 8 + 2 * q;
+                    if (mrow < N) {
+                        if (!dtile) {
+                            if (mcol + 1 < N) *reinterpret_cast<double2*>(Po + (size_t)mrow * ld + mcol) = make_double2(m0, m1);
+                            else if (mcol < N) Po[(size_t)mrow * ld + mcol] = m0;
+                        } else {
+                            if (mcol > mrow && mcol < N) Po[(size_t)mrow * ld + mcol] = m0;
+                            if (mcol + 1 > mrow && mcol + 1 < N) Po[(size_t)mrow * ld + mcol + 1] = m1;
+                        }
                     }
                 }
             }
         }
-        cp_async_wait<0>();
-        __syncthreads();
+        cur = nxt; ib ^= 1;
     }
-
-#pragma unroll
-    for (int it = 0; it < IPW; ++it) {
-        if (bi[it] < 0) continue;
-        const bool diag = bi[it] == bj[it];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int row = bi[it] * 16 + (t >> 1) * 8 + r, col = bj[it] * 16 + (t & 1) * 8 + 2 * q;
-            const double v0 = prune(c0[it][t]), v1 = prune(c1[it][t]);
-            if (row >= N) continue;
-            if (!diag) {
-                if (col + 1 < N) *reinterpret_cast<double2*>(Po + (size_t)row * ld + col) = make_double2(v0, v1);
-                else if (col < N) Po[(size_t)row * ld + col] = v0;
-                if (col < N) Po[(size_t)col * ld + row] = v0;
-                if (col + 1 < N) Po[(size_t)(col + 1) * ld + row] = v1;
-            } else {
-                if (col <= row) { Po[(size_t)row * ld + col] = v0; if (col != row) Po[(size_t)col * ld + row] = v0; }
-                if (col + 1 <= row) { Po[(size_t)row * ld + col + 1] = v1; if (col + 1 != row) Po[(size_t)(col + 1) * ld + row] = v1; }
-            }
-        }
-    }
+    cp_async_wait<0>();
 }
 
 template <int NW, int NBLK, int IPW>
@@ -740,14 +804,18 @@ cudaError_t launch_joseph_sym_t(const EkfPtrs& p, const double* Pin, double* Pou
     constexpr int ROWS = NBLK * 16;
     constexpr int A_DOUBLES = ROWS * SLDA;
     constexpr int B_DOUBLES = (SKC * (ROWS + 4) > A_DOUBLES) ? SKC * (ROWS + 4) : A_DOUBLES;
-    const size_t sm = (size_t)SNST * (A_DOUBLES + B_DOUBLES) * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
+    const size_t sm = (size_t)(SNST * (A_DOUBLES + B_DOUBLES) + NW * 8 * 10) * sizeof(double);
+    static int sms_count = 0;
+    if (!sms_count) {
         cudaError_t e = cudaFuncSetAttribute(ekf_joseph_sym<NW, NBLK, IPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
-        configured = true;
+        int dev = 0;
+        e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms_count, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
     }
-    ekf_joseph_sym<NW, NBLK, IPW><<<p.F, NW * 32, sm, st>>>(p, Pin, Pout);
+    const int grid = p.F < sms_count ? p.F : sms_count;    // persistent: one CTA per SM
+    ekf_joseph_sym<NW, NBLK, IPW><<<grid, NW * 32, sm, st>>>(p, Pin, Pout);
     return cudaGetLastError();
 }
 
@@ -761,7 +829,7 @@ bool joseph_sym_supported(const EkfPtrs& p) { return p.Nmax <= 176 && p.mmax <= 
 // Symmetric filters only (p.asym[f] == 0); the others are left to launch_joseph_tiled.
 cudaError_t launch_joseph_sym(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st) {
     if (p.Nmax <= 128) return launch_joseph_sym_t<9, 8, 4>(p, Pin, Pout, st);      // 36 blocks
-    return launch_joseph_sym_t<11, 11, 6>(p, Pin, Pout, st);                       // 66 blocks
+    return launch_joseph_sym_t<11, 11, 6>(p, Pin, Pout, st);                       // 66 blocks, 6 per warp
 }
 
 bool gain_tiled_supported(const EkfPtrs& p) { return p.Nmax <= 176 && p.mmax <= 104 && p.L != nullptr; }
@@ -791,3 +859,11 @@ cudaError_t launch_joseph_tiled(const EkfPtrs& p, const double* Pin, double* Pou
 }
 
 }  // namespace ekfvio
+
+#ifdef EKFVIO_PROFILE_CLOCKS
+extern "C" void ekfvio_debug_clocks(unsigned long long* out, int reset) {
+    cudaMemcpyFromSymbol(out, g_clk, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_clk, z, sizeof(z)); }
+}
+#endif
+

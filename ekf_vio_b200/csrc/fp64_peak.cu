@@ -11,7 +11,7 @@ __global__ void k_peak_dmma(double* out, int iters, double s) {
     double a = 1.0 + s * threadIdx.x, b = s;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ekfvio::dmma884(c0[i], c1[i], a, b);
+        for (int i = 0; i < 8; ++i) ekfvio::dmma884_volatile(c0[i], c1[i], a, b);
     }
     double r = 0;
 #pragma unroll
