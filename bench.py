@@ -224,7 +224,10 @@ def bench_klt(args, rank, world, local):
     import torch
     from ekf_vio_b200 import capi, workload
     B, npts, K, W = args.klt_pairs, 200, args.steps, args.warmup
-    prev, nxt, pts, flow = workload.klt_pairs(rank * B, B, 640, 480, npts)
+    G = min(B, 32)                      # distinct synthetic pairs; the batch cycles through them (separate buffers)
+    prev, nxt, pts, flow = workload.klt_pairs(rank * G, G, 640, 480, npts)
+    reps = (B + G - 1) // G
+    prev, nxt, pts, flow = (np.ascontiguousarray(np.concatenate([a] * reps)[:B]) for a in (prev, nxt, pts, flow))
     trk = capi.KltTracker(640, 480, B, npts, device=local)
     d_prev = torch.from_numpy(prev).cuda(); d_next = torch.from_numpy(nxt).cuda()
     d_pts = torch.from_numpy(pts).cuda()
@@ -237,8 +240,7 @@ def bench_klt(args, rank, world, local):
     d_passed = torch.zeros(B, npts, dtype=torch.uint8, device="cuda")
 
     def step():
-        trk.build_pyramid(0, d_prev, True)
-        trk.build_pyramid(1, d_next, False)
+        trk.build_pyramid_pair(0, d_prev, 1, d_next, False)       # both pyramids, as cv::calcOpticalFlowPyrLK rebuilds them per call
         d_out.copy_(d_pts)                                        # initial flow = previous positions
         trk.track(0, 1, d_pts, d_out, d_status, d_err, d_npts)
         trk.postprocess(d_out, d_status, d_npts, d_K9, d_meas, d_cov, d_passed)
@@ -283,8 +285,9 @@ def bench_klt(args, rank, world, local):
     # roofline of the dominant streaming kernel: level 0 (reads 640x480 once, writes derivatives + level 1)
     peaks = load_peaks()
     lvl0_calls = max(kcnt[0], 1)
-    # per step two level-0 launches: one with derivatives, one without (intensity only)
-    bytes_l0 = B * ((640 * 480 + 640 * 480 * 4 + 320 * 240) + (640 * 480 + 320 * 240)) / 2.0   # average per launch
+    # one level-0 launch per step covers both images of every pair: the previous frame (read, write
+    # derivatives + level 1) and the next frame (read, write level 1)
+    bytes_l0 = B * ((640 * 480 + 640 * 480 * 4 + 320 * 240) + (640 * 480 + 320 * 240))
     ms_l0 = kms[0] / lvl0_calls
     pyr_ms = float(kms[:4].sum() / K)
     pyr_bytes = B * (KLT_BYTES_WITH_DERIVS + KLT_BYTES_NO_DERIVS)
@@ -401,7 +404,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--filters", type=int, default=4096, help="EKF filters per GPU")
-    ap.add_argument("--klt-pairs", type=int, default=96, help="image pairs per GPU for the KLT leg")
+    ap.add_argument("--klt-pairs", type=int, default=256, help="image pairs per GPU for the KLT leg")
     ap.add_argument("--skip-klt", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()

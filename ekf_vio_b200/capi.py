@@ -92,6 +92,7 @@ SIGNATURES = {
     "ekfvio_klt_destroy": (c_int, [c_void_p]),
     "ekfvio_klt_num_levels": (c_int, [c_void_p]),
     "ekfvio_klt_build_pyramid": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "ekfvio_klt_build_pyramid_pair": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ekfvio_klt_track": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ekfvio_klt_postprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ekfvio_klt_track_pair_h": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -278,6 +279,11 @@ class KltTracker:
     def build_pyramid(self, slot: int, imgs, with_derivs: bool):
         """imgs: uint8 cuda tensor [batch, H, pitch]."""
         _check(lib.ekfvio_klt_build_pyramid(self._h, slot, _ptr(imgs), int(imgs.shape[2]), int(imgs.shape[0]), int(with_derivs), _stream()))
+
+    def build_pyramid_pair(self, prev_slot: int, prev_imgs, next_slot: int, next_imgs, next_with_derivs: bool = False):
+        """Both pyramids of a frame pair, sharing each level's launch. imgs: uint8 cuda [batch, H, pitch]."""
+        _check(lib.ekfvio_klt_build_pyramid_pair(self._h, prev_slot, _ptr(prev_imgs), next_slot, _ptr(next_imgs), int(prev_imgs.shape[2]),
+                                                 int(prev_imgs.shape[0]), int(next_with_derivs), _stream()))
 
     def track(self, prev_slot, next_slot, prev_pts, next_pts, status, err, npts):
         _check(lib.ekfvio_klt_track(self._h, prev_slot, next_slot, _ptr(prev_pts), _ptr(next_pts), _ptr(status), _ptr(err), _ptr(npts),

@@ -110,31 +110,54 @@ int ekfvio_klt_get_timing(ekfvio_klt* k, double* ms8, long long* count8) {
 int ekfvio_klt_num_levels(const ekfvio_klt* k) { return k ? k->pyr.levels : 0; }
 long long ekfvio_klt_launch_count(const ekfvio_klt* k) { return k ? k->launches : 0; }
 
-int ekfvio_klt_build_pyramid(ekfvio_klt* k, int slot, const uint8_t* d_imgs, int pitch, int batch, int with_derivs, void* stream) {
-    if (slot < 0 || slot >= k->num_slots || batch <= 0 || batch > k->max_batch) return fail_msg("ekfvio_klt_build_pyramid: bad slot or batch");
-    CU(cudaSetDevice(k->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    uint8_t* base = k->d_slots + (size_t)slot * k->slot_bytes;
+// Builds one or two slots level by level; both slots share each level's launch.
+static int build_slots(ekfvio_klt* k, int nslots, const int* slots, const uint8_t* const* imgs, int pitch, int batch, const int* with_derivs,
+                       cudaStream_t st) {
     const Pyr& P = k->pyr;
     for (int l = 0; l < P.levels; ++l) {
         const Level& L = P.lv[l];
-        const uint8_t* src; int spitch; size_t sstride;
-        uint8_t* copy_dst = nullptr;
-        if (l == 0 && d_imgs) { src = d_imgs; spitch = pitch; sstride = (size_t)pitch * k->height; copy_dst = base + L.img_off; }
-        else { src = base + L.img_off; spitch = L.pitch; sstride = L.img_stride; }
-        short2* der = with_derivs ? reinterpret_cast<short2*>(base + L.der_off) : nullptr;
-        uint8_t* down = nullptr; int npitch = 0; size_t nstride = 0;
-        if (l + 1 < P.levels) { down = base + P.lv[l + 1].img_off; npitch = P.lv[l + 1].pitch; nstride = P.lv[l + 1].img_stride; }
-        if (!copy_dst && !der && !down) continue;
+        LevelJob jobs[2];
+        bool any = false;
+        for (int s = 0; s < 2; ++s) {
+            LevelJob& J = jobs[s];
+            J = LevelJob{nullptr, 0, 0, nullptr, nullptr, nullptr, 0};
+            if (s >= nslots) continue;
+            uint8_t* base = k->d_slots + (size_t)slots[s] * k->slot_bytes;
+            J.batch = batch;
+            if (l == 0 && imgs[s]) { J.src = imgs[s]; J.spitch = pitch; J.sstride = (size_t)pitch * k->height; J.copy_dst = base + L.img_off; }
+            else { J.src = base + L.img_off; J.spitch = L.pitch; J.sstride = L.img_stride; }
+            if (with_derivs[s]) J.deriv = reinterpret_cast<short2*>(base + L.der_off);
+            if (l + 1 < P.levels) J.down = base + P.lv[l + 1].img_off;
+            any = any || J.copy_dst || J.deriv || J.down;
+        }
+        if (!any) continue;
+        int npitch = 0; size_t nstride = 0;
+        if (l + 1 < P.levels) { npitch = P.lv[l + 1].pitch; nstride = P.lv[l + 1].img_stride; }
         k->timer.begin(l < 3 ? l : 3, st);
-        CU(launch_level(src, spitch, sstride, L.w, L.h, copy_dst, L.pitch, L.img_stride, der, L.dpitch, L.der_stride / sizeof(short2), down,
-                        npitch, nstride, batch, st));
+        CU(launch_level(jobs[0], jobs[1], L.w, L.h, L.pitch, L.img_stride, L.dpitch, L.der_stride / sizeof(short2), npitch, nstride, st));
         k->timer.end(st);
         k->launches += 1;
     }
-    k->slot_has_derivs[slot] = with_derivs != 0;
-    k->slot_batch[slot] = batch;
+    for (int s = 0; s < nslots; ++s) { k->slot_has_derivs[slots[s]] = with_derivs[s] != 0; k->slot_batch[slots[s]] = batch; }
     return 0;
+}
+
+int ekfvio_klt_build_pyramid(ekfvio_klt* k, int slot, const uint8_t* d_imgs, int pitch, int batch, int with_derivs, void* stream) {
+    if (slot < 0 || slot >= k->num_slots || batch <= 0 || batch > k->max_batch) return fail_msg("ekfvio_klt_build_pyramid: bad slot or batch");
+    CU(cudaSetDevice(k->device));
+    return build_slots(k, 1, &slot, &d_imgs, pitch, batch, &with_derivs, (cudaStream_t)stream);
+}
+
+int ekfvio_klt_build_pyramid_pair(ekfvio_klt* k, int prev_slot, const uint8_t* d_prev, int next_slot, const uint8_t* d_next, int pitch, int batch,
+                                  int next_with_derivs, void* stream) {
+    if (prev_slot < 0 || prev_slot >= k->num_slots || next_slot < 0 || next_slot >= k->num_slots || prev_slot == next_slot || batch <= 0 ||
+        batch > k->max_batch)
+        return fail_msg("ekfvio_klt_build_pyramid_pair: bad slots or batch");
+    CU(cudaSetDevice(k->device));
+    const int slots[2] = {prev_slot, next_slot};
+    const uint8_t* imgs[2] = {d_prev, d_next};
+    const int wd[2] = {1, next_with_derivs};
+    return build_slots(k, 2, slots, imgs, pitch, batch, wd, (cudaStream_t)stream);
 }
 
 int ekfvio_klt_track(ekfvio_klt* k, int prev_slot, int next_slot, const float* d_prev_pts, float* d_next_pts, uint8_t* d_status, float* d_err,
@@ -188,9 +211,7 @@ int ekfvio_klt_track_pair_h(ekfvio_klt* k, const uint8_t* h_prev, const uint8_t*
     CU(cudaMemcpyAsync(k->d_npts, hn, batch * sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(k->d_status, 0, npt, st));
     CU(cudaMemsetAsync(k->d_err, 0, npt * sizeof(float), st));
-    int rc = ekfvio_klt_build_pyramid(k, 0, nullptr, 0, batch, 1, stream);
-    if (rc) return rc;
-    rc = ekfvio_klt_build_pyramid(k, 1, nullptr, 0, batch, 0, stream);
+    int rc = ekfvio_klt_build_pyramid_pair(k, 0, nullptr, 1, nullptr, 0, batch, 0, stream);
     if (rc) return rc;
     rc = ekfvio_klt_track(k, 0, 1, k->d_prev_pts, k->d_next_pts, k->d_status, k->d_err, k->d_npts, batch, stream);
     if (rc) return rc;

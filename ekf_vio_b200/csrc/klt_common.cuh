@@ -22,6 +22,13 @@ struct Level {
     size_t der_stride;
 };
 
+// One slot's share of a pyramid-level launch.
+struct LevelJob {
+    const uint8_t* src; int spitch; size_t sstride;
+    uint8_t* copy_dst; short2* deriv; uint8_t* down;
+    int batch;
+};
+
 struct Pyr {
     int levels;  // number of levels (effective max level + 1)
     Level lv[KLT_MAX_LEVELS];

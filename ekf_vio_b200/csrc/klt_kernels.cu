@@ -12,104 +12,138 @@ using namespace kltdev;
 
 namespace {
 
-constexpr int TW = 64, TH = 32;          // input pixels per CTA tile
-constexpr int SW = TW + 8, SH = TH + 4;  // staged tile: x0-4 .. x0+TW+3, y0-2 .. y0+TH+1
+__device__ __forceinline__ int dp4a_us(unsigned a_u8x4, int b_s8x4, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned dp4a_uu(unsigned a_u8x4, unsigned b_u8x4, unsigned c) {
+    unsigned d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_u8x4), "r"(c));
+    return d;
+}
+
+constexpr int TW = 64, TH = 32;            // input pixels per CTA tile
+constexpr int SW = TW + 16, SH = TH + 4;   // staged tile: x0-8 .. x0+TW+7 (16-byte aligned rows), y0-2 .. y0+TH+1
+
+__device__ __forceinline__ int reflect_once(int p, int len) { return p < 0 ? -p : (p >= len ? 2 * len - 2 - p : p); }
 
 // One pyramid level: reads level l of every image once and writes (a) an optional copy into the
 // slot (level 0 fed from a caller buffer), (b) the interleaved int16 Scharr derivatives,
-// (c) level l+1 = pyrDown(level l).  grid = (tiles_x, tiles_y, batch), 256 threads.
-__global__ void __launch_bounds__(256) klt_level_kernel(const uint8_t* __restrict__ src, int spitch, size_t sstride, int w, int h,
-                                                        uint8_t* __restrict__ copy_dst, int cpitch, size_t cstride,
-                                                        short2* __restrict__ deriv, int dpitch, size_t dstride,
-                                                        uint8_t* __restrict__ down, int npitch, size_t nstride) {
+// (c) level l+1 = pyrDown(level l).  grid = (tiles_x, tiles_y, images of both jobs), 256 threads.
+// Integer work is done with u8x4 dot products (IDP4A) on 32-bit windows of the staged tile, one
+// 16-byte vector store per 4 output pixels; the kernel is meant to be bound by HBM, not by issue.
+__global__ void __launch_bounds__(256) klt_level_kernel(LevelJob j0, LevelJob j1, int w, int h, int cpitch, size_t cstride, int dpitch,
+                                                        size_t dstride, int npitch, size_t nstride) {
     __shared__ __align__(16) uint8_t tile[SH][SW];
-    __shared__ uint16_t hs[SH][TW / 2];
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
-    const uint8_t* s = src + (size_t)b * sstride;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    int b = blockIdx.z;
+    const bool second = b >= j0.batch;
+    if (second) b -= j0.batch;
+    const LevelJob& J = second ? j1 : j0;      // two slots (e.g. the previous and the next frame) share one launch
+    uint8_t* __restrict__ copy_dst = J.copy_dst;
+    short2* __restrict__ deriv = J.deriv;
+    uint8_t* __restrict__ down = J.down;
+    if (!copy_dst && !deriv && !down) return;
+    const int spitch = J.spitch;
+    const uint8_t* __restrict__ s = J.src + (size_t)b * J.sstride;
 
-    // stage the tile with REFLECT_101 applied to image coordinates
-    const bool interior_x = (x0 - 4 >= 0) && (x0 + TW + 4 <= w) && ((spitch & 3) == 0) && ((((size_t)s) & 3) == 0);
-    if (interior_x) {
-        for (int e = tid; e < SH * (SW / 4); e += 256) {
-            int r = e / (SW / 4), wc = e % (SW / 4);
-            int sy = reflect101(y0 - 2 + r, h);
-            uint32_t v = *reinterpret_cast<const uint32_t*>(s + (size_t)sy * spitch + (x0 - 4) + wc * 4);
-            *reinterpret_cast<uint32_t*>(&tile[r][wc * 4]) = v;
+    // stage the tile with REFLECT_101 applied to image coordinates (one reflection suffices: the
+    // halo is at most 8 pixels and every level is wider than the 21-pixel window)
+    const bool aligned8 = ((spitch & 7) == 0) && ((((size_t)s) & 7) == 0);
+    if (aligned8 && x0 >= 8 && x0 + TW + 8 <= w) {
+        for (int e = tid; e < SH * (SW / 8); e += 256) {
+            const int r = e / (SW / 8), v = e % (SW / 8);
+            const int sy = reflect_once(y0 - 2 + r, h);
+            *reinterpret_cast<uint2*>(&tile[r][v * 8]) = *reinterpret_cast<const uint2*>(s + (size_t)sy * spitch + (x0 - 8) + v * 8);
         }
     } else {
-        for (int e = tid; e < SH * SW; e += 256) {
-            int r = e / SW, c = e % SW;
-            int sy = reflect101(y0 - 2 + r, h), sx = reflect101(x0 - 4 + c, w);
-            tile[r][c] = s[(size_t)sy * spitch + sx];
+        const bool aligned4 = ((spitch & 3) == 0) && ((((size_t)s) & 3) == 0);
+        for (int e = tid; e < SH * (SW / 4); e += 256) {
+            const int r = e / (SW / 4), wc = e % (SW / 4);
+            const int sy = reflect_once(y0 - 2 + r, h), xs = x0 - 8 + wc * 4;
+            const uint8_t* row = s + (size_t)sy * spitch;
+            uint32_t v;
+            if (aligned4 && xs >= 0 && xs + 3 < w) v = *reinterpret_cast<const uint32_t*>(row + xs);
+            else v = (uint32_t)row[reflect101(xs, w)] | ((uint32_t)row[reflect101(xs + 1, w)] << 8) | ((uint32_t)row[reflect101(xs + 2, w)] << 16) |
+                     ((uint32_t)row[reflect101(xs + 3, w)] << 24);
+            *reinterpret_cast<uint32_t*>(&tile[r][wc * 4]) = v;
         }
     }
     __syncthreads();
 
-    if (copy_dst) {
-        uint8_t* cd = copy_dst + (size_t)b * cstride;
-        for (int e = tid; e < TH * (TW / 4); e += 256) {
-            int r = e / (TW / 4), wc = e % (TW / 4);
-            int y = y0 + r, x = x0 + wc * 4;
-            if (y < h && x < w)  // pitch is a multiple of 16: whole words stay inside the row
-                *reinterpret_cast<uint32_t*>(cd + (size_t)y * cpitch + x) = *reinterpret_cast<const uint32_t*>(&tile[r + 2][wc * 4 + 4]);
-        }
+    if (copy_dst) {   // 32 rows x 8 eight-byte vectors = one per thread
+        const int r = tid >> 3, v = tid & 7;
+        const int y = y0 + r, x = x0 + v * 8;
+        if (y < h && x < w)   // the slot's pitch is a multiple of 16: whole vectors stay inside the row
+            *reinterpret_cast<uint2*>(copy_dst + (size_t)b * cstride + (size_t)y * cpitch + x) = *reinterpret_cast<const uint2*>(&tile[r + 2][v * 8 + 8]);
     }
 
     if (deriv) {
-        short2* dd = deriv + (size_t)b * dstride;
-        for (int g = tid; g < TH * (TW / 4); g += 256) {
-            int r = g / (TW / 4), xg = (g % (TW / 4)) * 4;
-            int y = y0 + r, x = x0 + xg;
-            if (y >= h || x >= w) continue;
-            // columns c0-1 .. c0+4 of rows r+1, r+2, r+3 (tile coordinates), c0 = 4 + xg
-            int sm_[6], dm_[6];
-            const uint8_t* t0 = &tile[r + 1][xg + 3];
-            const uint8_t* t1 = &tile[r + 2][xg + 3];
-            const uint8_t* t2 = &tile[r + 3][xg + 3];
+        // Scharr: for pixel x the window bytes (x-1, x, x+1, x+2) of rows y-1, y, y+1 are dotted with the
+        // packed 3x3 weights; one thread = 8 pixels of a row.
+        const int r = tid >> 3, xg = (tid & 7) * 8;
+        const int y = y0 + r, x = x0 + xg;
+        if (y < h && x < w) {
+            unsigned o[8];
+            int ix[8], iy[8];
 #pragma unroll
-            for (int c = 0; c < 6; ++c) {
-                int a = t0[c], m = t1[c], z = t2[c];
-                sm_[c] = 3 * a + 10 * m + 3 * z;
-                dm_[c] = z - a;
-            }
-            short2 o[4];
+            for (int j = 0; j < 8; ++j) { ix[j] = 0; iy[j] = 0; }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                o[q].x = (short)(sm_[q + 2] - sm_[q]);
-                o[q].y = (short)(3 * dm_[q] + 10 * dm_[q + 1] + 3 * dm_[q + 2]);
+            for (int rr = 0; rr < 3; ++rr) {
+                const unsigned* tw = reinterpret_cast<const unsigned*>(&tile[r + 1 + rr][xg + 4]);   // word 0 = pixels xg-4 .. xg-1
+                const unsigned w0 = tw[0], w1 = tw[1], w2 = tw[2], w3 = tw[3];
+                unsigned win[8];
+                win[0] = __funnelshift_r(w0, w1, 24);
+                win[1] = w1;
+                win[2] = __funnelshift_r(w1, w2, 8);
+                win[3] = __funnelshift_r(w1, w2, 16);
+                win[4] = __funnelshift_r(w1, w2, 24);
+                win[5] = w2;
+                win[6] = __funnelshift_r(w2, w3, 8);
+                win[7] = __funnelshift_r(w2, w3, 16);
+                const int wx = (rr == 1) ? 0x000A00F6 : 0x000300FD;                   // (-10,0,10,0) / (-3,0,3,0)
+                const int wy = (rr == 0) ? 0x00FDF6FD : 0x00030A03;                   // (-3,-10,-3,0) / (3,10,3,0)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    ix[j] = dp4a_us(win[j], wx, ix[j]);
+                    if (rr != 1) iy[j] = dp4a_us(win[j], wy, iy[j]);
+                }
             }
-            short2* out = dd + (size_t)y * dpitch + x;
-            if (x + 3 < w) {
-                uint4 v;
-                v.x = (uint32_t)(uint16_t)o[0].x | ((uint32_t)(uint16_t)o[0].y << 16);
-                v.y = (uint32_t)(uint16_t)o[1].x | ((uint32_t)(uint16_t)o[1].y << 16);
-                v.z = (uint32_t)(uint16_t)o[2].x | ((uint32_t)(uint16_t)o[2].y << 16);
-                v.w = (uint32_t)(uint16_t)o[3].x | ((uint32_t)(uint16_t)o[3].y << 16);
-                *reinterpret_cast<uint4*>(out) = v;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = __byte_perm((unsigned)ix[j], (unsigned)iy[j], 0x5410);   // short2(ix, iy)
+            short2* out = deriv + (size_t)b * dstride + (size_t)y * dpitch + x;
+            if (x + 7 < w) {
+                reinterpret_cast<uint4*>(out)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                reinterpret_cast<uint4*>(out)[1] = make_uint4(o[4], o[5], o[6], o[7]);
             } else {
-                for (int q = 0; q < 4 && x + q < w; ++q) out[q] = o[q];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (x + j < w) reinterpret_cast<unsigned*>(out)[j] = o[j];
             }
         }
     }
 
     if (down) {
+        // pyrDown: thread = two horizontally adjacent outputs; [1 4 6 4 1] across as (1,4,6,4).window + 5th
+        // byte, then [1 4 6 4 1] down the five rows, all in registers.
         const int dw = (w + 1) / 2, dh = (h + 1) / 2;
-        // horizontal [1 4 6 4 1] on every staged row
-        for (int e = tid; e < SH * (TW / 2); e += 256) {
-            int r = e / (TW / 2), ox = e % (TW / 2);
-            const uint8_t* t = &tile[r][2 + 2 * ox];
-            hs[r][ox] = (uint16_t)(t[0] + 4 * t[1] + 6 * t[2] + 4 * t[3] + t[4]);
-        }
-        __syncthreads();
-        uint8_t* nd = down + (size_t)b * nstride;
-        for (int e = tid; e < (TH / 2) * (TW / 2); e += 256) {
-            int oy = e / (TW / 2), ox = e % (TW / 2);
-            int gx = x0 / 2 + ox, gy = y0 / 2 + oy;
-            if (gx < dw && gy < dh) {
-                int sum = hs[2 * oy][ox] + 4 * hs[2 * oy + 1][ox] + 6 * hs[2 * oy + 2][ox] + 4 * hs[2 * oy + 3][ox] + hs[2 * oy + 4][ox];
-                nd[(size_t)gy * npitch + gx] = (uint8_t)((sum + 128) >> 8);
+        const int oy = tid >> 4, oxp = (tid & 15) * 2;
+        const int gx = x0 / 2 + oxp, gy = y0 / 2 + oy;
+        if (gx < dw && gy < dh) {
+            int sa = 0, sb = 0;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const unsigned* tw = reinterpret_cast<const unsigned*>(&tile[2 * oy + j][2 * oxp + 4]);   // bytes base+4 ..
+                const unsigned w1 = tw[0], w2 = tw[1], w3 = tw[2];
+                const unsigned ha = dp4a_uu(__funnelshift_r(w1, w2, 16), 0x04060401u, (w2 >> 16) & 0xffu);  // taps base+6 .. base+10
+                const unsigned hb = dp4a_uu(w2, 0x04060401u, w3 & 0xffu);                                    // taps base+8 .. base+12
+                const int wv = (j == 0 || j == 4) ? 1 : ((j == 2) ? 6 : 4);
+                sa += wv * (int)ha; sb += wv * (int)hb;
             }
+            uint8_t* nd = down + (size_t)b * nstride + (size_t)gy * npitch + gx;
+            nd[0] = (uint8_t)((sa + 128) >> 8);
+            if (gx + 1 < dw) nd[1] = (uint8_t)((sb + 128) >> 8);
         }
     }
 }
@@ -129,8 +163,17 @@ __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01,
 
 constexpr int WARPS = 4;      // features per CTA
 
+__host__ __device__ inline size_t track_warp_bytes(int win) {
+    size_t area = (size_t)win * win, t = ((size_t)win + 1) * (win + 1);
+    size_t bytes = area * 4 /*dI*/ + t * 4 /*Dt*/ + ((area * 2 + 3) & ~(size_t)3) /*Ip*/ + ((t + 3) & ~(size_t)3) /*Jt*/;
+    return (bytes + 15) & ~(size_t)15;
+}
+
 // LKTrackerInvoker for every level, one warp per point.  Per-warp shared memory:
-//   Ipatch[win*win] int16, dI[win*win] short2, Jt[(win+1)^2] u8.
+//   dI[win*win] short2 (Ix, Iy of the patch), Dt[(win+1)^2] short2 (staged derivative tile),
+//   Ip[win*win] int16 (patch intensities, 5 fractional bits), Jt[(win+1)^2] u8 (staged I or J tile).
+// Tiles are staged row by row (lanes = columns), so every bilinear tap is a shared-memory read and
+// no per-pixel integer division or border test remains in the loops.
 __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const uint8_t* __restrict__ prev_slot, const uint8_t* __restrict__ next_slot,
                                                                const float* __restrict__ prev_pts, float* __restrict__ next_pts,
                                                                uint8_t* __restrict__ status, float* __restrict__ err, const int* __restrict__ npts,
@@ -141,12 +184,15 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
     const int b = blockIdx.y;
     const int pt = blockIdx.x * WARPS + warp;
     if (pt >= npts[b]) return;
-    const int area = win * win, jw1 = win + 1;
-    const size_t per_warp = (size_t)area * 2 + (size_t)area * 4 + (((size_t)jw1 * jw1 + 15) & ~(size_t)15);
-    uint8_t* base = smem_raw + warp * ((per_warp + 15) & ~(size_t)15);
+    const int area = win * win, jw1 = win + 1, tarea = jw1 * jw1;
+    uint8_t* base = smem_raw + warp * track_warp_bytes(win);
     short2* dI = reinterpret_cast<short2*>(base);
-    short* Ip = reinterpret_cast<short*>(base + (size_t)area * 4);
-    uint8_t* Jt = base + (size_t)area * 6;
+    short2* Dt = dI + area;
+    short* Ip = reinterpret_cast<short*>(Dt + tarea);
+    uint8_t* Jt = reinterpret_cast<uint8_t*>(Ip) + ((area * 2 + 3) & ~3);
+    // lane's pixel slots: e = lane, lane + 32, ...  ->  (y, x) advanced without divisions
+    const int y_first = lane / win, x_first = lane - y_first * win;
+    const int qstep = 32 / win, rstep = 32 - qstep * win;
 
     const size_t pidx = ((size_t)b * max_points + pt) * 2;
     const float prevx = prev_pts[pidx], prevy = prev_pts[pidx + 1];
@@ -156,6 +202,21 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
     const float half = (win - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (1 << 20);
     const int top = pyr.levels - 1;
+
+    // stage a (win+1)^2 tile of an 8-bit image at (ox, oy) with REFLECT_101 borders
+    auto stage_u8 = [&](const uint8_t* img, const Level& L, int ox, int oy) {
+        if (lane < jw1) {
+            const bool inside = ox >= 0 && oy >= 0 && ox + win < L.w && oy + win < L.h;
+            if (inside) {
+                const uint8_t* p = img + (size_t)oy * L.pitch + ox + lane;
+                for (int y = 0; y < jw1; ++y) Jt[y * jw1 + lane] = p[(size_t)y * L.pitch];
+            } else {
+                const int cx = reflect101(ox + lane, L.w);
+                for (int y = 0; y < jw1; ++y) Jt[y * jw1 + lane] = img[(size_t)reflect101(oy + y, L.h) * L.pitch + cx];
+            }
+        }
+        __syncwarp();
+    };
 
     for (int level = top; level >= 0; --level) {
         const Level L = pyr.lv[level];
@@ -178,26 +239,30 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
         }
         int w00, w01, w10, w11;
         lk_weights(px - ipx, py - ipy, w00, w01, w10, w11);
+        // stage the I tile (into Jt) and the derivative tile (zero outside the image)
+        __syncwarp();
+        stage_u8(I, L, ipx, ipy);
+        if (lane < jw1) {
+            const int X = ipx + lane;
+            const bool xin = (unsigned)X < (unsigned)L.w;
+            for (int y = 0; y < jw1; ++y) {
+                const int Y = ipy + y;
+                Dt[y * jw1 + lane] = (xin && (unsigned)Y < (unsigned)L.h) ? dIm[(size_t)Y * L.dpitch + X] : make_short2(0, 0);
+            }
+        }
+        __syncwarp();
         long long a11 = 0, a12 = 0, a22 = 0;
-        for (int e = lane; e < area; e += 32) {
-            int y = e / win, x = e - y * win;
-            int X = ipx + x, Y = ipy + y;
-            int X0 = reflect101(X, L.w), X1 = reflect101(X + 1, L.w), Y0 = reflect101(Y, L.h), Y1 = reflect101(Y + 1, L.h);
-            int i00 = I[(size_t)Y0 * L.pitch + X0], i01 = I[(size_t)Y0 * L.pitch + X1];
-            int i10 = I[(size_t)Y1 * L.pitch + X0], i11 = I[(size_t)Y1 * L.pitch + X1];
-            int ival = (i00 * w00 + i01 * w01 + i10 * w10 + i11 * w11 + (1 << 8)) >> 9;
-            short2 z2 = make_short2(0, 0);
-            bool xin0 = (unsigned)X < (unsigned)L.w, xin1 = (unsigned)(X + 1) < (unsigned)L.w;
-            bool yin0 = (unsigned)Y < (unsigned)L.h, yin1 = (unsigned)(Y + 1) < (unsigned)L.h;
-            short2 d00 = (xin0 && yin0) ? dIm[(size_t)Y * L.dpitch + X] : z2;
-            short2 d01 = (xin1 && yin0) ? dIm[(size_t)Y * L.dpitch + X + 1] : z2;
-            short2 d10 = (xin0 && yin1) ? dIm[(size_t)(Y + 1) * L.dpitch + X] : z2;
-            short2 d11 = (xin1 && yin1) ? dIm[(size_t)(Y + 1) * L.dpitch + X + 1] : z2;
-            int ixval = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << 13)) >> 14;
-            int iyval = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << 13)) >> 14;
+        for (int e = lane, y = y_first, x = x_first; e < area; e += 32) {
+            const int o = y * jw1 + x;
+            const int ival = (Jt[o] * w00 + Jt[o + 1] * w01 + Jt[o + jw1] * w10 + Jt[o + jw1 + 1] * w11 + (1 << 8)) >> 9;
+            const short2 d00 = Dt[o], d01 = Dt[o + 1], d10 = Dt[o + jw1], d11 = Dt[o + jw1 + 1];
+            const int ixval = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << 13)) >> 14;
+            const int iyval = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << 13)) >> 14;
             Ip[e] = (short)ival;
             dI[e] = make_short2((short)ixval, (short)iyval);
             a11 += ixval * ixval; a12 += ixval * iyval; a22 += iyval * iyval;
+            y += qstep; x += rstep;
+            if (x >= win) { x -= win; ++y; }
         }
         a11 = warp_sum_ll(a11); a12 = warp_sum_ll(a12); a22 = warp_sum_ll(a22);
         float A11 = (float)a11 * FLT_SCALE, A12 = (float)a12 * FLT_SCALE, A22 = (float)a22 * FLT_SCALE;
@@ -210,7 +275,6 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
         D = 1.f / D;
         nx -= half; ny -= half;
         float pdx = 0.f, pdy = 0.f;
-        __syncwarp();
         for (int j = 0; j < max_count; ++j) {
             int inx = (int)floorf(nx), iny = (int)floorf(ny);
             if (inx < -win || inx >= L.w || iny < -win || iny >= L.h) {
@@ -218,21 +282,18 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
                 break;
             }
             lk_weights(nx - inx, ny - iny, w00, w01, w10, w11);
-            for (int e = lane; e < jw1 * jw1; e += 32) {
-                int y = e / jw1, x = e - y * jw1;
-                Jt[e] = J[(size_t)reflect101(iny + y, L.h) * L.pitch + reflect101(inx + x, L.w)];
-            }
             __syncwarp();
+            stage_u8(J, L, inx, iny);
             long long b1 = 0, b2 = 0;
-            for (int e = lane; e < area; e += 32) {
-                int y = e / win, x = e - y * win;
+            for (int e = lane, y = y_first, x = x_first; e < area; e += 32) {
                 const uint8_t* jp = Jt + y * jw1 + x;
-                int diff = ((jp[0] * w00 + jp[1] * w01 + jp[jw1] * w10 + jp[jw1 + 1] * w11 + (1 << 8)) >> 9) - Ip[e];
-                short2 d = dI[e];
+                const int diff = ((jp[0] * w00 + jp[1] * w01 + jp[jw1] * w10 + jp[jw1 + 1] * w11 + (1 << 8)) >> 9) - Ip[e];
+                const short2 d = dI[e];
                 b1 += diff * d.x; b2 += diff * d.y;
+                y += qstep; x += rstep;
+                if (x >= win) { x -= win; ++y; }
             }
             b1 = warp_sum_ll(b1); b2 = warp_sum_ll(b2);
-            __syncwarp();
             float fb1 = (float)b1 * FLT_SCALE, fb2 = (float)b2 * FLT_SCALE;
             float dx = (A12 * fb2 - A22 * fb1) * D, dy = (A12 * fb1 - A11 * fb2) * D;
             nx += dx; ny += dy;
@@ -252,17 +313,14 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
             } else {
                 lk_weights(fx - inx, fy - iny, w00, w01, w10, w11);
                 __syncwarp();
-                for (int e = lane; e < jw1 * jw1; e += 32) {
-                    int y = e / jw1, x = e - y * jw1;
-                    Jt[e] = J[(size_t)reflect101(iny + y, L.h) * L.pitch + reflect101(inx + x, L.w)];
-                }
-                __syncwarp();
+                stage_u8(J, L, inx, iny);
                 long long es = 0;
-                for (int e = lane; e < area; e += 32) {
-                    int y = e / win, x = e - y * win;
+                for (int e = lane, y = y_first, x = x_first; e < area; e += 32) {
                     const uint8_t* jp = Jt + y * jw1 + x;
-                    int diff = ((jp[0] * w00 + jp[1] * w01 + jp[jw1] * w10 + jp[jw1 + 1] * w11 + (1 << 8)) >> 9) - Ip[e];
+                    const int diff = ((jp[0] * w00 + jp[1] * w01 + jp[jw1] * w10 + jp[jw1 + 1] * w11 + (1 << 8)) >> 9) - Ip[e];
                     es += diff < 0 ? -diff : diff;
+                    y += qstep; x += rstep;
+                    if (x >= win) { x -= win; ++y; }
                 }
                 es = warp_sum_ll(es);
                 errv = (float)es * 1.f / (float)(32 * win * win);
@@ -304,19 +362,14 @@ __global__ void klt_postprocess_kernel(const float* __restrict__ next_pts, const
 
 namespace kltdev {
 
-cudaError_t launch_level(const uint8_t* src, int spitch, size_t sstride, int w, int h, uint8_t* copy_dst, int cpitch, size_t cstride,
-                         short2* deriv, int dpitch, size_t dstride, uint8_t* down, int npitch, size_t nstride, int batch, cudaStream_t st) {
-    dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH, batch);
-    klt_level_kernel<<<grid, 256, 0, st>>>(src, spitch, sstride, w, h, copy_dst, cpitch, cstride, deriv, dpitch, dstride, down, npitch, nstride);
+cudaError_t launch_level(const LevelJob& j0, const LevelJob& j1, int w, int h, int cpitch, size_t cstride, int dpitch, size_t dstride,
+                         int npitch, size_t nstride, cudaStream_t st) {
+    dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH, j0.batch + j1.batch);
+    klt_level_kernel<<<grid, 256, 0, st>>>(j0, j1, w, h, cpitch, cstride, dpitch, dstride, npitch, nstride);
     return cudaGetLastError();
 }
 
-size_t track_smem_bytes(int win) {
-    size_t area = (size_t)win * win, jw1 = (size_t)win + 1;
-    size_t per_warp = area * 2 + area * 4 + ((jw1 * jw1 + 15) & ~(size_t)15);
-    per_warp = (per_warp + 15) & ~(size_t)15;
-    return per_warp * WARPS;
-}
+size_t track_smem_bytes(int win) { return track_warp_bytes(win) * WARPS; }
 
 cudaError_t launch_track(const Pyr& pyr, const uint8_t* prev_slot, const uint8_t* next_slot, const float* prev_pts, float* next_pts,
                          uint8_t* status, float* err, const int* npts, int max_points, int batch, const ekfvio_klt_params& prm, cudaStream_t st) {

@@ -3,8 +3,8 @@
 #include "klt_common.cuh"
 
 namespace kltdev {
-cudaError_t launch_level(const uint8_t* src, int spitch, size_t sstride, int w, int h, uint8_t* copy_dst, int cpitch, size_t cstride,
-                         short2* deriv, int dpitch, size_t dstride, uint8_t* down, int npitch, size_t nstride, int batch, cudaStream_t st);
+cudaError_t launch_level(const LevelJob& j0, const LevelJob& j1, int w, int h, int cpitch, size_t cstride, int dpitch, size_t dstride,
+                         int npitch, size_t nstride, cudaStream_t st);
 size_t track_smem_bytes(int win);
 cudaError_t launch_track(const Pyr& pyr, const uint8_t* prev_slot, const uint8_t* next_slot, const float* prev_pts, float* next_pts,
                          uint8_t* status, float* err, const int* npts, int max_points, int batch, const ekfvio_klt_params& prm, cudaStream_t st);

@@ -171,6 +171,14 @@ int ekfvio_klt_num_levels(const ekfvio_klt* k);
  * Fills pyramid slot `slot`. */
 int ekfvio_klt_build_pyramid(ekfvio_klt* k, int slot, const uint8_t* d_imgs, int pitch, int batch, int with_derivs, void* stream);
 
+/* Both pyramids of a frame pair in one pass, as cv::calcOpticalFlowPyrLK builds them per call
+ * (KLTTracker.cpp:61): prev_slot gets intensities + derivatives, next_slot intensities (and
+ * derivatives if next_with_derivs, so it can serve as the previous frame of the next call).
+ * The two slots share each level's kernel launch.  NULL image pointers mean "level 0 is already
+ * in the slot". */
+int ekfvio_klt_build_pyramid_pair(ekfvio_klt* k, int prev_slot, const uint8_t* d_prev, int next_slot, const uint8_t* d_next, int pitch,
+                                  int batch, int next_with_derivs, void* stream);
+
 /* LKTrackerInvoker over all levels (cv::calcOpticalFlowPyrLK, KLTTracker.cpp:61-64) between
  * pyramid slots prev_slot (needs derivatives) and next_slot.  d_prev_pts[batch][max_points][2]
  * pixel coordinates, d_next_pts same shape: in = initial flow (if use_initial_flow), out =
