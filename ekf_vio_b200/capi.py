@@ -84,6 +84,8 @@ SIGNATURES = {
     "ekfvio_batch_add_features_h": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ekfvio_batch_update_h": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ekfvio_batch_read_mu_h": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ekfvio_batch_linearize_h": (c_int, [c_void_p, c_double, c_void_p]),
+    "ekfvio_batch_check_sigma_h": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ekfvio_batch_get_view": (c_int, [c_void_p, C.POINTER(BatchView)]),
     "ekfvio_batch_launch_count": (C.c_longlong, [c_void_p]),
     "ekfvio_batch_accumulate_errors": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),

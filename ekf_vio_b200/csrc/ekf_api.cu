@@ -338,6 +338,35 @@ int ekfvio_batch_update_h(ekfvio_batch* b, const double* h_z, const double* h_R,
     return ekfvio_batch_update(b, b->dd_z, b->dd_R, b->dd_pass, stream);
 }
 
+int ekfvio_batch_linearize_h(ekfvio_batch* b, double dt, double* h_F) {
+    CU(cudaSetDevice(b->device));
+    double* dF = nullptr;
+    const size_t bytes = (size_t)b->F * b->Nmax * b->Nmax * sizeof(double);
+    CU(cudaMalloc((void**)&dF, bytes));
+    cudaError_t e = launch_fill_dt(b->d_dt, dt, b->F, nullptr);
+    b->launches += 1;
+    int rc = 0;
+    if (e == cudaSuccess) rc = ekfvio_batch_linearize(b, b->d_dt, dF, nullptr);
+    if (e == cudaSuccess && rc == 0) e = cudaMemcpy(h_F, dF, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(dF);
+    if (e != cudaSuccess) return ekfvio::fail("linearize_h", e);
+    return rc;
+}
+
+int ekfvio_batch_check_sigma_h(ekfvio_batch* b, int* h_neg_diag, double* h_max_asym) {
+    CU(cudaSetDevice(b->device));
+    int* dn = nullptr; double* da = nullptr;
+    CU(cudaMalloc((void**)&dn, b->F * sizeof(int)));
+    if (cudaMalloc((void**)&da, b->F * sizeof(double)) != cudaSuccess) { cudaFree(dn); return fail_msg("check_sigma_h: cudaMalloc"); }
+    int rc = ekfvio_batch_check_sigma(b, dn, da, nullptr);
+    cudaError_t e = cudaSuccess;
+    if (rc == 0) e = cudaMemcpy(h_neg_diag, dn, b->F * sizeof(int), cudaMemcpyDeviceToHost);
+    if (rc == 0 && e == cudaSuccess) e = cudaMemcpy(h_max_asym, da, b->F * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(dn); cudaFree(da);
+    if (e != cudaSuccess) return ekfvio::fail("check_sigma_h", e);
+    return rc;
+}
+
 int ekfvio_batch_read_mu_h(ekfvio_batch* b, double* h_mu, double* h_feat, void* stream) {
     CU(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;

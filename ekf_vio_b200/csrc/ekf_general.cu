@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const do
         // are staged once per CTA; a warp's own three rows arrive by cp.async one task ahead.
         const int Np = (N + 3) & ~3;
         const int Npm = ((BASE + 3 * p.nmax) + 3) & ~3;
-        double* Pb = sm + ProcSmem::doubles(p.nmax);          // [9][Np]: rows 7..15
+        double* Pb = sm + ((ProcSmem::doubles(p.nmax) + 1) & ~(size_t)1);   // [9][Np]: rows 7..15 (16-byte aligned for cp.async)
         const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
         double* Tw = Pb + 9 * (size_t)Npm + (size_t)warp * 6 * Npm;   // [3][Np]
         double* Own = Tw + 3 * (size_t)Npm;                           // [3][Np]
@@ -667,7 +667,7 @@ static size_t proc_smem_bytes(int nmax) { return ProcSmem::doubles(nmax) * sizeo
 // fused covariance pass: + rows 7..15 of Sigma + a 3-row T slice and a 3-row prefetch slice per warp
 static size_t proc_fused_smem_bytes(int nmax) {
     size_t Np = ((size_t)(BASE + 3 * nmax) + 3) & ~(size_t)3;
-    return proc_smem_bytes(nmax) + (9 + 6 * (PT / 32)) * Np * sizeof(double);
+    return proc_smem_bytes(nmax) + sizeof(double) + (9 + 6 * (PT / 32)) * Np * sizeof(double);
 }
 
 cudaError_t launch_process_general(const EkfPtrs& p, const double* Pin, double* Pout, const double* dts, int mode, double* F_out, cudaStream_t st) {

@@ -1,0 +1,34 @@
+/* Frame.h — image + intrinsics, as the tracker and Feature see it (reference
+ * include/ekf_vio/Frame.h:24-43, Frame.cpp:15-55).  The resizing constructor (cv::resize,
+ * Frame.cpp:19) is the caller's business here (SURVEY.md §8f "next"): construct from an already
+ * scaled 8-bit image and a K already divided by inv_scale. */
+#ifndef EKFVIO_FRAME_H_
+#define EKFVIO_FRAME_H_
+
+#include "compat.h"
+#include "Params.h"
+
+class Frame {
+public:
+    Eigen::Matrix<float, 3, 3> K;
+    Eigen::Matrix<float, 1, 5> D;   /* distortion coefficients; unused by the hot path */
+    cv::Mat img;
+    ros::Time t;
+
+    Frame() {}
+    /* K9 row-major fx 0 cx 0 fy cy 0 0 1, as sensor_msgs/CameraInfo::K (Frame.cpp:26-33) */
+    Frame(int inv_scale, cv::Mat scaled_img, const double k[9], ros::Time _t) : img(scaled_img), t(_t) {
+        K.setZero();
+        K(0, 0) = (float)(k[0] / inv_scale);
+        K(0, 2) = (float)(k[2] / inv_scale);
+        K(1, 1) = (float)(k[4] / inv_scale);
+        K(1, 2) = (float)(k[5] / inv_scale);
+        K(2, 2) = 1.0f;
+    }
+    /* Frame.cpp:44-55 */
+    bool isPixelInBox(cv::Point2f px) const {
+        return !(px.x < KILL_PAD || px.y < KILL_PAD || this->img.cols - px.x < KILL_PAD || this->img.rows - px.y < KILL_PAD);
+    }
+};
+
+#endif

@@ -106,6 +106,10 @@ int ekfvio_batch_set_state(ekfvio_batch* b, const double* h_mu, const double* h_
  * enqueued (inputs are consumed before return). */
 int ekfvio_batch_add_features_h(ekfvio_batch* b, const int* h_k, const double* h_uv, int kmax, void* stream);
 int ekfvio_batch_update_h(ekfvio_batch* b, const double* h_z, const double* h_R, const uint8_t* h_pass, void* stream);
+/* numericallyLinearizeProcess with one dt for all filters, Jacobians to HOST memory
+ * h_F[F][Nmax][Nmax]; checkSigma with HOST outputs.  Synchronous (facade and test use). */
+int ekfvio_batch_linearize_h(ekfvio_batch* b, double dt, double* h_F);
+int ekfvio_batch_check_sigma_h(ekfvio_batch* b, int* h_neg_diag, double* h_max_asym);
 /* Copies mu (F x 22) and feat (F x nmax x 3) to host after the enqueued work; synchronises. */
 int ekfvio_batch_read_mu_h(ekfvio_batch* b, double* h_mu, double* h_feat, void* stream);
 
