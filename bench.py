@@ -109,22 +109,22 @@ def barrier(world):
     torch.cuda.synchronize()
 
 
-def max_over_ranks(x: float, world: int) -> float:
+def max_over_ranks(x: float, world: int, device: str = "cuda") -> float:
     import torch
     if world == 1:
         return x
     import torch.distributed as dist
-    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    t = torch.tensor([x], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t[0])
 
 
-def sum_over_ranks(x: float, world: int) -> float:
+def sum_over_ranks(x: float, world: int, device: str = "cuda") -> float:
     import torch
     if world == 1:
         return x
     import torch.distributed as dist
-    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    t = torch.tensor([x], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t[0])
 

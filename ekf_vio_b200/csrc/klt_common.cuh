@@ -1,5 +1,5 @@
 // Shared definitions for the KLT kernels (sm_100a).  Arithmetic follows OpenCV's
-// calcOpticalFlowPyrLK operation by operation (oracle/klt_oracle.c), which is
+// calcOpticalFlowPyrLK operation by operation, which is
 // what KLTTracker::findNewFeaturePositionsOpenCV calls (reference KLTTracker.cpp:61-64).
 #pragma once
 #include <cuda_runtime.h>

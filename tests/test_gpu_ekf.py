@@ -267,3 +267,32 @@ def test_capacity_overflow_is_flagged(cuda):
     b.add_features_h(np.array([3], np.int32), np.zeros((1, 3, 2)))
     s = b.get_state(want_P=False)
     assert int(s["nfeat"][0]) == 3 and int(s["status"][0]) & 4
+
+
+@pytest.mark.parametrize("nmax", [1, 2, 3, 5, 9, 17, 33, 51])
+def test_capacities_of_every_alignment(cuda, nmax):
+    """Capacities that make N = 22 + 3n odd / not a multiple of 4 or 8 (shared-memory alignment, tile tails)."""
+    rng = np.random.default_rng(nmax)
+    uv = rng.uniform(-0.7, 0.7, (nmax, 2))
+    orc = O.OracleFilter(); orc.add_features(uv)
+    b = make_batch(2, nmax)
+    b.add_features_h(np.array([nmax, max(nmax - 1, 0)], np.int32), np.stack([uv, uv]))
+    orc2 = O.OracleFilter()
+    if nmax > 1:
+        orc2.add_features(uv[:nmax - 1])
+    mu = orc.state()["mu"]; mu[7:10] = [0.1, -0.05, 0.02]; mu[10:13] = [0.01, 0.08, -0.03]
+    for o in (orc, orc2):
+        st = o.state(); o.set_state(mu=mu, feat=st["feat"], Pm=st["P"])
+    b.set_state(mu=np.stack([mu, mu]))
+    R = np.tile(np.array([1e-5, 0, 0, 1e-5]), (2, nmax, 1)); passed = np.ones((2, nmax), np.uint8)
+    for s in range(3):
+        orc.process(0.05); orc2.process(0.05); b.process(0.05)
+        z = np.zeros((2, nmax, 2))
+        z[0] = orc.state()["feat"][:, :2] + rng.normal(0, 1e-3, (nmax, 2))
+        if nmax > 1:
+            z[1, :nmax - 1] = orc2.state()["feat"][:, :2] + rng.normal(0, 1e-3, (nmax - 1, 2))
+        orc.update(z[0], R[0], passed[0])
+        orc2.update(z[1, :nmax - 1], R[1, :nmax - 1], passed[1, :nmax - 1])
+        b.update(*torch_inputs(z, R, passed))
+        assert_close(gpu_state(b, 0), orc.state(), what=f"nmax={nmax} filter 0 step {s}")
+        assert_close(gpu_state(b, 1), orc2.state(), what=f"nmax={nmax} filter 1 step {s}")
