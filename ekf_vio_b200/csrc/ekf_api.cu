@@ -52,7 +52,7 @@ int ekfvio_batch_destroy(ekfvio_batch* b) {
     cudaSetDevice(b->device);
     cudaFree(b->d_mu); cudaFree(b->d_feat); cudaFree(b->d_P[0]); cudaFree(b->d_P[1]); cudaFree(b->d_nfeat); cudaFree(b->d_cache);
     cudaFree(b->d_flags); cudaFree(b->d_klt_last); cudaFree(b->d_status); cudaFree(b->d_dt); cudaFree(b->d_K); cudaFree(b->d_W);
-    cudaFree(b->d_S); cudaFree(b->d_L); cudaFree(b->d_asym); cudaFree(b->d_y); cudaFree(b->d_idx); cudaFree(b->d_m); cudaFree(b->d_fjac);
+    cudaFree(b->d_S); cudaFree(b->d_L); cudaFree(b->d_asym); cudaFree(b->d_LS); cudaFree(b->d_LL); cudaFree(b->d_LT); cudaFree(b->d_y); cudaFree(b->d_idx); cudaFree(b->d_m); cudaFree(b->d_fjac);
     cudaFree(b->dd_z); cudaFree(b->dd_R); cudaFree(b->dd_pass);
     cudaFreeHost(b->h_z); cudaFreeHost(b->h_R); cudaFreeHost(b->h_pass); cudaFreeHost(b->h_out);
     delete b;
@@ -72,7 +72,8 @@ int ekfvio_batch_create(ekfvio_batch** out, int device, int num_filters, int max
     b->Nmax = BASE + 3 * max_features;
     b->ldP = (b->Nmax + 7) / 8 * 8;
     b->mmax = 2 * max_features > 0 ? 2 * max_features : 2;
-    b->ldK = (b->mmax + 15) / 16 * 16;    // K / W panels are chunk-major in 16-column chunks (kw_at)
+    b->large = b->Nmax > 176 || b->mmax > 104;                    // beyond the register-resident tiled path
+    b->ldK = b->large ? (b->mmax + 63) / 64 * 64 : (b->mmax + 15) / 16 * 16;    // K / W panels are chunk-major in 16-column chunks (kw_at)
     if (params) b->prm = *params; else ekfvio_default_params(&b->prm);
     size_t F = b->F, nm = b->nmax > 0 ? b->nmax : 1;
     size_t Pbytes = F * b->ldP * b->ldP * sizeof(double), Kbytes = F * b->ldP * b->ldK * sizeof(double);
@@ -93,8 +94,12 @@ int ekfvio_batch_create(ekfvio_batch** out, int device, int num_filters, int max
     ALLOC(b->d_idx, F * b->mmax * sizeof(int));
     ALLOC(b->d_m, F * sizeof(int));
     ALLOC(b->d_asym, F * sizeof(int));
-    if (gain_general_smem_doubles(b->mmax) == 0) ALLOC(b->d_S, F * ((size_t)b->mmax * b->mmax + b->mmax) * sizeof(double));
     if (b->Nmax <= 176 && b->mmax <= 104) ALLOC(b->d_L, F * gain_tiled_scratch_doubles(b->mmax) * sizeof(double));
+    if (b->large) {
+        ALLOC(b->d_LS, F * large_scratch_doubles_S(b->mmax) * sizeof(double));
+        ALLOC(b->d_LL, F * large_scratch_doubles_S(b->mmax) * sizeof(double));
+        ALLOC(b->d_LT, F * large_scratch_doubles_T(b->mmax) * sizeof(double));
+    }
     ALLOC(b->dd_z, F * nm * 2 * sizeof(double));
     ALLOC(b->dd_R, F * nm * 4 * sizeof(double));
     ALLOC(b->dd_pass, F * nm);
@@ -156,25 +161,35 @@ int ekfvio_batch_linearize(ekfvio_batch* b, const double* d_dt, double* d_F, voi
 int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, const uint8_t* d_pass, void* stream) {
     CU(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
-    {
-        EkfPtrs pp = ptrs(b);
-        if (!(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | 0x100u)) && gain_tiled_supported(pp)) {
-            b->timer.begin(1, st);
-            CU(launch_gain_tiled(0, pp, b->d_P[b->cur], d_z, d_R, d_pass, st));
-            b->timer.end(st);
-            b->timer.begin(3, st);
-            CU(launch_gain_tiled(1, pp, b->d_P[b->cur], d_z, d_R, d_pass, st));
-            b->timer.end(st);
-            b->launches += 1;
-        } else {
-            b->timer.begin(1, st);
-            CU(launch_gain_general(pp, b->d_P[b->cur], d_z, d_R, d_pass, b->d_S, st));
-            b->timer.end(st);
+    EkfPtrs pp = ptrs(b);
+    const bool general = (b->prm.flags & EKFVIO_FLAG_FORCE_GENERAL_PATH) != 0;
+    if (b->large && !general) {   // blocked multi-CTA-per-filter path for large states
+        LargePtrs lp;
+        lp.S = b->d_LS; lp.L = b->d_LL; lp.T = b->d_LT;
+        lp.mp = (b->mmax + 63) / 64 * 64; lp.nblk = lp.mp / 64; lp.nrt_max = (b->Nmax + 63) / 64;
+        CU(launch_update_large(pp, lp, b->d_P[b->cur], b->d_P[b->cur ^ 1], d_z, d_R, d_pass, st, &b->launches, &b->timer));
+        b->cur ^= 1;
+        return 0;
+    }
+    if (!(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | 0x100u)) && gain_tiled_supported(pp)) {
+        b->timer.begin(1, st);
+        CU(launch_gain_tiled(0, pp, b->d_P[b->cur], d_z, d_R, d_pass, st));
+        b->timer.end(st);
+        b->timer.begin(3, st);
+        CU(launch_gain_tiled(1, pp, b->d_P[b->cur], d_z, d_R, d_pass, st));
+        b->timer.end(st);
+        b->launches += 1;
+    } else {
+        if (!b->d_S && gain_general_smem_doubles(b->mmax) == 0) {
+            size_t bytes = (size_t)b->F * ((size_t)b->mmax * b->mmax + b->mmax) * sizeof(double);
+            CU(cudaMalloc((void**)&b->d_S, bytes));
         }
+        b->timer.begin(1, st);
+        CU(launch_gain_general(pp, b->d_P[b->cur], d_z, d_R, d_pass, b->d_S, st));
+        b->timer.end(st);
     }
     b->timer.begin(2, st);
     {
-        EkfPtrs pp = ptrs(b);
         const bool tiled = !(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | 0x200u)) && joseph_tiled_supported(pp);
         const bool sym = tiled && !(b->prm.flags & 0x400u) && joseph_sym_supported(pp);
         if (sym) {   // symmetric filters: lower-triangle kernel; the (rare) asymmetric ones: full kernel

@@ -149,6 +149,10 @@ struct ekfvio_batch {
     double* d_W = nullptr;         // [F][ldK/16][ldP][16]   Joseph residual panel
     double* d_S = nullptr;         // [F][mmax][mmax] (general path only; lazily allocated)
     double* d_L = nullptr;         // [F][tiles] Cholesky factor + inverse diagonal tiles (tiled path)
+    double* d_LS = nullptr;        // large path: S [F][mp][mp]
+    double* d_LL = nullptr;        // large path: L [F][mp][mp]
+    double* d_LT = nullptr;        // large path: diagonal-block tiles + inverses
+    bool large = false;
     double* d_y = nullptr;         // [F][mmax]
     int* d_idx = nullptr;          // [F][mmax]
     int* d_m = nullptr;            // [F]

@@ -4,6 +4,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "timing.h"
+
 namespace ekfvio {
 
 // Plain device-pointer bundle passed by value to every EKF kernel.
@@ -37,6 +39,13 @@ cudaError_t launch_gain_tiled(int which, const EkfPtrs& p, const double* Pin, co
 cudaError_t launch_joseph_tiled(const EkfPtrs& p, const double* Pin, double* Pout, int only_asym, cudaStream_t st);
 bool joseph_sym_supported(const EkfPtrs& p);
 cudaError_t launch_joseph_sym(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st);
+
+// large-state blocked path (ekf_large.cu)
+struct LargePtrs { double* S; double* L; double* T; int mp; int nblk; int nrt_max; };
+size_t large_scratch_doubles_S(int mmax);
+size_t large_scratch_doubles_T(int mmax);
+cudaError_t launch_update_large(const EkfPtrs& p, const LargePtrs& lp, const double* Pin, double* Pout, const double* z, const double* R,
+                                const uint8_t* pass, cudaStream_t st, long long* launches, KernelTimer* timer);
 
 // FP64 peak probe (fp64_peak.cu)
 cudaError_t measure_fp64_peak(double* dmma_tflops, double* dfma_tflops);

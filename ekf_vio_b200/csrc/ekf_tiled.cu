@@ -11,24 +11,11 @@
 // is bank-conflict free.
 #include "ekf_common.cuh"
 #include "ekf_kernels.h"
+#include "ekf_tiles.cuh"
 
 using namespace ekfvio;
 
 namespace {
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-// A global load the compiler may not sink below later volatile asm (the DMMAs): keeps software
-// prefetches one block ahead of their use.
-__device__ __forceinline__ double ldg_pinned(const double* p) {
-    double v;
-    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 constexpr int JT = 11;              // column tiles per pass
 constexpr int KC = 16;              // k-chunk depth
@@ -164,20 +151,6 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const 
 // distinct banks per half-warp.  Each warp then owns a 16-row strip of Sigma(:,idx) and carries it
 // through both triangular solves entirely in registers (right-looking, 8-wide column blocks,
 // diagonal blocks applied through their explicit 8x8 inverses).
-__device__ __forceinline__ int tsw(int r, int c) { return r * 8 + (c ^ (((r >> 1) & 1) << 2)); }
-__device__ __forceinline__ int tile_of(int ib, int jb) { return (ib * (ib + 1) / 2 + jb) * 64; }
-
-// C-fragment (row = lane/4, cols 2q,2q+1) -> the two A-fragments (row = lane/4, k = q + 4kk)
-__device__ __forceinline__ void cfrag_to_afrag(double c0, double c1, int lane, double& a0, double& a1) {
-    const int q = lane & 3, base = lane & ~3;
-    double v0 = __shfl_sync(0xffffffffu, c0, base | (q >> 1));
-    double v1 = __shfl_sync(0xffffffffu, c1, base | (q >> 1));
-    a0 = (q & 1) ? v1 : v0;
-    v0 = __shfl_sync(0xffffffffu, c0, base | 2 | (q >> 1));
-    v1 = __shfl_sync(0xffffffffu, c1, base | 2 | (q >> 1));
-    a1 = (q & 1) ? v1 : v0;
-}
-
 // Kernel 1 of 2: measurement map, residual vector, lower(S) from upper(S), blocked right-looking
 // Cholesky (8x8 tiles) and the explicit inverses of the diagonal tiles.  128 threads per filter
 // and ~54 KB of shared memory, so four filters share an SM and hide each other's serial
@@ -275,81 +248,7 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
     }
     __syncthreads();
 
-    for (int jb = 0; jb < nb; ++jb) {
-        if (warp == 0) {   // diagonal tile: lane rr (< 8) owns row rr
-            double* T = Ls + tile_of(jb, jb);
-            const int rr = lane & 7;
-            double a[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) a[c] = T[tsw(rr, c)];
-            bool bad = false;
-            double rd[8];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                double dcc = __shfl_sync(0xffffffffu, a[c], c);
-                if (!(dcc > 0.0)) bad = true;
-                double piv = sqrt(dcc);
-                double rpiv = 1.0 / piv;       // one reciprocal per column instead of a division per row
-                rd[c] = rpiv;
-                if (rr == c) a[c] = piv; else if (rr > c) a[c] = a[c] * rpiv;
-#pragma unroll
-                for (int c2 = c + 1; c2 < 8; ++c2) {
-                    double l = __shfl_sync(0xffffffffu, a[c], c2);
-                    if (rr >= c2) a[c2] -= a[c] * l;
-                }
-            }
-            // column j = rr of inv(L): forward substitution with rows fetched by shuffle
-            double x[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                double sacc = (i == rr) ? 1.0 : 0.0;
-#pragma unroll
-                for (int k = 0; k < i; ++k) sacc -= __shfl_sync(0xffffffffu, a[k], i) * x[k];
-                x[i] = sacc * rd[i];
-            }
-            if (lane < 8) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) T[tsw(rr, c)] = (c <= rr) ? a[c] : 0.0;
-                double* I8 = Li + jb * 64;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) I8[tsw(i, rr)] = (i >= rr) ? x[i] : 0.0;
-                if (bad && lane == 0) s_bad = 1;
-            }
-        }
-        __syncthreads();
-        {   // panel: L(ib,jb) = A(ib,jb) * inv(Ljj)'
-            const double* I8 = Li + jb * 64;
-            double b0 = I8[tsw(r, q)], b1 = I8[tsw(r, 4 + q)];
-            for (int ib = jb + 1 + warp; ib < nb; ib += NWC) {
-                double* T = Ls + tile_of(ib, jb);
-                double a0 = T[tsw(r, q)], a1 = T[tsw(r, 4 + q)];
-                double c0 = 0.0, c1 = 0.0;
-                dmma884(c0, c1, a0, b0);
-                dmma884(c0, c1, a1, b1);
-                __syncwarp();
-                *reinterpret_cast<double2*>(&T[tsw(r, 2 * q)]) = make_double2(c0, c1);
-            }
-        }
-        __syncthreads();
-        {   // trailing update: A(ib,kb) -= L(ib,jb) L(kb,jb)'  for ib >= kb > jb
-            const int t = nb - 1 - jb;
-            for (int e = warp; e < t * (t + 1) / 2; e += NWC) {
-                int ii = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
-                while (ii * (ii + 1) / 2 > e) --ii;
-                while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
-                int kk2 = e - ii * (ii + 1) / 2;
-                int ib = jb + 1 + ii, kb = jb + 1 + kk2;
-                const double* TA = Ls + tile_of(ib, jb);
-                const double* TB = Ls + tile_of(kb, jb);
-                double* TC = Ls + tile_of(ib, kb);
-                double2 c = *reinterpret_cast<double2*>(&TC[tsw(r, 2 * q)]);
-                dmma884(c.x, c.y, -TA[tsw(r, q)], TB[tsw(r, q)]);
-                dmma884(c.x, c.y, -TA[tsw(r, 4 + q)], TB[tsw(r, 4 + q)]);
-                *reinterpret_cast<double2*>(&TC[tsw(r, 2 * q)]) = c;
-            }
-        }
-        __syncthreads();
-    }
+    chol_tiles<NWC>(Ls, Li, nb, &s_bad);
     if (tid == 0 && s_bad) atomicOr(&p.status[f], 1);
     // factor and inverse tiles to global scratch (same swizzled layout)
     double* Lg = p.L + (size_t)f * (NT + NB) * 64;

@@ -296,3 +296,30 @@ def test_capacities_of_every_alignment(cuda, nmax):
         b.update(*torch_inputs(z, R, passed))
         assert_close(gpu_state(b, 0), orc.state(), what=f"nmax={nmax} filter 0 step {s}")
         assert_close(gpu_state(b, 1), orc2.state(), what=f"nmax={nmax} filter 1 step {s}")
+
+
+@pytest.mark.parametrize("n,frac,asym", [(60, 1.0, False), (64, 0.6, True), (150, 0.8, False)])
+def test_large_state_blocked_path(cuda, n, frac, asym):
+    """n > 51 takes the blocked multi-CTA path (ekf_large.cu): 64-wide column blocks, ragged m, asymmetric R."""
+    rng = np.random.default_rng(n)
+    uv = rng.uniform(-0.9, 0.9, (n, 2))
+    orc = O.OracleFilter(); orc.add_features(uv)
+    b = make_batch(2, n)
+    b.add_features_h(np.array([n, n], np.int32), np.stack([uv, uv]))
+    mu = orc.state()["mu"]; mu[7:10] = [0.15, -0.1, 0.05]; mu[10:13] = [0.03, 0.07, -0.04]
+    st = orc.state(); orc.set_state(mu=mu, feat=st["feat"], Pm=st["P"])
+    b.set_state(mu=np.stack([mu, mu]))
+    R = np.tile(np.array([1e-5, 0, 0, 1e-5]), (2, n, 1))
+    if asym:
+        R[:, :, 1] = 2e-6; R[:, :, 2] = 5e-7
+    for s in range(2):
+        orc.process(0.05); b.process(0.05)
+        assert_close(gpu_state(b, 1), orc.state(), what=f"large n={n} process {s}")
+        passed = (rng.uniform(size=(1, n)) < frac).astype(np.uint8).repeat(2, 0)
+        z = np.repeat((orc.state()["feat"][:, :2] + rng.normal(0, 1e-3, (n, 2)))[None], 2, 0)
+        orc.update(z[0], R[0], passed[0]); b.update(*torch_inputs(z, R, passed))
+        g0, g1, o = gpu_state(b, 0), gpu_state(b, 1), orc.state()
+        assert_close(g0, o, what=f"large n={n} update {s}")
+        np.testing.assert_array_equal(g0["P"], g1["P"])          # the two identical filters of the batch agree bit for bit
+        np.testing.assert_array_equal(g0["flags"], o["flags"])
+        assert g0["status"] == 0
