@@ -342,14 +342,23 @@ int ekfvio_batch_update_h(ekfvio_batch* b, const double* h_z, const double* h_R,
     cudaStream_t st = (cudaStream_t)stream;
     size_t F = b->F, nm = b->nmax;
     if (nm == 0) return ekfvio_batch_update(b, b->dd_z, b->dd_R, b->dd_pass, stream);
-    // the staging buffers are reused: wait for the previous consumer before overwriting them
-    CU(cudaStreamSynchronize(st));
-    memcpy(b->h_z, h_z, F * nm * 2 * sizeof(double));
-    memcpy(b->h_R, h_R, F * nm * 4 * sizeof(double));
-    memcpy(b->h_pass, h_pass, F * nm);
-    CU(cudaMemcpyAsync(b->dd_z, b->h_z, F * nm * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(b->dd_R, b->h_R, F * nm * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(b->dd_pass, b->h_pass, F * nm, cudaMemcpyHostToDevice, st));
+    // page-locked caller buffers are DMA'd from where they are; pageable ones are staged through the
+    // batch's pinned buffers (reused: wait for the previous consumer before overwriting them)
+    const void* src[3] = {h_z, h_R, h_pass};
+    void* stg[3] = {b->h_z, b->h_R, b->h_pass};
+    void* dst[3] = {b->dd_z, b->dd_R, b->dd_pass};
+    const size_t bytes[3] = {F * nm * 2 * sizeof(double), F * nm * 4 * sizeof(double), F * nm};
+    bool synced = false;
+    for (int i = 0; i < 3; ++i) {
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, src[i]) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (!pinned) {
+            cudaGetLastError();
+            if (!synced) { CU(cudaStreamSynchronize(st)); synced = true; }
+            memcpy(stg[i], src[i], bytes[i]);
+        }
+        CU(cudaMemcpyAsync(dst[i], pinned ? src[i] : stg[i], bytes[i], cudaMemcpyHostToDevice, st));
+    }
     return ekfvio_batch_update(b, b->dd_z, b->dd_R, b->dd_pass, stream);
 }
 

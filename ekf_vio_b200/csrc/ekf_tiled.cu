@@ -17,6 +17,13 @@ using namespace ekfvio;
 
 namespace {
 
+#ifdef EKFVIO_PROFILE_CLOCKS
+__device__ unsigned long long g_clk[8];
+#define CLK_MARK(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(&g_clk[i], (unsigned long long)(t_ - t_prev)); t_prev = t_; } } while (0)
+#else
+#define CLK_MARK(i) do {} while (0)
+#endif
+
 constexpr int JT = 11;              // column tiles per pass
 constexpr int KC = 16;              // k-chunk depth
 constexpr int NST = 3;              // cp.async stages
@@ -212,7 +219,6 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
         return;
     }
     const int nb = (m + 7) >> 3;
-    const int r = lane >> 2, q = lane & 3;
 
     // lower(a,b), a >= b  <-  upper(S)(b,a) = Sigma(idx[b], idx[a]) + R(b,a)  (SimplicialLDLT::compute(S')
     // reads upper(S), :578); identity tail.  Four independent gathers in flight per thread.
@@ -274,6 +280,9 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m = p.m[f];
     if (m == 0) return;
+#ifdef EKFVIO_PROFILE_CLOCKS
+    long long t_prev = clock64();
+#endif
     const int n = p.nfeat[f], N = BASE + 3 * n;
     const int ld = p.ldP, ldK = p.ldK, nmax = p.nmax;
     const double* Pi = Pin + (size_t)f * ld * ld;
@@ -296,6 +305,21 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
         for (int a = tid; a < NB * 8; a += NW * 32) { s_idx[a] = a < m ? idx_g[a] : 0; s_y[a] = a < m ? y_g[a] : 0.0; }
     }
     __syncthreads();
+    // this warp's 16-row strip of Sigma(:,idx): the gathers are issued now, so that their latency
+    // overlaps with the arrival of the L tiles
+    const int i0 = warp * 16;
+    double k0[2][NB], k1[2][NB];
+#pragma unroll
+    for (int rt = 0; rt < 2; ++rt) {
+        const int row = i0 + rt * 8 + r;
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) {
+            int a = jb * 8 + 2 * q;
+            bool ok = row < N && a < m && jb < nb;
+            k0[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a]] : 0.0;
+            k1[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a + 1]] : 0.0;
+        }
+    }
     // inverse measurement map: state row -> measurement index (or -1); identity tail rows of Ss
     for (int i = tid; i < ld; i += NW * 32) s_inv[i] = -1;
     __syncthreads();
@@ -307,19 +331,11 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
     cp_async_wait<0>();
     __syncthreads();
 
-    const int i0 = warp * 16;
+    CLK_MARK(4);
     if (i0 < N) {
-        double k0[2][NB], k1[2][NB];
 #pragma unroll
         for (int rt = 0; rt < 2; ++rt) {
             const int row = i0 + rt * 8 + r;
-#pragma unroll
-            for (int jb = 0; jb < NB; ++jb) {
-                int a = jb * 8 + 2 * q;
-                bool ok = row < N && a < m && jb < nb;
-                k0[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a]] : 0.0;
-                k1[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a + 1]] : 0.0;
-            }
             // a measured state row of Sigma(:,idx) is a row of S = Sigma(idx,idx) + R: the full S (no
             // symmetry assumed) is assembled from the strips instead of being gathered a second time
             const int am = row < N ? s_inv[row] : -1;
@@ -367,6 +383,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
                 }
             }
         }
+        CLK_MARK(5);
         // backward: K L = Z
 #pragma unroll
         for (int jr = 0; jr < NB; ++jr) {
@@ -417,6 +434,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
             if (q == 0 && row < N) { if (row < BASE) mu_g[row] += dot; else feat_g[row - BASE] += dot; }
         }
     }
+    CLK_MARK(6);
     __syncthreads();   // every strip has contributed its rows of S, and K is in global memory
     if (i0 < N) {
         // W = Sigma(:,idx) - K S with the full S
@@ -467,6 +485,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
         }
     }
     __syncthreads();
+    CLK_MARK(7);
     if (tid == 0) {  // renormalise the quaternion (:605-609) and flag non-finite states
         double qn = sqrt(mu_g[3] * mu_g[3] + mu_g[4] * mu_g[4] + mu_g[5] * mu_g[5] + mu_g[6] * mu_g[6]);
         mu_g[3] /= qn; mu_g[4] /= qn; mu_g[5] /= qn; mu_g[6] /= qn;
@@ -493,12 +512,6 @@ cudaError_t launch_gain_tiled_t(int which, const EkfPtrs& p, const double* Pin, 
     return cudaGetLastError();
 }
 
-#ifdef EKFVIO_PROFILE_CLOCKS
-__device__ unsigned long long g_clk[8];
-#define CLK_MARK(i) do { if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(&g_clk[i], (unsigned long long)(t_ - t_prev)); t_prev = t_; } } while (0)
-#else
-#define CLK_MARK(i) do {} while (0)
-#endif
 // ---------------------------------------------------------------------------------------------
 // ekf_joseph_sym: the covariance update for filters whose Sigma and R are symmetric (the normal
 // case; p.asym[f] == 0).  Only the 16x16 blocks on or below the diagonal are computed —

@@ -191,14 +191,26 @@ int ekfvio_klt_track_pair_h(ekfvio_klt* k, const uint8_t* h_prev, const uint8_t*
     const Level& L0 = k->pyr.lv[0];
     uint8_t* s0 = k->d_slots;                   // slot 0 <- prev
     uint8_t* s1 = k->d_slots + k->slot_bytes;   // slot 1 <- next
-    // frames go straight into level 0 of the slots (no staging copy on the device)
+    // frames go straight into level 0 of the slots (no staging copy on the device).  Page-locked caller
+    // buffers are DMA'd from where they are; pageable ones go through the tracker's pinned staging area.
     for (int which = 0; which < 2; ++which) {
         const uint8_t* h = which ? h_next : h_prev;
-        uint8_t* stage = k->h_img + (size_t)which * L0.img_stride * k->max_batch;
-        for (int b = 0; b < batch; ++b)
-            for (int y = 0; y < k->height; ++y)
-                memcpy(stage + (size_t)b * L0.img_stride + (size_t)y * L0.pitch, h + ((size_t)b * k->height + y) * pitch, (size_t)k->width);
-        CU(cudaMemcpyAsync((which ? s1 : s0) + L0.img_off, stage, L0.img_stride * batch, cudaMemcpyHostToDevice, st));
+        uint8_t* dst = (which ? s1 : s0) + L0.img_off;
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, h) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (!pinned) cudaGetLastError();
+        if (pinned && L0.img_stride == (size_t)L0.pitch * k->height) {
+            CU(cudaMemcpy2DAsync(dst, L0.pitch, h, pitch, k->width, (size_t)k->height * batch, cudaMemcpyHostToDevice, st));
+        } else if (pinned) {
+            for (int b = 0; b < batch; ++b)
+                CU(cudaMemcpy2DAsync(dst + (size_t)b * L0.img_stride, L0.pitch, h + (size_t)b * k->height * pitch, pitch, k->width, k->height, cudaMemcpyHostToDevice, st));
+        } else {
+            uint8_t* stage = k->h_img + (size_t)which * L0.img_stride * k->max_batch;
+            for (int b = 0; b < batch; ++b)
+                for (int y = 0; y < k->height; ++y)
+                    memcpy(stage + (size_t)b * L0.img_stride + (size_t)y * L0.pitch, h + ((size_t)b * k->height + y) * pitch, (size_t)k->width);
+            CU(cudaMemcpyAsync(dst, stage, L0.img_stride * batch, cudaMemcpyHostToDevice, st));
+        }
     }
     size_t npt = (size_t)batch * k->max_points;
     float* hp = k->h_pts;

@@ -11,4 +11,4 @@ for s in range(6):
     b.process(0.05); b.update(dm[s], R, ps); torch.cuda.synchronize()
     capi.lib.ekfvio_debug_clocks(out, 1)
     v = np.array(list(out), dtype=np.float64) / F
-    print("step", s, "cycles per CTA: setup+phase0 prologue marks:", v[:4].round(0))
+    print("step", s, "joseph marks", v[:4].round(0), "solve marks [setup, S+fwd, bwd+store, W+store]", v[4:8].round(0))
