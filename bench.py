@@ -185,12 +185,13 @@ def bench_ekf(args, rank, world, local):
     batch.reset()
     batch.add_features_h(kvec, init_uv)
     h_mu = np.zeros((F, 22)); h_feat = np.zeros((F, n, 3))
-    meas_np = h_meas.numpy()
+    meas_np = h_meas.numpy()                                   # page-locked: the C ABI DMAs straight from it
+    R_pin = torch.from_numpy(R).pin_memory().numpy(); passed_pin = torch.from_numpy(passed).pin_memory().numpy()
 
     def run_e2e(a, b):
         for s in range(a, b):
             batch.process(DT)
-            batch.update_h(meas_np[s], R, passed)
+            batch.update_h(meas_np[s], R_pin, passed_pin)
             batch.read_mu_h(h_mu, h_feat)
 
     run_e2e(0, W)
@@ -267,7 +268,8 @@ def bench_klt(args, rank, world, local):
     good = d_status.bool()
     fl = (d_out - d_pts)[good].mean(0).cpu().numpy() if bool(good.any()) else np.zeros(2)
 
-    # e2e: host images + points in, host results out
+    # e2e: host images + points in (page-locked host memory), host results out
+    prev = torch.from_numpy(prev).pin_memory().numpy(); nxt = torch.from_numpy(nxt).pin_memory().numpy()
     nn = pts.copy()
     npts_h = np.full(B, npts, np.int32)
     for _ in range(max(1, W // 2)):

@@ -101,9 +101,11 @@ int ekfvio_batch_get_state(ekfvio_batch* b, double* h_mu, double* h_feat, double
 int ekfvio_batch_set_state(ekfvio_batch* b, const double* h_mu, const double* h_feat, const double* h_P, const int* h_nfeat,
                            const double* h_cache, const uint8_t* h_flags, const double* h_klt_last);
 
-/* Host-buffer convenience wrappers (the calls the C++ facade and the e2e benchmark use): inputs
- * are staged through pinned memory, copied on `stream`, and the call returns after the work is
- * enqueued (inputs are consumed before return). */
+/* Host-buffer convenience wrappers (the calls the C++ facade and the e2e benchmark use): the copies
+ * are enqueued on `stream` and the call returns after the work is enqueued.  Pageable inputs are
+ * staged through the batch's pinned buffers (consumed before return); page-locked inputs
+ * (cudaHostAlloc / cudaHostRegister) are DMA'd from where they are and must stay unchanged until
+ * the stream has passed this call. */
 int ekfvio_batch_add_features_h(ekfvio_batch* b, const int* h_k, const double* h_uv, int kmax, void* stream);
 int ekfvio_batch_update_h(ekfvio_batch* b, const double* h_z, const double* h_R, const uint8_t* h_pass, void* stream);
 /* numericallyLinearizeProcess with one dt for all filters, Jacobians to HOST memory
