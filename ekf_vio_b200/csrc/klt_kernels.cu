@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
             }
         }
         __syncwarp();
-        long long a11 = 0, a12 = 0, a22 = 0;
+        int sa11 = 0, sa12 = 0, sa22 = 0;     // per-lane partial sums fit 32 bits (<= 31 slots x 4080^2)
         for (int e = lane, y = y_first, x = x_first; e < area; e += 32) {
             const int o = y * jw1 + x;
             const int ival = (Jt[o] * w00 + Jt[o + 1] * w01 + Jt[o + jw1] * w10 + Jt[o + jw1 + 1] * w11 + (1 << 8)) >> 9;
@@ -260,11 +260,11 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
             const int iyval = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << 13)) >> 14;
             Ip[e] = (short)ival;
             dI[e] = make_short2((short)ixval, (short)iyval);
-            a11 += ixval * ixval; a12 += ixval * iyval; a22 += iyval * iyval;
+            sa11 += ixval * ixval; sa12 += ixval * iyval; sa22 += iyval * iyval;
             y += qstep; x += rstep;
             if (x >= win) { x -= win; ++y; }
         }
-        a11 = warp_sum_ll(a11); a12 = warp_sum_ll(a12); a22 = warp_sum_ll(a22);
+        const long long a11 = warp_sum_ll(sa11), a12 = warp_sum_ll(sa12), a22 = warp_sum_ll(sa22);
         float A11 = (float)a11 * FLT_SCALE, A12 = (float)a12 * FLT_SCALE, A22 = (float)a22 * FLT_SCALE;
         float D = A11 * A22 - A12 * A12;
         float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
@@ -284,16 +284,16 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
             lk_weights(nx - inx, ny - iny, w00, w01, w10, w11);
             __syncwarp();
             stage_u8(J, L, inx, iny);
-            long long b1 = 0, b2 = 0;
+            int sb1 = 0, sb2 = 0;                 // <= 31 slots x 8160 x 4080 fits 32 bits
             for (int e = lane, y = y_first, x = x_first; e < area; e += 32) {
                 const uint8_t* jp = Jt + y * jw1 + x;
                 const int diff = ((jp[0] * w00 + jp[1] * w01 + jp[jw1] * w10 + jp[jw1 + 1] * w11 + (1 << 8)) >> 9) - Ip[e];
                 const short2 d = dI[e];
-                b1 += diff * d.x; b2 += diff * d.y;
+                sb1 += diff * d.x; sb2 += diff * d.y;
                 y += qstep; x += rstep;
                 if (x >= win) { x -= win; ++y; }
             }
-            b1 = warp_sum_ll(b1); b2 = warp_sum_ll(b2);
+            const long long b1 = warp_sum_ll(sb1), b2 = warp_sum_ll(sb2);
             float fb1 = (float)b1 * FLT_SCALE, fb2 = (float)b2 * FLT_SCALE;
             float dx = (A12 * fb2 - A22 * fb1) * D, dy = (A12 * fb1 - A11 * fb2) * D;
             nx += dx; ny += dy;
