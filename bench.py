@@ -304,7 +304,10 @@ def bench_klt(args, rank, world, local):
         "kernel_ms": {"pyr_level0": ms_l0, "pyramids_per_step": pyr_ms, "track": kms[4] / max(kcnt[4], 1)},
         "roofline": {"bound": "hbm", "kernel": "klt_level_kernel (pyramid + Scharr, all levels of both images)",
                      "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                     "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     # level-0 launch of 64 pairs in profiles/r01_ncu_traffic.txt: 39.3 MB read + 80.5 MB written (the rest of the
+                     # 127.8 MB algorithmic bytes is still in L2 when the kernel ends), scaled per pair
+                     "traffic": (39.33e6 + 80.51e6) / 64 * B, "peak_source": peaks["source"],
                      "level0_achieved": bytes_l0 / (ms_l0 * 1e-3) / 1e9},
     }
     trk.close()
@@ -444,7 +447,10 @@ def main():
             "e2e": ekf["e2e"],
             "gpu_launches": ekf["launches"] + (klt["gpu_launches"] if klt else 0),
             "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA.8x8x4 / DFMA share one pipe on sm_100)", "kernel": "covariance (Joseph) update",
-                         "achieved": cov_achieved, "peak": peak, "unit": "TFLOP/s", "frac": cov_achieved / peak if peak else None, "traffic": None,
+                         "achieved": cov_achieved, "peak": peak, "unit": "TFLOP/s", "frac": cov_achieved / peak if peak else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ekf_joseph_sym from the ncu --set full capture in
+                         # profiles/r01_ncu_traffic.txt (870.8 MB for 1184 filters), scaled to this launch's filter count
+                         "traffic": 870.8e6 / 1184 * F if n == 50 else None,
                          "peak_source": "measured live by ekfvio_measure_fp64_peak (register-resident DMMA/DFMA loops); MEASURED_PEAKS.json has no FP64 entry",
                          "flops_per_launch": F * flops_cov_update(n),
                          "whole_step": {"flops_per_filter_step": fstep, "achieved": step_achieved, "frac": step_achieved / peak if peak else None}},
