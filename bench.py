@@ -45,6 +45,13 @@ def flops_cov_update(n: int) -> float:
     return 4.0 * N * N * m
 
 
+def ekf_config(F: int, n: int, world: int) -> dict:
+    """The workload both arms (ours and --impl reference) are measured on: BASELINE.json configs[2]."""
+    return {"workload": f"batched EKF: {F} filters/GPU x (22+3*{n})-dim state, process(dt)+update(all {n} measured) per step, dt={DT}",
+            "l2": "working set per step (two 1.0 GB Sigma buffers + 1.3 GB gain panels at 4096 filters) is larger than the 126 MB L2; no flush needed",
+            "filters_total": F * world, "features": n}
+
+
 KLT_BYTES_WITH_DERIVS = 2_140_800   # SURVEY.md §8d, 640x480 levels 0-3, read once + write levels 1-3 + int16x2 derivatives
 KLT_BYTES_NO_DERIVS = 508_800
 
@@ -392,7 +399,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "EKF filter-steps/s", "value": v, "unit": "filter-steps/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * args.filters / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"batched EKF: {args.filters} filters/GPU x (22+3*{N_FEAT})-dim state, process(dt)+update(all measured) per step",
+        "config": {**ekf_config(args.filters, N_FEAT, 1),
                    "note": "reference EKF cannot be compiled here (Eigen/ROS/OpenCV C++ headers absent): FP64 oracle port timed on a bounded sample"},
         "cpu_baseline": {**t, "value": v},
         "e2e": {"value": v, "unit": "filter-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -440,9 +447,7 @@ def main():
         line = {
             "metric": "EKF filter-steps/s", "value": ekf["value"], "unit": "filter-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ekf["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"batched EKF: {F} filters/GPU x (22+3*{n})-dim state, process(dt)+update(all {n} measured) per step, dt={DT}",
-                       "l2": "working set per step (two 1.0 GB Sigma buffers + 1.5 GB gain panels at 4096 filters) is larger than the 126 MB L2; no flush needed",
-                       "filters_total": F * world, "features": n},
+            "config": ekf_config(F, n, world),
             "clocks": ekf["clocks"],
             "e2e": ekf["e2e"],
             "gpu_launches": ekf["launches"] + (klt["gpu_launches"] if klt else 0),
