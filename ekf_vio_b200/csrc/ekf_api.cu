@@ -137,10 +137,9 @@ int ekfvio_batch_add_features(ekfvio_batch* b, const int* d_k, const double* d_u
 int ekfvio_batch_process(ekfvio_batch* b, const double* d_dt, void* stream) {
     CU(cudaSetDevice(b->device));
     b->timer.begin(0, (cudaStream_t)stream);
-    CU(launch_process_general(ptrs(b), b->d_P[b->cur], b->d_P[b->cur ^ 1], d_dt, 0, nullptr, (cudaStream_t)stream));
+    CU(launch_process_general(ptrs(b), b->d_P[b->cur], b->d_P[b->cur ^ 1], d_dt, 0, nullptr, (cudaStream_t)stream, &b->launches));
     b->timer.end((cudaStream_t)stream);
     b->cur ^= 1;
-    b->launches += 1;
     return 0;
 }
 
@@ -153,8 +152,7 @@ int ekfvio_batch_process_dt(ekfvio_batch* b, double dt, void* stream) {
 
 int ekfvio_batch_linearize(ekfvio_batch* b, const double* d_dt, double* d_F, void* stream) {
     CU(cudaSetDevice(b->device));
-    CU(launch_process_general(ptrs(b), b->d_P[b->cur], nullptr, d_dt, 1, d_F, (cudaStream_t)stream));
-    b->launches += 1;
+    CU(launch_process_general(ptrs(b), b->d_P[b->cur], nullptr, d_dt, 1, d_F, (cudaStream_t)stream, &b->launches));
     return 0;
 }
 

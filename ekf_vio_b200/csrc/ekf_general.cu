@@ -130,7 +130,15 @@ __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const do
     __syncthreads();
     linearize_block(s, n, dt, cache_g, (p.flags & EKFVIO_FLAG_FRESH_DQ_CACHE) != 0);
 
-    if (n > 0 && tid == 0) {  // cache ends fresh for the base omega (see linearize_block)
+    // Row-split launch (gridDim.y > 1, large states): every CTA of a filter reads the old state and
+    // dq cache, so the new ones are staged in the (idle) gain panel and committed by
+    // ekf_commit_state_kernel afterwards.
+    const int ysplit = gridDim.y, yb = blockIdx.y;
+    if (ysplit > 1) {
+        double* stage = p.K + (size_t)f * ld * p.ldK;
+        mu_g = stage; feat_g = stage + BASE; cache_g = stage + BASE + 3 * p.nmax;
+    }
+    if (n > 0 && tid == 0 && yb == 0) {  // cache ends fresh for the base omega (see linearize_block)
         cache_g[0] = s.mu[10]; cache_g[1] = s.mu[11]; cache_g[2] = s.mu[12];
         cache_g[3] = s.dq[4]; cache_g[4] = s.dq[5]; cache_g[5] = s.dq[6]; cache_g[6] = s.dq[7];
     }
@@ -152,6 +160,7 @@ __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const do
     }
 
     // state propagation: features with the OLD base state (:102-104), then the base state (:107)
+    if (yb == 0)
     for (int fi = tid; fi < n; fi += blockDim.x) {
         V3 vel{s.mu[7], s.mu[8], s.mu[9]}, acc{s.mu[13], s.mu[14], s.mu[15]};
         Q4 dq{s.dq[4], s.dq[5], s.dq[6], s.dq[7]};
@@ -159,7 +168,7 @@ __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const do
         convolve_feature(dq, vel, acc, dt, s.feat[3 * fi], s.feat[3 * fi + 1], s.feat[3 * fi + 2], o);
         feat_g[3 * fi] = o[0]; feat_g[3 * fi + 1] = o[1]; feat_g[3 * fi + 2] = o[2];
     }
-    if (tid == 0) {
+    if (tid == 0 && yb == 0) {
         double o[22];
         convolve_base(s.mu, dt, o);
         for (int i = 0; i < 22; ++i) mu_g[i] = o[i];
@@ -296,13 +305,13 @@ __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const do
                 double pb[22];
 #pragma unroll
                 for (int k = 0; k < 22; ++k) pb[k] = Pi[(size_t)k * ld + c];
-                for (int i = g; i < BASE; i += G) {
+                for (int i = yb + ysplit * g; i < BASE; i += ysplit * G) {
                     double acc = 0.0;
 #pragma unroll
                     for (int k = 0; k < 22; ++k) acc += s.A[i * 23 + k] * pb[k];
                     Po[(size_t)i * ld + c] = acc;
                 }
-                for (int r3 = g; r3 < 3 * n; r3 += G) {
+                for (int r3 = yb + ysplit * g; r3 < 3 * n; r3 += ysplit * G) {
                     int fi = r3 / 3;
                     const double* b = s.B + r3 * 9;
                     double acc = 0.0;
@@ -317,10 +326,13 @@ __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const do
         }
     }
     __syncthreads();
-    // pass 2: one warp per row, in place on the row
+    // pass 2: one warp per row, in place on the row (a CTA of a row-split launch owns base rows
+    // i = yb mod ysplit and feature rows r3 = yb mod ysplit, in both passes)
     {
         const int lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
-        for (int i = warp; i < N; i += nw) {
+        const int nb_own = (BASE - yb + ysplit - 1) / ysplit, nf_own = (3 * n - yb + ysplit - 1) / ysplit;
+        for (int t = warp; t < nb_own + nf_own; t += nw) {
+            const int i = t < nb_own ? yb + ysplit * t : BASE + yb + ysplit * (t - nb_own);
             double* row = Po + (size_t)i * ld;
             double tb[22];
 #pragma unroll
@@ -613,6 +625,18 @@ __global__ void ekf_check_sigma_kernel(EkfPtrs p, const double* P0, int* neg, do
     if (tid == 0) { neg[f] = s_ng[0]; asym[f] = s_mx[0]; }
 }
 
+// second half of a row-split process launch: staged state (gain panel) -> mu / feat, dq cache refresh
+__global__ void ekf_commit_state_kernel(EkfPtrs p) {
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int n = p.nfeat[f];
+    const double* stage = p.K + (size_t)f * p.ldP * p.ldK;
+    double* mu_g = p.mu + (size_t)f * BASE;
+    double* feat_g = p.feat + (size_t)f * p.nmax * 3;
+    for (int i = tid; i < BASE; i += blockDim.x) mu_g[i] = stage[i];
+    for (int i = tid; i < 3 * n; i += blockDim.x) feat_g[i] = stage[BASE + i];
+    if (n > 0 && tid < 7) p.cache[(size_t)f * 7 + tid] = stage[BASE + 3 * p.nmax + tid];
+}
+
 __global__ void ekf_fill_dt_kernel(double* dts, double dt, int F) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < F) dts[i] = dt;
@@ -670,7 +694,8 @@ static size_t proc_fused_smem_bytes(int nmax) {
     return proc_smem_bytes(nmax) + sizeof(double) + (9 + 6 * (PT / 32)) * Np * sizeof(double);
 }
 
-cudaError_t launch_process_general(const EkfPtrs& p, const double* Pin, double* Pout, const double* dts, int mode, double* F_out, cudaStream_t st) {
+cudaError_t launch_process_general(const EkfPtrs& p, const double* Pin, double* Pout, const double* dts, int mode, double* F_out, cudaStream_t st,
+                                   long long* launches) {
     size_t sm = proc_smem_bytes(p.nmax);
     const int fused = (mode == 0 && proc_fused_smem_bytes(p.nmax) <= 110 * 1024) ? 1 : 0;   // two CTAs per SM
     if (fused) sm = proc_fused_smem_bytes(p.nmax);
@@ -680,7 +705,15 @@ cudaError_t launch_process_general(const EkfPtrs& p, const double* Pin, double* 
         if (e != cudaSuccess) return e;
         configured = sm;
     }
-    ekf_process_general<<<p.F, PT, sm, st>>>(p, Pin, Pout, dts, mode, F_out, fused);
+    // two-pass path: split the rows of a filter over several CTAs when the batch alone cannot fill the GPU
+    int ysplit = 1;
+    if (!fused && mode == 0 && p.F < 4 * 148 && (size_t)p.ldP * p.ldK >= (size_t)BASE + 3 * p.nmax + 7) {
+        ysplit = (4 * 148 + p.F - 1) / p.F;
+        if (ysplit > 16) ysplit = 16;
+    }
+    ekf_process_general<<<dim3(p.F, ysplit), PT, sm, st>>>(p, Pin, Pout, dts, mode, F_out, fused);
+    if (ysplit > 1) ekf_commit_state_kernel<<<p.F, 128, 0, st>>>(p);
+    if (launches) *launches += ysplit > 1 ? 2 : 1;
     return cudaGetLastError();
 }
 

@@ -78,16 +78,36 @@ __global__ void __launch_bounds__(256) ekf_large_gather(EkfPtrs p, LargePtrs lp,
     double* Lg = lp.L + (size_t)f * mp * mp;
     double* Kf = p.K + (size_t)f * ld * p.ldK;
     double* Wf = p.W + (size_t)f * ld * p.ldK;
-    for (int a = part; a < me; a += nparts) {                    // S rows
-        const int ra = a < m ? idx[a] : 0;
-        for (int b = tid; b < me; b += 256) {
-            double v;
-            if (a < m && b < m) {
-                v = Pi[(size_t)ra * ld + idx[b]];
-                if ((a >> 1) == (b >> 1)) v += Rf[4 * ((ra - BASE) / 3) + (a & 1) * 2 + (b & 1)];
-            } else v = (a == b) ? 1.0 : 0.0;
-            Sg[(size_t)a * mp + b] = v;
-            if (b >= a) Lg[(size_t)b * mp + a] = v;              // lower(L)(b,a) <- upper(S)(a,b)
+    // S in 16 x 32 tiles, one warp each: rows of S and rows of lower(L) are both written in full
+    // 128-byte lines (the transpose goes through shared memory).
+    __shared__ double tile[8][16][33];
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        const int tcols = me / 32, trows = me / 16;
+        for (int t = part * 8 + warp; t < trows * tcols; t += nparts * 8) {
+            const int a0 = (t / tcols) * 16, b0 = (t % tcols) * 32;
+            const int b = b0 + lane;
+            const int cb = b < m ? idx[b] : 0;
+#pragma unroll 4
+            for (int aa = 0; aa < 16; ++aa) {
+                const int a = a0 + aa;
+                double v;
+                if (a < m && b < m) {
+                    const int ra = idx[a];
+                    v = Pi[(size_t)ra * ld + cb];
+                    if ((a >> 1) == (b >> 1)) v += Rf[4 * ((ra - BASE) / 3) + (a & 1) * 2 + (b & 1)];
+                } else v = (a == b) ? 1.0 : 0.0;
+                Sg[(size_t)a * mp + b] = v;
+                tile[warp][aa][lane] = v;
+            }
+            __syncwarp();
+            if (b0 + 31 >= a0) {                                  // lower(L)(b,a) <- upper(S)(a,b)
+                const int aa = lane & 15;
+#pragma unroll 4
+                for (int bb = lane >> 4; bb < 32; bb += 2)
+                    if (b0 + bb >= a0 + aa) Lg[(size_t)(b0 + bb) * mp + a0 + aa] = tile[warp][aa][bb];
+            }
+            __syncwarp();
         }
     }
     const int Ne = ((N + BLK - 1) / BLK) * BLK < ld ? ((N + BLK - 1) / BLK) * BLK : ld;
@@ -255,7 +275,14 @@ __global__ void __launch_bounds__(256) ekf_large_finalize(EkfPtrs p) {
     const double* y = p.y + (size_t)f * p.mmax;
     double* mu_g = p.mu + (size_t)f * BASE;
     double* feat_g = p.feat + (size_t)f * p.nmax * 3;
-    for (int i = warp; i < N; i += 8) {
+    // base rows (and the normalisation below) belong to part 0; feature rows are dealt over all parts
+    const int part = blockIdx.y, nparts = gridDim.y;
+    const int nbase_rounds = part == 0 ? (BASE + 7) / 8 : 0;
+    const int nfrows = N - BASE;
+    const int nfeat_rounds = (nfrows + 8 * nparts - 1) / (8 * nparts);
+    for (int r = 0; r < nbase_rounds + nfeat_rounds; ++r) {
+        const int i = r < nbase_rounds ? r * 8 + warp : BASE + ((r - nbase_rounds) * nparts + part) * 8 + warp;
+        if (r < nbase_rounds ? i >= BASE : i >= N) continue;
         double dot = 0.0;
         for (int k = lane; k < m; k += 32) {
             size_t o = kw_at(ld, i, k);
@@ -267,7 +294,7 @@ __global__ void __launch_bounds__(256) ekf_large_finalize(EkfPtrs p) {
         if (lane == 0) { if (i < BASE) mu_g[i] += dot; else feat_g[i - BASE] += dot; }
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && part == 0) {
         double qn = sqrt(mu_g[3] * mu_g[3] + mu_g[4] * mu_g[4] + mu_g[5] * mu_g[5] + mu_g[6] * mu_g[6]);
         mu_g[3] /= qn; mu_g[4] /= qn; mu_g[5] /= qn; mu_g[6] /= qn;
         bool fin = true;
@@ -500,7 +527,7 @@ cudaError_t launch_update_large(const EkfPtrs& p, const LargePtrs& lp, const dou
         ekf_large_trsm<2><<<dim3(rowgrp, F), 256, 0, st>>>(p, lp, jb); ++n;
         if (jb > 0) { ekf_large_gemm<<<dim3(nrt, jb, F), 256, sm, st>>>(p, lp, nullptr, nullptr, OP_BWDUPD, jb, 0); ++n; }
     }
-    ekf_large_finalize<<<F, 256, 0, st>>>(p); ++n;
+    ekf_large_finalize<<<dim3(F, 16), 256, 0, st>>>(p); ++n;
     ekf_large_gemm<<<dim3(nrt, nblk, F), 256, sm, st>>>(p, lp, nullptr, nullptr, OP_W, 0, 0); ++n;
     mark(mark_ctx, 2, st);
     ekf_large_gemm<<<dim3(nrt * (nrt + 1) / 2, 1, F), 256, sm, st>>>(p, lp, Pin, Pout, OP_JOSEPH, 0, 1); ++n;   // symmetric filters
