@@ -23,21 +23,76 @@ __device__ __forceinline__ unsigned dp4a_uu(unsigned a_u8x4, unsigned b_u8x4, un
     return d;
 }
 
-constexpr int TW = 64, TH = 32;            // input pixels per CTA tile
-constexpr int SW = TW + 16, SH = TH + 4;   // staged tile: x0-8 .. x0+TW+7 (16-byte aligned rows), y0-2 .. y0+TH+1
+constexpr int TW = 64, TH = 64;            // input pixels per CTA tile
+constexpr int SW = TW + 16, SH = TH + 4;   // staged tile: x0-8 .. x0+TW+7 (8-byte aligned rows), y0-2 .. y0+TH+1
+constexpr int RPT = 8;                     // rows per thread
+constexpr int LT = 8 * (TH / RPT);         // threads per CTA: 8 column groups (8 pixels) x TH/RPT row groups
 
-__device__ __forceinline__ int reflect_once(int p, int len) { return p < 0 ? -p : (p >= len ? 2 * len - 2 - p : p); }
+// (rows further than one reflection away are only ever staged for threads that are outside the image; clamp them)
+__device__ __forceinline__ int reflect_once(int p, int len) { p = p < 0 ? -p : (p >= len ? 2 * len - 2 - p : p); return max(0, min(p, len - 1)); }
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+// Stage one TW x TH tile (+ halo) with REFLECT_101 applied to image coordinates (one reflection
+// suffices: every level is wider than the 21-pixel window).  Only pixels x0-2 .. x0+TW are ever
+// used: the TW interior columns travel as 8-byte cp.async vectors, the two halo words (x0-4..,
+// x0+TW..) separately; tiles that overhang the right edge or unaligned sources take the word path.
+__device__ __forceinline__ void stage_tile(uint8_t (*tile)[SW], const uint8_t* __restrict__ s, int spitch, int w, int h, int x0, int y0, int tid,
+                                           bool aligned8) {
+    if (aligned8 && x0 + TW <= w) {
+        const int v = tid & 7;
+        for (int r = tid >> 3; r < SH; r += LT / 8) {
+            const int sy = reflect_once(y0 - 2 + r, h);
+            cp_async8(&tile[r][8 + v * 8], s + (size_t)sy * spitch + x0 + v * 8);
+        }
+        for (int e = tid; e < 2 * SH; e += LT) {
+            const int r = e >> 1, right = e & 1;
+            const int sy = reflect_once(y0 - 2 + r, h), xs = right ? x0 + TW : x0 - 4;
+            const uint8_t* row = s + (size_t)sy * spitch;
+            uint8_t* dst = &tile[r][right ? 8 + TW : 4];
+            if (xs >= 0 && xs + 3 < w) cp_async4(dst, row + xs);
+            else
+                *reinterpret_cast<uint32_t*>(dst) = (uint32_t)row[reflect101(xs, w)] | ((uint32_t)row[reflect101(xs + 1, w)] << 8) |
+                                                    ((uint32_t)row[reflect101(xs + 2, w)] << 16) | ((uint32_t)row[reflect101(xs + 3, w)] << 24);
+        }
+    } else {
+        const bool aligned4 = ((spitch & 3) == 0) && ((((size_t)s) & 3) == 0);
+        constexpr int WPR = TW / 4 + 2;        // words per staged row: columns 4 .. TW+11
+        for (int e = tid; e < SH * WPR; e += LT) {
+            const int r = e / WPR, wc = e % WPR + 1;
+            const int sy = reflect_once(y0 - 2 + r, h), xs = x0 - 8 + wc * 4;
+            const uint8_t* row = s + (size_t)sy * spitch;
+            uint32_t v4;
+            if (aligned4 && xs >= 0 && xs + 3 < w) v4 = *reinterpret_cast<const uint32_t*>(row + xs);
+            else v4 = (uint32_t)row[reflect101(xs, w)] | ((uint32_t)row[reflect101(xs + 1, w)] << 8) | ((uint32_t)row[reflect101(xs + 2, w)] << 16) |
+                      ((uint32_t)row[reflect101(xs + 3, w)] << 24);
+            *reinterpret_cast<uint32_t*>(&tile[r][wc * 4]) = v4;
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
 // One pyramid level: reads level l of every image once and writes (a) an optional copy into the
 // slot (level 0 fed from a caller buffer), (b) the interleaved int16 Scharr derivatives,
-// (c) level l+1 = pyrDown(level l).  grid = (tiles_x, tiles_y, images of both jobs), 256 threads.
-// Integer work is done with u8x4 dot products (IDP4A) on 32-bit windows of the staged tile, one
-// 16-byte vector store per 4 output pixels; the kernel is meant to be bound by HBM, not by issue.
-__global__ void __launch_bounds__(256) klt_level_kernel(LevelJob j0, LevelJob j1, int w, int h, int cpitch, size_t cstride, int dpitch,
-                                                        size_t dstride, int npitch, size_t nstride) {
-    __shared__ __align__(16) uint8_t tile[SH][SW];
+// (c) level l+1 = pyrDown(level l).  grid = (tiles_x, y chunks, images of both jobs), LT threads.
+// A CTA walks down its chunk of a tile column with the next tile's cp.async staging in flight while
+// it computes the current one.  A thread owns an 8 x RPT pixel block of the tile and walks down the
+// RPT + 3 staged rows it needs once: each row is three shared-memory loads; the Scharr 3x3 and the
+// pyrDown 5-tap rows are u8x4 dot products (IDP4A) on those words, the Scharr windows of the last
+// three rows stay in registers, and every global store is a full 8/16-byte vector.  The kernel is
+// meant to be bound by HBM, not by issue.
+__global__ void __launch_bounds__(LT, 16) klt_level_kernel(LevelJob j0, LevelJob j1, int w, int h, int cpitch, size_t cstride, int dpitch,
+                                                       size_t dstride, int npitch, size_t nstride, int tiles_per_cta) {
+    __shared__ __align__(16) uint8_t tiles[2][SH][SW];
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int x0 = blockIdx.x * TW;
     int b = blockIdx.z;
     const bool second = b >= j0.batch;
     if (second) b -= j0.batch;
@@ -48,103 +103,116 @@ __global__ void __launch_bounds__(256) klt_level_kernel(LevelJob j0, LevelJob j1
     if (!copy_dst && !deriv && !down) return;
     const int spitch = J.spitch;
     const uint8_t* __restrict__ s = J.src + (size_t)b * J.sstride;
-
-    // stage the tile with REFLECT_101 applied to image coordinates (one reflection suffices: the
-    // halo is at most 8 pixels and every level is wider than the 21-pixel window)
     const bool aligned8 = ((spitch & 7) == 0) && ((((size_t)s) & 7) == 0);
-    if (aligned8 && x0 >= 8 && x0 + TW + 8 <= w) {
-        for (int e = tid; e < SH * (SW / 8); e += 256) {
-            const int r = e / (SW / 8), v = e % (SW / 8);
-            const int sy = reflect_once(y0 - 2 + r, h);
-            *reinterpret_cast<uint2*>(&tile[r][v * 8]) = *reinterpret_cast<const uint2*>(s + (size_t)sy * spitch + (x0 - 8) + v * 8);
-        }
+    const int ty_begin = blockIdx.y * tiles_per_cta;
+    const int ty_end = min(ty_begin + tiles_per_cta, (h + TH - 1) / TH);
+    if (ty_begin >= ty_end) return;
+
+    stage_tile(tiles[0], s, spitch, w, h, x0, ty_begin * TH, tid, aligned8);
+    for (int ty = ty_begin; ty < ty_end; ++ty) {
+    uint8_t (*tile)[SW] = tiles[(ty - ty_begin) & 1];
+    const int y0 = ty * TH;
+    if (ty + 1 < ty_end) {
+        stage_tile(tiles[(ty + 1 - ty_begin) & 1], s, spitch, w, h, x0, y0 + TH, tid, aligned8);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
-        const bool aligned4 = ((spitch & 3) == 0) && ((((size_t)s) & 3) == 0);
-        for (int e = tid; e < SH * (SW / 4); e += 256) {
-            const int r = e / (SW / 4), wc = e % (SW / 4);
-            const int sy = reflect_once(y0 - 2 + r, h), xs = x0 - 8 + wc * 4;
-            const uint8_t* row = s + (size_t)sy * spitch;
-            uint32_t v;
-            if (aligned4 && xs >= 0 && xs + 3 < w) v = *reinterpret_cast<const uint32_t*>(row + xs);
-            else v = (uint32_t)row[reflect101(xs, w)] | ((uint32_t)row[reflect101(xs + 1, w)] << 8) | ((uint32_t)row[reflect101(xs + 2, w)] << 16) |
-                     ((uint32_t)row[reflect101(xs + 3, w)] << 24);
-            *reinterpret_cast<uint32_t*>(&tile[r][wc * 4]) = v;
-        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
 
-    if (copy_dst) {   // 32 rows x 8 eight-byte vectors = one per thread
-        const int r = tid >> 3, v = tid & 7;
-        const int y = y0 + r, x = x0 + v * 8;
-        if (y < h && x < w)   // the slot's pitch is a multiple of 16: whole vectors stay inside the row
-            *reinterpret_cast<uint2*>(copy_dst + (size_t)b * cstride + (size_t)y * cpitch + x) = *reinterpret_cast<const uint2*>(&tile[r + 2][v * 8 + 8]);
-    }
+    const int cg = tid & 7, rg = tid >> 3;
+    const int xg = cg * 8, x = x0 + xg;        // first of the thread's eight columns
+    const int yb = y0 + rg * RPT;              // first of its RPT rows
+    if (x < w && yb < h) {                     // (otherwise its pyrDown outputs are outside level l+1 as well)
+    const bool full = x + 7 < w;
+    const int dw = (w + 1) / 2, dh = (h + 1) / 2;
+    const int gx = x / 2, gy = yb / 2;
 
-    if (deriv) {
-        // Scharr: for pixel x the window bytes (x-1, x, x+1, x+2) of rows y-1, y, y+1 are dotted with the
-        // packed 3x3 weights; one thread = 8 pixels of a row.
-        const int r = tid >> 3, xg = (tid & 7) * 8;
-        const int y = y0 + r, x = x0 + xg;
-        if (y < h && x < w) {
-            unsigned o[8];
-            int ix[8], iy[8];
+    unsigned win[3][8];                        // Scharr windows (x-1, x, x+1, x+2) of the last three rows
+    unsigned acc[RPT / 2][4];                  // pyrDown sums of output rows gy .. gy + RPT/2 - 1
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { ix[j] = 0; iy[j] = 0; }
+    for (int o = 0; o < RPT / 2; ++o)
 #pragma unroll
-            for (int rr = 0; rr < 3; ++rr) {
-                const unsigned* tw = reinterpret_cast<const unsigned*>(&tile[r + 1 + rr][xg + 4]);   // word 0 = pixels xg-4 .. xg-1
-                const unsigned w0 = tw[0], w1 = tw[1], w2 = tw[2], w3 = tw[3];
-                unsigned win[8];
-                win[0] = __funnelshift_r(w0, w1, 24);
-                win[1] = w1;
-                win[2] = __funnelshift_r(w1, w2, 8);
-                win[3] = __funnelshift_r(w1, w2, 16);
-                win[4] = __funnelshift_r(w1, w2, 24);
-                win[5] = w2;
-                win[6] = __funnelshift_r(w2, w3, 8);
-                win[7] = __funnelshift_r(w2, w3, 16);
-                const int wx = (rr == 1) ? 0x000A00F6 : 0x000300FD;                   // (-10,0,10,0) / (-3,0,3,0)
-                const int wy = (rr == 0) ? 0x00FDF6FD : 0x00030A03;                   // (-3,-10,-3,0) / (3,10,3,0)
+        for (int k = 0; k < 4; ++k) acc[o][k] = 0u;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    ix[j] = dp4a_us(win[j], wx, ix[j]);
-                    if (rr != 1) iy[j] = dp4a_us(win[j], wy, iy[j]);
+    for (int i = 0; i < RPT + 3; ++i) {        // staged row rg*RPT + i  <->  image row yb - 2 + i
+        const uint8_t* tr = &tile[rg * RPT + i][xg];
+        const unsigned w0 = *reinterpret_cast<const unsigned*>(tr + 4);     // pixels x-4 .. x-1
+        const uint2 w12 = *reinterpret_cast<const uint2*>(tr + 8);          // pixels x .. x+7
+        const unsigned w3 = *reinterpret_cast<const unsigned*>(tr + 16);    // pixels x+8 .. x+11
+        const unsigned w1 = w12.x, w2 = w12.y;
+        if (copy_dst && i >= 2 && i < RPT + 2) {   // the slot's pitch is a multiple of 16: whole vectors stay inside the row
+            const int y = yb + i - 2;
+            if (y < h) *reinterpret_cast<uint2*>(copy_dst + (size_t)b * cstride + (size_t)y * cpitch + x) = w12;
+        }
+        if (down) {
+            // [1 4 6 4 1] across for the outputs centred on pixels x, x+2, x+4, x+6: two dot products
+            // each on the aligned words, then the same taps down the rows (output row gy + o is
+            // centred on staged row 2o + 2)
+            unsigned hz[4];
+            hz[0] = dp4a_uu(w1, 0x00010406u, dp4a_uu(w0, 0x04010000u, 0u));
+            hz[1] = dp4a_uu(w2, 0x00000001u, dp4a_uu(w1, 0x04060401u, 0u));
+            hz[2] = dp4a_uu(w2, 0x00010406u, dp4a_uu(w1, 0x04010000u, 0u));
+            hz[3] = dp4a_uu(w3, 0x00000001u, dp4a_uu(w2, 0x04060401u, 0u));
+#pragma unroll
+            for (int o = 0; o < RPT / 2; ++o) {
+                const int d = i - (2 * o + 2);
+                const unsigned wv = (d == 0) ? 6u : (d == 1 || d == -1) ? 4u : (d == 2 || d == -2) ? 1u : 0u;
+                if (wv) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[o][k] += wv * hz[k];
+                }
+                if (d == 2 && gy + o < dh) {   // row complete: round, pack, store
+                    const unsigned r0 = (acc[o][0] + 128u) >> 8, r1 = (acc[o][1] + 128u) >> 8, r2 = (acc[o][2] + 128u) >> 8, r3 = (acc[o][3] + 128u) >> 8;
+                    uint8_t* nd = down + (size_t)b * nstride + (size_t)(gy + o) * npitch + gx;
+                    if (gx + 3 < dw) *reinterpret_cast<unsigned*>(nd) = r0 | (r1 << 8) | (r2 << 16) | (r3 << 24);
+                    else {
+                        nd[0] = (uint8_t)r0;
+                        if (gx + 1 < dw) nd[1] = (uint8_t)r1;
+                        if (gx + 2 < dw) nd[2] = (uint8_t)r2;
+                    }
                 }
             }
+        }
+        if (deriv && i >= 1) {
+            unsigned* W = win[i % 3];
+            W[0] = __funnelshift_r(w0, w1, 24);
+            W[1] = w1;
+            W[2] = __funnelshift_r(w1, w2, 8);
+            W[3] = __funnelshift_r(w1, w2, 16);
+            W[4] = __funnelshift_r(w1, w2, 24);
+            W[5] = w2;
+            W[6] = __funnelshift_r(w2, w3, 8);
+            W[7] = __funnelshift_r(w2, w3, 16);
+            if (i >= 3) {                      // rows i-2, i-1, i are the 3x3 neighbourhood of image row yb + i - 3
+                const int y = yb + i - 3;
+                if (y < h) {
+                    const unsigned* A = win[(i - 2) % 3];
+                    const unsigned* C = win[(i - 1) % 3];
+                    unsigned o[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = __byte_perm((unsigned)ix[j], (unsigned)iy[j], 0x5410);   // short2(ix, iy)
-            short2* out = deriv + (size_t)b * dstride + (size_t)y * dpitch + x;
-            if (x + 7 < w) {
-                reinterpret_cast<uint4*>(out)[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                reinterpret_cast<uint4*>(out)[1] = make_uint4(o[4], o[5], o[6], o[7]);
-            } else {
+                    for (int j = 0; j < 8; ++j) {
+                        int ix = dp4a_us(A[j], 0x000300FD, 0);            // (-3, 0, 3, 0)
+                        ix = dp4a_us(C[j], 0x000A00F6, ix);               // (-10, 0, 10, 0)
+                        ix = dp4a_us(W[j], 0x000300FD, ix);
+                        int iy = dp4a_us(A[j], 0x00FDF6FD, 0);            // (-3, -10, -3, 0)
+                        iy = dp4a_us(W[j], 0x00030A03, iy);               // (3, 10, 3, 0)
+                        o[j] = __byte_perm((unsigned)ix, (unsigned)iy, 0x5410);   // short2(ix, iy)
+                    }
+                    short2* out = deriv + (size_t)b * dstride + (size_t)y * dpitch + x;
+                    if (full) {
+                        reinterpret_cast<uint4*>(out)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                        reinterpret_cast<uint4*>(out)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                    } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) if (x + j < w) reinterpret_cast<unsigned*>(out)[j] = o[j];
+                        for (int j = 0; j < 8; ++j) if (x + j < w) reinterpret_cast<unsigned*>(out)[j] = o[j];
+                    }
+                }
             }
         }
     }
-
-    if (down) {
-        // pyrDown: thread = two horizontally adjacent outputs; [1 4 6 4 1] across as (1,4,6,4).window + 5th
-        // byte, then [1 4 6 4 1] down the five rows, all in registers.
-        const int dw = (w + 1) / 2, dh = (h + 1) / 2;
-        const int oy = tid >> 4, oxp = (tid & 15) * 2;
-        const int gx = x0 / 2 + oxp, gy = y0 / 2 + oy;
-        if (gx < dw && gy < dh) {
-            int sa = 0, sb = 0;
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const unsigned* tw = reinterpret_cast<const unsigned*>(&tile[2 * oy + j][2 * oxp + 4]);   // bytes base+4 ..
-                const unsigned w1 = tw[0], w2 = tw[1], w3 = tw[2];
-                const unsigned ha = dp4a_uu(__funnelshift_r(w1, w2, 16), 0x04060401u, (w2 >> 16) & 0xffu);  // taps base+6 .. base+10
-                const unsigned hb = dp4a_uu(w2, 0x04060401u, w3 & 0xffu);                                    // taps base+8 .. base+12
-                const int wv = (j == 0 || j == 4) ? 1 : ((j == 2) ? 6 : 4);
-                sa += wv * (int)ha; sb += wv * (int)hb;
-            }
-            uint8_t* nd = down + (size_t)b * nstride + (size_t)gy * npitch + gx;
-            nd[0] = (uint8_t)((sa + 128) >> 8);
-            if (gx + 1 < dw) nd[1] = (uint8_t)((sb + 128) >> 8);
-        }
+    }
+    __syncthreads();   // the buffer is restaged two tiles ahead
     }
 }
 
@@ -364,8 +432,15 @@ namespace kltdev {
 
 cudaError_t launch_level(const LevelJob& j0, const LevelJob& j1, int w, int h, int cpitch, size_t cstride, int dpitch, size_t dstride,
                          int npitch, size_t nstride, cudaStream_t st) {
-    dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH, j0.batch + j1.batch);
-    klt_level_kernel<<<grid, 256, 0, st>>>(j0, j1, w, h, cpitch, cstride, dpitch, dstride, npitch, nstride);
+    // a CTA walks down several tiles of a column (staging overlapped with compute) when the batch is
+    // large enough to fill the GPU without splitting columns
+    const int tx = (w + TW - 1) / TW, ty = (h + TH - 1) / TH, imgs = j0.batch + j1.batch;
+    const long long want = 148LL * 32;
+    int chunks = (int)((want + (long long)tx * imgs - 1) / ((long long)tx * imgs));
+    chunks = chunks < 1 ? 1 : (chunks > ty ? ty : chunks);
+    const int per = (ty + chunks - 1) / chunks;
+    dim3 grid(tx, (ty + per - 1) / per, imgs);
+    klt_level_kernel<<<grid, LT, 0, st>>>(j0, j1, w, h, cpitch, cstride, dpitch, dstride, npitch, nstride, per);
     return cudaGetLastError();
 }
 

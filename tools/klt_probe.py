@@ -15,3 +15,14 @@ for it in range(4):
 torch.cuda.synchronize()
 ms, cnt = trk.timing()
 print("per-launch ms:", (ms / np.maximum(cnt, 1)).round(4), "tracked", int(st.sum()), "of", B * 200)
+# separate timings of the two slots' builds and of the pair build (CUDA events on torch's current stream)
+def timed(fn, reps=20):
+    for _ in range(3): fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+print("build prev (copy + Scharr + pyrDown) ms:", round(timed(lambda: trk.build_pyramid(0, dp, True)), 4),
+      " build next (copy + pyrDown) ms:", round(timed(lambda: trk.build_pyramid(1, dn, False)), 4),
+      " pair build ms:", round(timed(lambda: trk.build_pyramid_pair(0, dp, 1, dn)), 4))
