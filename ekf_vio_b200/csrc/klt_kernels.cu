@@ -4,6 +4,7 @@
 // integer pyrDown/Scharr, Q14 bilinear weights, int16 patches, exact integer window sums,
 // FP32 2x2 solve.  Compiled with --fmad=false so FP32 expressions round as OpenCV's do.
 #include <float.h>
+#include <limits.h>
 
 #include "klt_common.cuh"
 #include "klt_kernels.h"
@@ -216,10 +217,11 @@ __global__ void __launch_bounds__(LT, 16) klt_level_kernel(LevelJob j0, LevelJob
     }
 }
 
-__device__ __forceinline__ long long warp_sum_ll(long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+// exact warp-wide sum of 32-bit partials in 64 bits: two REDUX.SUM on the 16-bit halves
+__device__ __forceinline__ long long warp_sum_ll(int v) {
+    const int lo = v & 0xffff, hi = v >> 16;       // v == hi * 65536 + lo
+    const int slo = __reduce_add_sync(0xffffffffu, lo), shi = __reduce_add_sync(0xffffffffu, hi);
+    return (long long)shi * 65536 + slo;
 }
 
 __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01, int& w10, int& w11) {
@@ -343,6 +345,7 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
         D = 1.f / D;
         nx -= half; ny -= half;
         float pdx = 0.f, pdy = 0.f;
+        int sjx = INT_MIN, sjy = INT_MIN;         // cell of the J tile currently staged (none: Jt holds the I tile)
         for (int j = 0; j < max_count; ++j) {
             int inx = (int)floorf(nx), iny = (int)floorf(ny);
             if (inx < -win || inx >= L.w || iny < -win || iny >= L.h) {
@@ -350,8 +353,11 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
                 break;
             }
             lk_weights(nx - inx, ny - iny, w00, w01, w10, w11);
-            __syncwarp();
-            stage_u8(J, L, inx, iny);
+            if (inx != sjx || iny != sjy) {       // the staged J tile is reused while the integer cell does not move
+                __syncwarp();
+                stage_u8(J, L, inx, iny);
+                sjx = inx; sjy = iny;
+            }
             int sb1 = 0, sb2 = 0;                 // <= 31 slots x 8160 x 4080 fits 32 bits
             for (int e = lane, y = y_first, x = x_first; e < area; e += 32) {
                 const uint8_t* jp = Jt + y * jw1 + x;
@@ -380,9 +386,11 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
                 st = 0;
             } else {
                 lk_weights(fx - inx, fy - iny, w00, w01, w10, w11);
-                __syncwarp();
-                stage_u8(J, L, inx, iny);
-                long long es = 0;
+                if (inx != sjx || iny != sjy) {
+                    __syncwarp();
+                    stage_u8(J, L, inx, iny);
+                }
+                int es = 0;                       // <= 14 slots x 8160
                 for (int e = lane, y = y_first, x = x_first; e < area; e += 32) {
                     const uint8_t* jp = Jt + y * jw1 + x;
                     const int diff = ((jp[0] * w00 + jp[1] * w01 + jp[jw1] * w10 + jp[jw1 + 1] * w11 + (1 << 8)) >> 9) - Ip[e];
@@ -390,8 +398,8 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
                     y += qstep; x += rstep;
                     if (x >= win) { x -= win; ++y; }
                 }
-                es = warp_sum_ll(es);
-                errv = (float)es * 1.f / (float)(32 * win * win);
+                const long long est = warp_sum_ll(es);
+                errv = (float)est * 1.f / (float)(32 * win * win);
             }
         }
         __syncwarp();
