@@ -232,16 +232,60 @@ __device__ __forceinline__ void lk_weights(float a, float b, int& w00, int& w01,
 }
 
 constexpr int WARPS = 4;      // features per CTA
+constexpr int SEG = 7;        // pixels per row segment: 8 tile bytes give 7 horizontal tap pairs
 
+__host__ __device__ inline int track_segs_per_row(int win) { return (win + SEG - 1) / SEG; }
+// bytes per staged u8 tile row: the last segment reads three aligned words from its start; odd word count
+__host__ __device__ inline int track_tile_stride(int win) {
+    int words = ((SEG * (track_segs_per_row(win) - 1)) >> 2) + 3;
+    if (words * 4 < win + 1) words = (win + 4) / 4;
+    return (words | 1) * 4;
+}
 __host__ __device__ inline size_t track_warp_bytes(int win) {
-    size_t area = (size_t)win * win, t = ((size_t)win + 1) * (win + 1);
-    size_t bytes = area * 4 /*dI*/ + t * 4 /*Dt*/ + ((area * 2 + 3) & ~(size_t)3) /*Ip*/ + ((t + 3) & ~(size_t)3) /*Jt*/;
+    size_t nseg = (size_t)win * track_segs_per_row(win), t = ((size_t)win + 1) * (win + 1);
+    size_t bytes = nseg * 8 * 4 /*Cp*/ + nseg * 8 * 4 /*dI*/ + t * 4 /*Dt*/ + ((size_t)win + 1) * track_tile_stride(win) /*Jt*/;
     return (bytes + 15) & ~(size_t)15;
 }
 
-// LKTrackerInvoker for every level, one warp per point.  Per-warp shared memory:
-//   dI[win*win] short2 (Ix, Iy of the patch), Dt[(win+1)^2] short2 (staged derivative tile),
-//   Ip[win*win] int16 (patch intensities, 5 fractional bits), Jt[(win+1)^2] u8 (staged I or J tile).
+// (signed 16-bit weights: rounding can leave w11 = -1)
+__device__ __forceinline__ unsigned dp2a_lo(unsigned a_u16x2, unsigned b_u8x4, unsigned c) {
+    unsigned d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u16x2), "r"(b_u8x4), "r"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned dp2a_hi(unsigned a_u16x2, unsigned b_u8x4, unsigned c) {
+    unsigned d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u16x2), "r"(b_u8x4), "r"(c));
+    return d;
+}
+
+// Bilinear taps of one 7-pixel row segment: v[k] = c[k] + w00 t[k] + w01 t[k+1] + w10 b[k] + w11 b[k+1]
+// where t / b are the 8 tile bytes of the segment in the upper / lower row.  wt = w00 | w01 << 16,
+// wb = w10 | w11 << 16 (Q14 weights fit signed 16 bits), two IDP2A per pixel.
+__device__ __forceinline__ void seg_taps(const uint8_t* Jt, int JS, int r, int sg, unsigned wt, unsigned wb, const int (&c)[SEG], int (&v)[SEG]) {
+    const int off = SEG * sg, sh = (off & 3) * 8;
+    const unsigned* tr = reinterpret_cast<const unsigned*>(Jt + r * JS) + (off >> 2);
+    const unsigned* br = tr + (JS >> 2);
+    const unsigned t0 = tr[0], t1 = tr[1], t2 = tr[2], b0 = br[0], b1 = br[1], b2 = br[2];
+    const unsigned tlo = __funnelshift_r(t0, t1, sh), thi = __funnelshift_r(t1, t2, sh);   // bytes 0..3, 4..7
+    const unsigned blo = __funnelshift_r(b0, b1, sh), bhi = __funnelshift_r(b1, b2, sh);
+    const unsigned tm = __funnelshift_r(tlo, thi, 8), tm2 = thi >> 8;                      // bytes 1..4, 5..7
+    const unsigned bm = __funnelshift_r(blo, bhi, 8), bm2 = bhi >> 8;
+    v[0] = (int)dp2a_lo(wb, blo, dp2a_lo(wt, tlo, (unsigned)c[0]));
+    v[1] = (int)dp2a_lo(wb, bm, dp2a_lo(wt, tm, (unsigned)c[1]));
+    v[2] = (int)dp2a_hi(wb, blo, dp2a_hi(wt, tlo, (unsigned)c[2]));
+    v[3] = (int)dp2a_hi(wb, bm, dp2a_hi(wt, tm, (unsigned)c[3]));
+    v[4] = (int)dp2a_lo(wb, bhi, dp2a_lo(wt, thi, (unsigned)c[4]));
+    v[5] = (int)dp2a_lo(wb, bm2, dp2a_lo(wt, tm2, (unsigned)c[5]));
+    v[6] = (int)dp2a_hi(wb, bhi, dp2a_hi(wt, thi, (unsigned)c[6]));
+}
+
+// LKTrackerInvoker for every level, one warp per point.  The win x win patch is cut into row
+// segments of 7 pixels (8 slots each); a lane owns segments lane, lane + 32, ...  Per-warp shared memory:
+//   Cp[nseg*8] int32: 256 - 512 * (patch intensity), the rounding constant and the patch value folded
+//                     into the accumulator the IDP2A chain starts from, so diff = chain >> 9;
+//   dI[nseg*8] short2 (Ix, Iy of the patch; zero in unused slots),
+//   Dt[(win+1)^2] short2 (staged derivative tile), Jt[(win+1) x stride] u8 (staged I or J tile).
 // Tiles are staged row by row (lanes = columns), so every bilinear tap is a shared-memory read and
 // no per-pixel integer division or border test remains in the loops.
 __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const uint8_t* __restrict__ prev_slot, const uint8_t* __restrict__ next_slot,
@@ -254,15 +298,16 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
     const int b = blockIdx.y;
     const int pt = blockIdx.x * WARPS + warp;
     if (pt >= npts[b]) return;
-    const int area = win * win, jw1 = win + 1, tarea = jw1 * jw1;
+    const int jw1 = win + 1, tarea = jw1 * jw1;
+    const int SPR = track_segs_per_row(win), nseg = win * SPR, JS = track_tile_stride(win);
     uint8_t* base = smem_raw + warp * track_warp_bytes(win);
-    short2* dI = reinterpret_cast<short2*>(base);
-    short2* Dt = dI + area;
-    short* Ip = reinterpret_cast<short*>(Dt + tarea);
-    uint8_t* Jt = reinterpret_cast<uint8_t*>(Ip) + ((area * 2 + 3) & ~3);
-    // lane's pixel slots: e = lane, lane + 32, ...  ->  (y, x) advanced without divisions
-    const int y_first = lane / win, x_first = lane - y_first * win;
-    const int qstep = 32 / win, rstep = 32 - qstep * win;
+    int* Cp = reinterpret_cast<int*>(base);
+    unsigned* dI = reinterpret_cast<unsigned*>(Cp + nseg * 8);
+    short2* Dt = reinterpret_cast<short2*>(dI + nseg * 8);
+    uint8_t* Jt = reinterpret_cast<uint8_t*>(Dt + tarea);
+    // lane's segments: s = lane, lane + 32, ...  ->  (row, segment in row) advanced without divisions
+    const int r_first = lane / SPR, sg_first = lane - r_first * SPR;
+    const int qstep = 32 / SPR, rstep = 32 - qstep * SPR;
 
     const size_t pidx = ((size_t)b * max_points + pt) * 2;
     const float prevx = prev_pts[pidx], prevy = prev_pts[pidx + 1];
@@ -279,10 +324,10 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
             const bool inside = ox >= 0 && oy >= 0 && ox + win < L.w && oy + win < L.h;
             if (inside) {
                 const uint8_t* p = img + (size_t)oy * L.pitch + ox + lane;
-                for (int y = 0; y < jw1; ++y) Jt[y * jw1 + lane] = p[(size_t)y * L.pitch];
+                for (int y = 0; y < jw1; ++y) Jt[y * JS + lane] = p[(size_t)y * L.pitch];
             } else {
                 const int cx = reflect101(ox + lane, L.w);
-                for (int y = 0; y < jw1; ++y) Jt[y * jw1 + lane] = img[(size_t)reflect101(oy + y, L.h) * L.pitch + cx];
+                for (int y = 0; y < jw1; ++y) Jt[y * JS + lane] = img[(size_t)reflect101(oy + y, L.h) * L.pitch + cx];
             }
         }
         __syncwarp();
@@ -322,17 +367,37 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
         }
         __syncwarp();
         int sa11 = 0, sa12 = 0, sa22 = 0;     // per-lane partial sums fit 32 bits (<= 31 slots x 4080^2)
-        for (int e = lane, y = y_first, x = x_first; e < area; e += 32) {
-            const int o = y * jw1 + x;
-            const int ival = (Jt[o] * w00 + Jt[o + 1] * w01 + Jt[o + jw1] * w10 + Jt[o + jw1 + 1] * w11 + (1 << 8)) >> 9;
-            const short2 d00 = Dt[o], d01 = Dt[o + 1], d10 = Dt[o + jw1], d11 = Dt[o + jw1 + 1];
-            const int ixval = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << 13)) >> 14;
-            const int iyval = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << 13)) >> 14;
-            Ip[e] = (short)ival;
-            dI[e] = make_short2((short)ixval, (short)iyval);
-            sa11 += ixval * ixval; sa12 += ixval * iyval; sa22 += iyval * iyval;
-            y += qstep; x += rstep;
-            if (x >= win) { x -= win; ++y; }
+        {
+            const unsigned wt = ((unsigned)w00 & 0xffffu) | ((unsigned)w01 << 16), wb = ((unsigned)w10 & 0xffffu) | ((unsigned)w11 << 16);
+            const int c256[SEG] = {256, 256, 256, 256, 256, 256, 256};
+            for (int sI = lane, r = r_first, sg = sg_first; sI < nseg; sI += 32) {
+                int v[SEG];
+                seg_taps(Jt, JS, r, sg, wt, wb, c256, v);
+                int cw[8];
+                unsigned dw[8];
+#pragma unroll
+                for (int k = 0; k < SEG; ++k) {
+                    const int x = SEG * sg + k;
+                    if (x < win) {
+                        const int ival = v[k] >> 9;
+                        const int o = r * jw1 + x;
+                        const short2 d00 = Dt[o], d01 = Dt[o + 1], d10 = Dt[o + jw1], d11 = Dt[o + jw1 + 1];
+                        const int ixval = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << 13)) >> 14;
+                        const int iyval = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << 13)) >> 14;
+                        cw[k] = 256 - 512 * (int)(short)ival;
+                        dw[k] = ((unsigned)ixval & 0xffffu) | ((unsigned)iyval << 16);
+                        const int sx = (short)ixval, sy = (short)iyval;
+                        sa11 += sx * sx; sa12 += sx * sy; sa22 += sy * sy;
+                    } else { cw[k] = 0; dw[k] = 0u; }
+                }
+                cw[7] = 0; dw[7] = 0u;
+                *reinterpret_cast<int4*>(Cp + sI * 8) = make_int4(cw[0], cw[1], cw[2], cw[3]);
+                *reinterpret_cast<int4*>(Cp + sI * 8 + 4) = make_int4(cw[4], cw[5], cw[6], cw[7]);
+                *reinterpret_cast<uint4*>(dI + sI * 8) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+                *reinterpret_cast<uint4*>(dI + sI * 8 + 4) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+                r += qstep; sg += rstep;
+                if (sg >= SPR) { sg -= SPR; ++r; }
+            }
         }
         const long long a11 = warp_sum_ll(sa11), a12 = warp_sum_ll(sa12), a22 = warp_sum_ll(sa22);
         float A11 = (float)a11 * FLT_SCALE, A12 = (float)a12 * FLT_SCALE, A22 = (float)a22 * FLT_SCALE;
@@ -358,14 +423,25 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
                 stage_u8(J, L, inx, iny);
                 sjx = inx; sjy = iny;
             }
-            int sb1 = 0, sb2 = 0;                 // <= 31 slots x 8160 x 4080 fits 32 bits
-            for (int e = lane, y = y_first, x = x_first; e < area; e += 32) {
-                const uint8_t* jp = Jt + y * jw1 + x;
-                const int diff = ((jp[0] * w00 + jp[1] * w01 + jp[jw1] * w10 + jp[jw1 + 1] * w11 + (1 << 8)) >> 9) - Ip[e];
-                const short2 d = dI[e];
-                sb1 += diff * d.x; sb2 += diff * d.y;
-                y += qstep; x += rstep;
-                if (x >= win) { x -= win; ++y; }
+            int sb1 = 0, sb2 = 0;                 // <= 35 slots x 8160 x 4080 fits 32 bits
+            {
+                const unsigned wt = ((unsigned)w00 & 0xffffu) | ((unsigned)w01 << 16), wb = ((unsigned)w10 & 0xffffu) | ((unsigned)w11 << 16);
+                for (int sI = lane, r = r_first, sg = sg_first; sI < nseg; sI += 32) {
+                    const int4 c0 = *reinterpret_cast<const int4*>(Cp + sI * 8), c1 = *reinterpret_cast<const int4*>(Cp + sI * 8 + 4);
+                    const uint4 d0 = *reinterpret_cast<const uint4*>(dI + sI * 8), d1 = *reinterpret_cast<const uint4*>(dI + sI * 8 + 4);
+                    const int c[SEG] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z};
+                    const unsigned dw[SEG] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z};
+                    int v[SEG];
+                    seg_taps(Jt, JS, r, sg, wt, wb, c, v);
+#pragma unroll
+                    for (int k = 0; k < SEG; ++k) {   // unused slots carry zero derivatives
+                        const int diff = v[k] >> 9;
+                        sb1 += diff * (int)(short)(dw[k] & 0xffffu);
+                        sb2 += diff * ((int)dw[k] >> 16);
+                    }
+                    r += qstep; sg += rstep;
+                    if (sg >= SPR) { sg -= SPR; ++r; }
+                }
             }
             const long long b1 = warp_sum_ll(sb1), b2 = warp_sum_ll(sb2);
             float fb1 = (float)b1 * FLT_SCALE, fb2 = (float)b2 * FLT_SCALE;
@@ -390,13 +466,22 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
                     __syncwarp();
                     stage_u8(J, L, inx, iny);
                 }
-                int es = 0;                       // <= 14 slots x 8160
-                for (int e = lane, y = y_first, x = x_first; e < area; e += 32) {
-                    const uint8_t* jp = Jt + y * jw1 + x;
-                    const int diff = ((jp[0] * w00 + jp[1] * w01 + jp[jw1] * w10 + jp[jw1 + 1] * w11 + (1 << 8)) >> 9) - Ip[e];
-                    es += diff < 0 ? -diff : diff;
-                    y += qstep; x += rstep;
-                    if (x >= win) { x -= win; ++y; }
+                int es = 0;                       // <= 35 slots x 8160
+                {
+                    const unsigned wt = ((unsigned)w00 & 0xffffu) | ((unsigned)w01 << 16), wb = ((unsigned)w10 & 0xffffu) | ((unsigned)w11 << 16);
+                    for (int sI = lane, r = r_first, sg = sg_first; sI < nseg; sI += 32) {
+                        const int4 c0 = *reinterpret_cast<const int4*>(Cp + sI * 8), c1 = *reinterpret_cast<const int4*>(Cp + sI * 8 + 4);
+                        const int c[SEG] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z};
+                        int v[SEG];
+                        seg_taps(Jt, JS, r, sg, wt, wb, c, v);
+#pragma unroll
+                        for (int k = 0; k < SEG; ++k) {
+                            const int diff = v[k] >> 9;
+                            if (SEG * sg + k < win) es += diff < 0 ? -diff : diff;
+                        }
+                        r += qstep; sg += rstep;
+                        if (sg >= SPR) { sg -= SPR; ++r; }
+                    }
                 }
                 const long long est = warp_sum_ll(es);
                 errv = (float)est * 1.f / (float)(32 * win * win);
