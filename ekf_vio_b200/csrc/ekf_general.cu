@@ -13,18 +13,26 @@ constexpr int PT = 256;  // threads per CTA for the general kernels
 
 // ---------------------------------------------------------------------------------------------
 // Finite-difference Jacobian pieces + state propagation, shared by process and linearize.
-// smem layout (doubles): mu[22] | fdb[32][22] | A[22][23] | dq[8][4] | feat[3n] | B[3n][9] | D[n][9]
+// smem layout (doubles): mu[22] | fdb[32][22] | A[22][23] | dq[8][4] | bvec[19][3] (+pad) | feat[3n] | B[3n][9] | D[n][9]
 struct ProcSmem {
-    double* mu; double* fdb; double* A; double* dq; double* feat; double* B; double* D;
+    double* mu; double* fdb; double* A; double* dq; double* bvec; double* feat; double* B; double* D;
     __device__ ProcSmem(double* base, int n) {
-        mu = base; fdb = mu + 22; A = fdb + 32 * 22; dq = A + 22 * 23; feat = dq + 32; B = feat + 3 * n; D = B + 27 * n;
+        mu = base; fdb = mu + 22; A = fdb + 32 * 22; dq = A + 22 * 23; bvec = dq + 32; feat = bvec + 64; B = feat + 3 * n; D = B + 27 * n;
     }
-    static __host__ __device__ size_t doubles(int n) { return 22 + 32 * 22 + 22 * 23 + 32 + 3 * (size_t)n + 27 * (size_t)n + 9 * (size_t)n; }
+    static __host__ __device__ size_t doubles(int n) { return 22 + 32 * 22 + 22 * 23 + 32 + 64 + 3 * (size_t)n + 27 * (size_t)n + 9 * (size_t)n; }
 };
 
 // numericallyLinearizeProcess (TightlyCoupledEKF.cpp:176-325) as independent evaluations.
 // Fills s.A (22x22, ld 23), s.B (3n x 9: d feature / d base cols 7..15), s.D (n x 3 x 3) and
 // leaves the dq_inv the reference's convolveFeature cache ends with in s.dq[1] (fresh, base omega).
+// x / z given r = RN(1 / z): one multiply and two fused corrections give the correctly rounded
+// quotient (Markstein), i.e. the bits a division would — a third of the instructions.
+__device__ __forceinline__ double div_with_rcp(double x, double z, double r) {
+    const double q0 = __dmul_rn(x, r);
+    const double rem = __fma_rn(-q0, z, x);
+    return __fma_rn(rem, r, q0);
+}
+
 __device__ void linearize_block(const ProcSmem& s, int n, double dt, const double* cache7, bool fresh_cache) {
     const int tid = threadIdx.x;
     const double two_d = 2 * DELTA_SHIFT;
@@ -66,60 +74,103 @@ __device__ void linearize_block(const ProcSmem& s, int n, double dt, const doubl
     }
     __syncthreads();
     // A = d base / d base
+    const double r2d = 1.0 / two_d;
     for (int e = tid; e < 22 * 22; e += blockDim.x) {
         int i = e / 22, j = e % 22;
         double v;
-        if (j < 16) v = (s.fdb[(2 * j) * 22 + i] - s.fdb[(2 * j + 1) * 22 + i]) / two_d;
+        if (j < 16) v = div_with_rcp(s.fdb[(2 * j) * 22 + i] - s.fdb[(2 * j + 1) * 22 + i], two_d, r2d);
         else v = (i == j) ? 1.0 : 0.0;
         s.A[i * 23 + j] = v;
     }
-    // feature evaluations: (feature f, column c): c in 0..8 -> base columns 7..15, c in 9..11 -> own u,v,rho
-    for (int e = tid; e < n * 12; e += blockDim.x) {
-        int f = e / 12, c = e % 12;
-        double u = s.feat[3 * f], v = s.feat[3 * f + 1], rho = s.feat[3 * f + 2];
+    // convolveFeature evaluates  (R fp - R tr) / z  with fp from the feature and tr, R from the base
+    // state.  R tr does not depend on the feature: the 19 variants (columns 7..15 x {+,-}, and the
+    // unperturbed one) are computed once per filter.
+    const double hdt2 = 0.5 * dt * dt;
+    if (tid >= 64 && tid < 64 + 19) {
+        const int t = tid - 64;
+        V3 vel{s.mu[7], s.mu[8], s.mu[9]}, acc{s.mu[13], s.mu[14], s.mu[15]};
+        int qi = 1;
+        if (t < 18) {
+            const int j = 7 + (t >> 1), sgn = t & 1;
+            double val = s.mu[j] + DELTA_SHIFT;
+            if (sgn) val = val - two_d;
+            if (j <= 9) { (j == 7 ? vel.x : j == 8 ? vel.y : vel.z) = val; qi = 0; }
+            else if (j <= 12) { qi = 2 + 2 * (j - 10) + sgn; }
+            else { (j == 13 ? acc.x : j == 14 ? acc.y : acc.z) = val; }
+        }
+        const Q4 dq{s.dq[qi * 4], s.dq[qi * 4 + 1], s.dq[qi * 4 + 2], s.dq[qi * 4 + 3]};
+        const V3 tr{dt * vel.x + hdt2 * acc.x, dt * vel.y + hdt2 * acc.y, dt * vel.z + hdt2 * acc.z};
+        const V3 bv = qrot(dq, tr);
+        s.bvec[t * 3] = bv.x; s.bvec[t * 3 + 1] = bv.y; s.bvec[t * 3 + 2] = bv.z;
+    }
+    __syncthreads();
+    // feature evaluations, item (feature f, group g): g = 0 -> columns 7..9 (cached dq_inv, E2),
+    // g = 1 -> columns 13..15, g = 2 -> columns 10..12 (one dq_inv per evaluation), g = 3 -> own u, v, rho
+    auto project = [&](const V3& a, const double* bv, double* o) {   // (x/z, y/z, 1/z) of a - b
+        const double x = a.x - bv[0], y = a.y - bv[1], z = a.z - bv[2];
+        const double iz = 1.0 / z;   // quotients stay correctly rounded: one-ulp differences here grow ~5000x through the gain
+        o[0] = div_with_rcp(x, z, iz); o[1] = div_with_rcp(y, z, iz); o[2] = iz;
+    };
+    for (int e = tid; e < n * 4; e += blockDim.x) {
+        const int f = e >> 2, g = e & 3;
+        const double u = s.feat[3 * f], v = s.feat[3 * f + 1], rho = s.feat[3 * f + 2];
         double hi[3], lo[3];
-        if (c < 9) {
-            int j = 7 + c;
-            double vals[2];
-            vals[0] = s.mu[j] + DELTA_SHIFT;
-            vals[1] = vals[0] - two_d;
+        if (g < 3) {
+            V3 fp;
+            fp.z = 1.0 / rho; fp.x = u * fp.z; fp.y = v * fp.z;
+            if (g < 2) {
+                const Q4 dq{s.dq[g * 4], s.dq[g * 4 + 1], s.dq[g * 4 + 2], s.dq[g * 4 + 3]};
+                const V3 a = qrot(dq, fp);
 #pragma unroll
-            for (int sgn = 0; sgn < 2; ++sgn) {
-                V3 vel{s.mu[7], s.mu[8], s.mu[9]}, acc{s.mu[13], s.mu[14], s.mu[15]};
-                int qi = 1;
-                if (j <= 9) { (j == 7 ? vel.x : j == 8 ? vel.y : vel.z) = vals[sgn]; qi = 0; }
-                else if (j <= 12) { qi = 2 + 2 * (j - 10) + sgn; }
-                else { (j == 13 ? acc.x : j == 14 ? acc.y : acc.z) = vals[sgn]; }
-                Q4 dq{s.dq[qi * 4], s.dq[qi * 4 + 1], s.dq[qi * 4 + 2], s.dq[qi * 4 + 3]};
-                convolve_feature(dq, vel, acc, dt, u, v, rho, sgn == 0 ? hi : lo);
+                for (int k = 0; k < 3; ++k) {
+                    const int c = (g == 0 ? 0 : 6) + k;
+                    project(a, s.bvec + (2 * c) * 3, hi);
+                    project(a, s.bvec + (2 * c + 1) * 3, lo);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) s.B[(3 * f + r) * 9 + c] = div_with_rcp(hi[r] - lo[r], two_d, r2d);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int c = 3 + k;
+#pragma unroll
+                    for (int sgn = 0; sgn < 2; ++sgn) {
+                        const int qi = 2 + 2 * k + sgn;
+                        const Q4 dq{s.dq[qi * 4], s.dq[qi * 4 + 1], s.dq[qi * 4 + 2], s.dq[qi * 4 + 3]};
+                        project(qrot(dq, fp), s.bvec + (2 * c + sgn) * 3, sgn == 0 ? hi : lo);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) s.B[(3 * f + r) * 9 + c] = div_with_rcp(hi[r] - lo[r], two_d, r2d);
+                }
             }
-#pragma unroll
-            for (int r = 0; r < 3; ++r) s.B[(3 * f + r) * 9 + c] = (hi[r] - lo[r]) / two_d;
         } else {
-            int k = c - 9;
-            V3 vel{s.mu[7], s.mu[8], s.mu[9]}, acc{s.mu[13], s.mu[14], s.mu[15]};
-            Q4 dq{s.dq[4], s.dq[5], s.dq[6], s.dq[7]};
-            double t[3] = {u, v, rho};
-            double up = t[k] + DELTA_SHIFT;
-            t[k] = up;
-            convolve_feature(dq, vel, acc, dt, t[0], t[1], t[2], hi);
-            t[k] = up - two_d;
-            convolve_feature(dq, vel, acc, dt, t[0], t[1], t[2], lo);
+            const Q4 dq{s.dq[4], s.dq[5], s.dq[6], s.dq[7]};
 #pragma unroll
-            for (int r = 0; r < 3; ++r) s.D[f * 9 + r * 3 + k] = (hi[r] - lo[r]) / two_d;
+            for (int k = 0; k < 3; ++k) {
+                double t[3] = {u, v, rho};
+                const double up = t[k] + DELTA_SHIFT;
+#pragma unroll
+                for (int sgn = 0; sgn < 2; ++sgn) {
+                    t[k] = sgn == 0 ? up : up - two_d;
+                    V3 fp;
+                    fp.z = 1.0 / t[2]; fp.x = t[0] * fp.z; fp.y = t[1] * fp.z;
+                    project(qrot(dq, fp), s.bvec + 18 * 3, sgn == 0 ? hi : lo);
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) s.D[f * 9 + r * 3 + k] = div_with_rcp(hi[r] - lo[r], two_d, r2d);
+            }
         }
     }
     __syncthreads();
 }
 
-// process(dt) — TightlyCoupledEKF.cpp:96-121.  mode 0: full step (state + covariance).
-// mode 1: linearize only (dense F written to F_out, state untouched except the dq cache).
-__global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const double* __restrict__ Pin, double* __restrict__ Pout,
-                                                          const double* __restrict__ dts, int mode, double* __restrict__ F_out, int fused) {
+// First half of process(dt) for batches that fill the GPU: linearisation (A, B, D into the idle W
+// panel), dq cache refresh and state propagation, in small CTAs so that the serial finite-difference
+// chains of many filters overlap.  ekf_process_general(pre = 1) then does the covariance pass.
+__global__ void __launch_bounds__(128) ekf_linearize_kernel(EkfPtrs p, const double* __restrict__ dts) {
     extern __shared__ double sm[];
     const int f = blockIdx.x, tid = threadIdx.x;
-    const int n = p.nfeat[f], N = BASE + 3 * n;
-    const int ld = p.ldP;
+    const int n = p.nfeat[f];
     ProcSmem s(sm, n);
     const double dt = dts[f];
     double* mu_g = p.mu + (size_t)f * BASE;
@@ -129,6 +180,55 @@ __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const do
     for (int i = tid; i < 3 * n; i += blockDim.x) s.feat[i] = feat_g[i];
     __syncthreads();
     linearize_block(s, n, dt, cache_g, (p.flags & EKFVIO_FLAG_FRESH_DQ_CACHE) != 0);
+    if (n > 0 && tid == 0) {
+        cache_g[0] = s.mu[10]; cache_g[1] = s.mu[11]; cache_g[2] = s.mu[12];
+        cache_g[3] = s.dq[4]; cache_g[4] = s.dq[5]; cache_g[5] = s.dq[6]; cache_g[6] = s.dq[7];
+    }
+    double* lin = p.W + (size_t)f * p.ldP * p.ldK;
+    for (int i = tid; i < 22 * 23; i += blockDim.x) lin[i] = s.A[i];
+    for (int i = tid; i < 27 * n; i += blockDim.x) lin[22 * 23 + i] = s.B[i];
+    for (int i = tid; i < 9 * n; i += blockDim.x) lin[22 * 23 + 27 * p.nmax + i] = s.D[i];
+    for (int fi = tid; fi < n; fi += blockDim.x) {
+        V3 vel{s.mu[7], s.mu[8], s.mu[9]}, acc{s.mu[13], s.mu[14], s.mu[15]};
+        Q4 dq{s.dq[4], s.dq[5], s.dq[6], s.dq[7]};
+        double o[3];
+        convolve_feature(dq, vel, acc, dt, s.feat[3 * fi], s.feat[3 * fi + 1], s.feat[3 * fi + 2], o);
+        feat_g[3 * fi] = o[0]; feat_g[3 * fi + 1] = o[1]; feat_g[3 * fi + 2] = o[2];
+    }
+    if (tid == 0) {
+        double o[22];
+        convolve_base(s.mu, dt, o);
+        for (int i = 0; i < 22; ++i) mu_g[i] = o[i];
+    }
+}
+
+// process(dt) — TightlyCoupledEKF.cpp:96-121.  mode 0: full step (state + covariance).
+// mode 1: linearize only (dense F written to F_out, state untouched except the dq cache).
+__global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const double* __restrict__ Pin, double* __restrict__ Pout,
+                                                          const double* __restrict__ dts, int mode, double* __restrict__ F_out, int fused,
+                                                          int pre) {
+    extern __shared__ double sm[];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int n = p.nfeat[f], N = BASE + 3 * n;
+    const int ld = p.ldP;
+    ProcSmem s(sm, n);
+    const double dt = dts[f];
+    double* mu_g = p.mu + (size_t)f * BASE;
+    double* feat_g = p.feat + (size_t)f * p.nmax * 3;
+    double* cache_g = p.cache + (size_t)f * 7;
+    if (pre) {
+        // A, B, D were left in the (idle) W panel by ekf_linearize_kernel, which also moved the state
+        const double* lin = p.W + (size_t)f * ld * p.ldK;
+        for (int i = tid; i < 22 * 23; i += blockDim.x) s.A[i] = lin[i];
+        for (int i = tid; i < 27 * n; i += blockDim.x) s.B[i] = lin[22 * 23 + i];
+        for (int i = tid; i < 9 * n; i += blockDim.x) s.D[i] = lin[22 * 23 + 27 * p.nmax + i];
+        __syncthreads();
+    } else {
+    for (int i = tid; i < BASE; i += blockDim.x) s.mu[i] = mu_g[i];
+    for (int i = tid; i < 3 * n; i += blockDim.x) s.feat[i] = feat_g[i];
+    __syncthreads();
+    linearize_block(s, n, dt, cache_g, (p.flags & EKFVIO_FLAG_FRESH_DQ_CACHE) != 0);
+    }
 
     // Row-split launch (gridDim.y > 1, large states): every CTA of a filter reads the old state and
     // dq cache, so the new ones are staged in the (idle) gain panel and committed by
@@ -138,7 +238,7 @@ __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const do
         double* stage = p.K + (size_t)f * ld * p.ldK;
         mu_g = stage; feat_g = stage + BASE; cache_g = stage + BASE + 3 * p.nmax;
     }
-    if (n > 0 && tid == 0 && yb == 0) {  // cache ends fresh for the base omega (see linearize_block)
+    if (n > 0 && tid == 0 && yb == 0 && !pre) {  // cache ends fresh for the base omega (see linearize_block)
         cache_g[0] = s.mu[10]; cache_g[1] = s.mu[11]; cache_g[2] = s.mu[12];
         cache_g[3] = s.dq[4]; cache_g[4] = s.dq[5]; cache_g[5] = s.dq[6]; cache_g[6] = s.dq[7];
     }
@@ -160,7 +260,7 @@ __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const do
     }
 
     // state propagation: features with the OLD base state (:102-104), then the base state (:107)
-    if (yb == 0)
+    if (yb == 0 && !pre)
     for (int fi = tid; fi < n; fi += blockDim.x) {
         V3 vel{s.mu[7], s.mu[8], s.mu[9]}, acc{s.mu[13], s.mu[14], s.mu[15]};
         Q4 dq{s.dq[4], s.dq[5], s.dq[6], s.dq[7]};
@@ -168,7 +268,7 @@ __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const do
         convolve_feature(dq, vel, acc, dt, s.feat[3 * fi], s.feat[3 * fi + 1], s.feat[3 * fi + 2], o);
         feat_g[3 * fi] = o[0]; feat_g[3 * fi + 1] = o[1]; feat_g[3 * fi + 2] = o[2];
     }
-    if (tid == 0 && yb == 0) {
+    if (tid == 0 && yb == 0 && !pre) {
         double o[22];
         convolve_base(s.mu, dt, o);
         for (int i = 0; i < 22; ++i) mu_g[i] = o[i];
@@ -176,6 +276,7 @@ __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const do
 
     const double* Pi = Pin + (size_t)f * ld * ld;
     double* Po = Pout + (size_t)f * ld * ld;
+    if (p.flags & 0x800u) return;   // debug bit: linearisation + state only (timing experiments)
     if (fused) {
         // Sigma' = F Sigma F' + Q fused by row blocks: a warp takes three rows I of F, forms
         // T = F(I,:) Sigma (3 x N) in its slice of shared memory, then Sigma'(I,:) = T F'.
@@ -711,7 +812,14 @@ cudaError_t launch_process_general(const EkfPtrs& p, const double* Pin, double* 
         ysplit = (4 * 148 + p.F - 1) / p.F;
         if (ysplit > 16) ysplit = 16;
     }
-    ekf_process_general<<<dim3(p.F, ysplit), PT, sm, st>>>(p, Pin, Pout, dts, mode, F_out, fused);
+    // fused path on a batch that fills the GPU: linearisation in its own small-CTA launch
+    int pre = 0;
+    if (fused && p.F >= 2 * 148 && (size_t)p.ldP * p.ldK >= (size_t)22 * 23 + 36 * (size_t)p.nmax && proc_smem_bytes(p.nmax) <= 48 * 1024) {
+        ekf_linearize_kernel<<<p.F, 128, proc_smem_bytes(p.nmax), st>>>(p, dts);
+        pre = 1;
+        if (launches) *launches += 1;
+    }
+    ekf_process_general<<<dim3(p.F, ysplit), PT, sm, st>>>(p, Pin, Pout, dts, mode, F_out, fused, pre);
     if (ysplit > 1) ekf_commit_state_kernel<<<p.F, 128, 0, st>>>(p);
     if (launches) *launches += ysplit > 1 ? 2 : 1;
     return cudaGetLastError();
