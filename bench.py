@@ -191,7 +191,8 @@ def bench_ekf(args, rank, world, local):
     # ---- end-to-end arm: host buffers in, host state out, every step ----
     batch.reset()
     batch.add_features_h(kvec, init_uv)
-    h_mu = np.zeros((F, 22)); h_feat = np.zeros((F, n, 3))
+    h_mu = torch.zeros(F, 22, dtype=torch.float64).pin_memory().numpy()          # page-locked: the state is DMA'd straight into them
+    h_feat = torch.zeros(F, n, 3, dtype=torch.float64).pin_memory().numpy()
     meas_np = h_meas.numpy()                                   # page-locked: the C ABI DMAs straight from it
     R_pin = torch.from_numpy(R).pin_memory().numpy(); passed_pin = torch.from_numpy(passed).pin_memory().numpy()
 

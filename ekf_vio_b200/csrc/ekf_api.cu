@@ -55,6 +55,10 @@ int ekfvio_batch_destroy(ekfvio_batch* b) {
     cudaFree(b->d_S); cudaFree(b->d_L); cudaFree(b->d_asym); cudaFree(b->d_LS); cudaFree(b->d_LL); cudaFree(b->d_LT); cudaFree(b->d_y); cudaFree(b->d_idx); cudaFree(b->d_m); cudaFree(b->d_fjac);
     cudaFree(b->dd_z); cudaFree(b->dd_R); cudaFree(b->dd_pass);
     cudaFreeHost(b->h_z); cudaFreeHost(b->h_R); cudaFreeHost(b->h_pass); cudaFreeHost(b->h_out);
+    if (b->copy_st) cudaStreamDestroy(b->copy_st);
+    if (b->ev_h2d) cudaEventDestroy(b->ev_h2d);
+    if (b->ev_inputs_free) cudaEventDestroy(b->ev_inputs_free);
+    if (b->ev_state) cudaEventDestroy(b->ev_state);
     delete b;
     return 0;
 }
@@ -109,6 +113,13 @@ int ekfvio_batch_create(ekfvio_batch** out, int device, int num_filters, int max
         ekfvio_batch_destroy(b);
         return fail_msg("cudaMallocHost failed");
     }
+    if (cudaStreamCreateWithFlags(&b->copy_st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_inputs_free, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_state, cudaEventDisableTiming) != cudaSuccess) {
+        ekfvio_batch_destroy(b);
+        return fail_msg("stream / event creation failed");
+    }
     *out = b;
     int rc = ekfvio_batch_reset(b, nullptr);
     if (rc) { ekfvio_batch_destroy(b); *out = nullptr; return rc; }
@@ -122,6 +133,7 @@ long long ekfvio_batch_launch_count(const ekfvio_batch* b) { return b ? b->launc
 
 int ekfvio_batch_reset(ekfvio_batch* b, void* stream) {
     CU(cudaSetDevice(b->device));
+    b->state_ev_valid = false;   // state written on the caller's stream: downloads order behind that stream
     CU(launch_reset(ptrs(b), b->d_P[b->cur], (cudaStream_t)stream));
     b->launches += 1;
     return 0;
@@ -129,6 +141,7 @@ int ekfvio_batch_reset(ekfvio_batch* b, void* stream) {
 
 int ekfvio_batch_add_features(ekfvio_batch* b, const int* d_k, const double* d_uv, int kmax, void* stream) {
     CU(cudaSetDevice(b->device));
+    b->state_ev_valid = false;   // state written on the caller's stream: downloads order behind that stream
     CU(launch_add_features(ptrs(b), b->d_P[b->cur], d_k, d_uv, kmax, (cudaStream_t)stream));
     b->launches += 1;
     return 0;
@@ -139,6 +152,8 @@ int ekfvio_batch_process(ekfvio_batch* b, const double* d_dt, void* stream) {
     b->timer.begin(0, (cudaStream_t)stream);
     CU(launch_process_general(ptrs(b), b->d_P[b->cur], b->d_P[b->cur ^ 1], d_dt, 0, nullptr, (cudaStream_t)stream, &b->launches));
     b->timer.end((cudaStream_t)stream);
+    CU(cudaEventRecord(b->ev_state, (cudaStream_t)stream));
+    b->state_ev_valid = true;
     b->cur ^= 1;
     return 0;
 }
@@ -166,6 +181,8 @@ int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, c
         lp.S = b->d_LS; lp.L = b->d_LL; lp.T = b->d_LT;
         lp.mp = (b->mmax + 63) / 64 * 64; lp.nblk = lp.mp / 64; lp.nrt_max = (b->Nmax + 63) / 64;
         CU(launch_update_large(pp, lp, b->d_P[b->cur], b->d_P[b->cur ^ 1], d_z, d_R, d_pass, st, &b->launches, &b->timer));
+        CU(cudaEventRecord(b->ev_state, st)); CU(cudaEventRecord(b->ev_inputs_free, st));
+        b->state_ev_valid = b->inputs_ev_valid = true;
         b->cur ^= 1;
         return 0;
     }
@@ -186,6 +203,10 @@ int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, c
         CU(launch_gain_general(pp, b->d_P[b->cur], d_z, d_R, d_pass, b->d_S, st));
         b->timer.end(st);
     }
+    // the gain kernels have consumed z / R / pass and written the new state: the next upload and the
+    // state download may proceed while the covariance update runs
+    CU(cudaEventRecord(b->ev_state, st)); CU(cudaEventRecord(b->ev_inputs_free, st));
+    b->state_ev_valid = b->inputs_ev_valid = true;
     b->timer.begin(2, st);
     {
         const bool tiled = !(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | 0x200u)) && joseph_tiled_supported(pp);
@@ -271,6 +292,7 @@ int ekfvio_batch_get_state(ekfvio_batch* b, double* h_mu, double* h_feat, double
 int ekfvio_batch_set_state(ekfvio_batch* b, const double* h_mu, const double* h_feat, const double* h_P, const int* h_nfeat,
                            const double* h_cache, const uint8_t* h_flags, const double* h_klt_last) {
     CU(cudaSetDevice(b->device));
+    b->state_ev_valid = false;
     CU(cudaDeviceSynchronize());
     size_t F = b->F, nm = b->nmax;
     if (h_nfeat) {
@@ -341,22 +363,27 @@ int ekfvio_batch_update_h(ekfvio_batch* b, const double* h_z, const double* h_R,
     size_t F = b->F, nm = b->nmax;
     if (nm == 0) return ekfvio_batch_update(b, b->dd_z, b->dd_R, b->dd_pass, stream);
     // page-locked caller buffers are DMA'd from where they are; pageable ones are staged through the
-    // batch's pinned buffers (reused: wait for the previous consumer before overwriting them)
+    // batch's pinned buffers.  The copies run on the batch's copy stream: they wait for the previous
+    // update's gain kernels (the last readers of the device input buffers) and overlap whatever the
+    // caller's stream is still running (typically process()).
     const void* src[3] = {h_z, h_R, h_pass};
     void* stg[3] = {b->h_z, b->h_R, b->h_pass};
     void* dst[3] = {b->dd_z, b->dd_R, b->dd_pass};
     const size_t bytes[3] = {F * nm * 2 * sizeof(double), F * nm * 4 * sizeof(double), F * nm};
+    if (b->inputs_ev_valid) CU(cudaStreamWaitEvent(b->copy_st, b->ev_inputs_free, 0));
     bool synced = false;
     for (int i = 0; i < 3; ++i) {
         cudaPointerAttributes attr;
         const bool pinned = cudaPointerGetAttributes(&attr, src[i]) == cudaSuccess && attr.type == cudaMemoryTypeHost;
         if (!pinned) {
             cudaGetLastError();
-            if (!synced) { CU(cudaStreamSynchronize(st)); synced = true; }
+            if (!synced) { CU(cudaStreamSynchronize(b->copy_st)); synced = true; }   // staging buffers free again
             memcpy(stg[i], src[i], bytes[i]);
         }
-        CU(cudaMemcpyAsync(dst[i], pinned ? src[i] : stg[i], bytes[i], cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(dst[i], pinned ? src[i] : stg[i], bytes[i], cudaMemcpyHostToDevice, b->copy_st));
     }
+    CU(cudaEventRecord(b->ev_h2d, b->copy_st));
+    CU(cudaStreamWaitEvent(st, b->ev_h2d, 0));
     return ekfvio_batch_update(b, b->dd_z, b->dd_R, b->dd_pass, stream);
 }
 
@@ -393,11 +420,23 @@ int ekfvio_batch_read_mu_h(ekfvio_batch* b, double* h_mu, double* h_feat, void* 
     CU(cudaSetDevice(b->device));
     cudaStream_t st = (cudaStream_t)stream;
     size_t F = b->F, nm = b->nmax;
-    CU(cudaMemcpyAsync(b->h_out, b->d_mu, F * BASE * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (h_feat && nm) CU(cudaMemcpyAsync(b->h_out + F * BASE, b->d_feat, F * nm * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    if (h_mu) memcpy(h_mu, b->h_out, F * BASE * sizeof(double));
-    if (h_feat && nm) memcpy(h_feat, b->h_out + F * BASE, F * nm * 3 * sizeof(double));
+    // the download waits only for the last kernel that wrote the state, not for the covariance update
+    // behind it; page-locked caller buffers receive the DMA directly
+    cudaStream_t cs = st;
+    if (b->state_ev_valid) { cs = b->copy_st; CU(cudaStreamWaitEvent(cs, b->ev_state, 0)); }
+    auto is_pinned = [](const void* p) {
+        cudaPointerAttributes attr;
+        const bool ok = p && cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (!ok) cudaGetLastError();
+        return ok;
+    };
+    const bool want_feat = h_feat && nm;
+    const bool pin_mu = is_pinned(h_mu), pin_feat = want_feat && is_pinned(h_feat);
+    if (h_mu) CU(cudaMemcpyAsync(pin_mu ? h_mu : b->h_out, b->d_mu, F * BASE * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    if (want_feat) CU(cudaMemcpyAsync(pin_feat ? h_feat : b->h_out + F * BASE, b->d_feat, F * nm * 3 * sizeof(double), cudaMemcpyDeviceToHost, cs));
+    CU(cudaStreamSynchronize(cs));
+    if (h_mu && !pin_mu) memcpy(h_mu, b->h_out, F * BASE * sizeof(double));
+    if (want_feat && !pin_feat) memcpy(h_feat, b->h_out + F * BASE, F * nm * 3 * sizeof(double));
     return 0;
 }
 

@@ -164,4 +164,9 @@ struct ekfvio_batch {
     double* h_out = nullptr;
     long long launches = 0;
     KernelTimer timer;
+    // host-buffer entry points: copies run on their own stream, ordered against the kernels by events, so
+    // the upload of a step's measurements overlaps process() and the state download overlaps the covariance update
+    cudaStream_t copy_st = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_inputs_free = nullptr, ev_state = nullptr;
+    bool inputs_ev_valid = false, state_ev_valid = false;
 };
