@@ -100,6 +100,14 @@ SIGNATURES = {
     "ekfvio_klt_track_pair_h": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ekfvio_klt_read_level": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, C.POINTER(c_int), C.POINTER(c_int)]),
     "ekfvio_klt_launch_count": (C.c_longlong, [c_void_p]),
+    "ekfvio_fast_create": (c_int, [C.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int]),
+    "ekfvio_fast_destroy": (c_int, [c_void_p]),
+    "ekfvio_fast_detect": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ekfvio_fast_select": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_int, c_int, c_void_p]),
+    "ekfvio_fast_replenish_h": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "ekfvio_fast_launch_count": (C.c_longlong, [c_void_p]),
     "ekfvio_batch_enable_timing": (c_int, [c_void_p, c_int]),
     "ekfvio_batch_get_timing": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ekfvio_measure_fp64_peak": (c_int, [c_int, C.POINTER(c_double), C.POINTER(c_double)]),
@@ -325,3 +333,60 @@ class KltTracker:
         ms = np.zeros(8, np.float64); cnt = np.zeros(8, np.int64)
         _check(lib.ekfvio_klt_get_timing(self._h, _ptr(ms), _ptr(cnt)))
         return ms, cnt
+
+
+class FastDetector:
+    """Batched EKFVIO::replenishFeatures (EKFVIO.cpp:224-311): cv::FAST + check image + greedy scan."""
+
+    def __init__(self, width: int, height: int, max_batch: int, max_keypoints: int = 4096, device: int = 0):
+        self._h = c_void_p()
+        self.width, self.height, self.max_batch, self.max_keypoints = width, height, max_batch, max_keypoints
+        _check(lib.ekfvio_fast_create(C.byref(self._h), device, width, height, max_batch, max_keypoints))
+
+    def close(self):
+        if self._h:
+            lib.ekfvio_fast_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def detect(self, imgs, threshold: int, nonmax: bool, kp_xy, response, count):
+        """imgs: uint8 cuda [batch,H,pitch]; kp_xy int16 cuda [batch,max_keypoints,2]; response int32 or None; count int32 [batch]."""
+        _check(lib.ekfvio_fast_detect(self._h, _ptr(imgs), int(imgs.shape[2]), int(imgs.shape[0]), int(threshold), int(nonmax), _ptr(kp_xy),
+                                      _ptr(response), _ptr(count), _stream()))
+
+    def select(self, kp_xy, count, existing_px, n_existing, needed, min_dist, kill_pad, K9, new_px, new_metric, n_new):
+        """Device tensors; existing_px float32 [batch,max_existing,2] or None; new_px int16 [batch,max_new,2]."""
+        max_existing = int(existing_px.shape[1]) if existing_px is not None else 0
+        _check(lib.ekfvio_fast_select(self._h, _ptr(kp_xy), _ptr(count), _ptr(existing_px), _ptr(n_existing), max_existing, _ptr(needed),
+                                      int(min_dist), int(kill_pad), _ptr(K9), _ptr(new_px), _ptr(new_metric), _ptr(n_new), int(new_px.shape[1]),
+                                      int(new_px.shape[0]), _stream()))
+
+    def replenish_h(self, imgs: np.ndarray, threshold: int, existing_px, n_existing, needed, min_dist: int = 30, kill_pad: int = 11, K9=None,
+                    max_new: int = 128):
+        """Host arrays in, host arrays out: (new_px [batch,max_new,2] i16, new_metric f32 or None, n_new, kp_xy, count)."""
+        batch = imgs.shape[0]
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        needed = np.ascontiguousarray(needed, np.int32)
+        max_existing = 0
+        if existing_px is not None:
+            existing_px = np.ascontiguousarray(existing_px, np.float32); n_existing = np.ascontiguousarray(n_existing, np.int32)
+            max_existing = existing_px.shape[1]
+        if K9 is not None:
+            K9 = np.ascontiguousarray(K9, np.float32)
+        new_px = np.zeros((batch, max_new, 2), np.int16)
+        new_metric = np.zeros((batch, max_new, 2), np.float32) if K9 is not None else None
+        n_new = np.zeros(batch, np.int32)
+        kp = np.zeros((batch, self.max_keypoints, 2), np.int16); cnt = np.zeros(batch, np.int32)
+        _check(lib.ekfvio_fast_replenish_h(self._h, _ptr(imgs), int(imgs.shape[2]), batch, int(threshold), _ptr(existing_px), _ptr(n_existing),
+                                           max_existing, _ptr(needed), int(min_dist), int(kill_pad), _ptr(K9), _ptr(new_px), _ptr(new_metric),
+                                           _ptr(n_new), max_new, _ptr(kp), _ptr(cnt), _stream()))
+        return new_px, new_metric, n_new, kp, cnt
+
+    @property
+    def launches(self) -> int:
+        return int(lib.ekfvio_fast_launch_count(self._h))

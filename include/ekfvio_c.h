@@ -215,6 +215,43 @@ long long ekfvio_klt_launch_count(const ekfvio_klt* k);
 int ekfvio_klt_enable_timing(ekfvio_klt* k, int on);
 int ekfvio_klt_get_timing(ekfvio_klt* k, double* ms8, long long* count8);
 
+/* ------------------------------------------------------------------------------------------------
+ * Feature replenishment — EKFVIO::replenishFeatures (EKFVIO.cpp:224-311), the caller of
+ * TightlyCoupledEKF::addNewFeatures: cv::FAST(img, kp, FAST_THRESHOLD, true) (:242), the check image
+ * with cv::circle(.., MIN_NEW_FEATURE_DIST, 255, -1) around every feature already in the state
+ * (:255-260) and the greedy scan over the keypoints in detector order (:262-305).  Bit-identical to
+ * OpenCV: keypoint set, order (rows top to bottom, x ascending) and response, filled-circle raster.
+ * FAST_BLUR_SIGMA is 0 in the reference's defaults (Params.h:26), so no blur stage.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ekfvio_fast ekfvio_fast;
+
+/* max_keypoints: capacity of the keypoint list per image (more are counted but not stored). */
+int ekfvio_fast_create(ekfvio_fast** out, int device, int width, int height, int max_batch, int max_keypoints);
+int ekfvio_fast_destroy(ekfvio_fast* f);
+
+/* cv::FAST with the 9/16 pattern for a batch of 8-bit images d_imgs[batch][height][pitch].
+ * d_kp_xy[batch][max_keypoints][2] int16 (x, y); d_response[batch][max_keypoints] (cv::KeyPoint::response,
+ * may be NULL); d_count[batch] = number of keypoints found (the first max_keypoints are stored). */
+int ekfvio_fast_detect(ekfvio_fast* f, const uint8_t* d_imgs, int pitch, int batch, int threshold, int nonmax, short* d_kp_xy, int* d_response,
+                       int* d_count, void* stream);
+
+/* The greedy scan: d_existing_px[batch][max_existing][2] float pixel positions of the features in the
+ * state (Feature::getPixel, rounded like cv::Point), d_n_existing[batch] (both may be NULL),
+ * d_needed[batch] = NUM_FEATURES - features.size().  Outputs d_new_px[batch][max_new][2] int16,
+ * d_new_metric[batch][max_new][2] = Feature::pixel2Metric with d_K9[batch][9] column-major (E1
+ * semantics; both may be NULL), d_n_new[batch]. */
+int ekfvio_fast_select(ekfvio_fast* f, const short* d_kp_xy, const int* d_count, const float* d_existing_px, const int* d_n_existing,
+                       int max_existing, const int* d_needed, int min_dist, int kill_pad, const float* d_K9, short* d_new_px,
+                       float* d_new_metric, int* d_n_new, int max_new, int batch, void* stream);
+
+/* Host-buffer convenience for the whole of replenishFeatures: upload, detect (non-max suppression
+ * on), select, download; synchronous.  h_kp_xy / h_count (may be NULL) return the detector output. */
+int ekfvio_fast_replenish_h(ekfvio_fast* f, const uint8_t* h_imgs, int pitch, int batch, int threshold, const float* h_existing_px,
+                            const int* h_n_existing, int max_existing, const int* h_needed, int min_dist, int kill_pad, const float* h_K9,
+                            short* h_new_px, float* h_new_metric, int* h_n_new, int max_new, short* h_kp_xy, int* h_count, void* stream);
+
+long long ekfvio_fast_launch_count(const ekfvio_fast* f);
+
 #ifdef __cplusplus
 }
 #endif
