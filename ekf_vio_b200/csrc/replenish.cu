@@ -24,9 +24,8 @@ using ekfvio::fail_msg;
 
 struct ekfvio_fast {
     int device = 0, width = 0, height = 0, max_batch = 0, max_keypoints = 0;
-    int spitch = 0;                 // pitch of the score / mask planes (multiple of 16)
+    int spitch = 0;                 // pitch of the score plane (multiple of 16)
     uint8_t* d_score = nullptr;     // [max_batch][height][spitch]  cornerScore + 1, 0 = not a corner
-    uint8_t* d_mask = nullptr;      // [max_batch][height][spitch]  checkImg of the greedy scan
     // staging for the host-buffer entry point
     uint8_t* d_img = nullptr; short* d_kp = nullptr; int* d_resp = nullptr; int* d_count = nullptr;
     float* d_exist = nullptr; int* d_nexist = nullptr; int* d_needed = nullptr; float* d_K9 = nullptr;
@@ -233,25 +232,34 @@ __device__ void circle_half_widths(int radius, int* hw /*[2*radius+1]*/) {
     }
 }
 
-// The greedy scan of EKFVIO.cpp:252-305, one warp per frame.  The check image lives in global
-// memory (zeroed by the caller); circles are drawn row by row with the lanes along x.
+// The greedy scan of EKFVIO.cpp:252-305, one warp per frame.  The check image is a bit mask in shared
+// memory (one word per 32 pixels); a circle is drawn with the lanes along its rows, each lane OR-ing
+// the span of its row into the two or three words it touches.
 __global__ void __launch_bounds__(32) replenish_select_kernel(const short* __restrict__ kp_xy, const int* __restrict__ count, int max_kp,
                                                               const float* __restrict__ existing_px, const int* __restrict__ n_existing,
                                                               int max_existing, const int* __restrict__ needed_in, int radius, int kill_pad,
-                                                              const float* __restrict__ K9, uint8_t* __restrict__ mask_all, int mpitch,
-                                                              size_t mstride, int w, int h, short* __restrict__ new_px,
+                                                              const float* __restrict__ K9, int w, int h, short* __restrict__ new_px,
                                                               float* __restrict__ new_metric, int* __restrict__ n_new, int max_new) {
-    extern __shared__ int hw[];                // [2*radius+1]
+    extern __shared__ int sm_sel[];
+    int* hw = sm_sel;                          // [2*radius+1]
+    const int wpr = (w + 31) >> 5;
+    unsigned* bits = reinterpret_cast<unsigned*>(sm_sel + 2 * radius + 1);   // [h][wpr]
     const int b = blockIdx.x, lane = threadIdx.x;
-    uint8_t* mask = mask_all + (size_t)b * mstride;
+    for (int i = lane; i < h * wpr; i += 32) bits[i] = 0u;
     if (lane == 0) circle_half_widths(radius, hw);
     __syncwarp();
     auto draw = [&](int cx, int cy) {
-        for (int i = 0; i <= 2 * radius; ++i) {
+        for (int i = lane; i <= 2 * radius; i += 32) {
             const int y = cy - radius + i, half = hw[i];
             if (half < 0 || y < 0 || y >= h) continue;
             const int xa = max(cx - half, 0), xb = min(cx + half, w - 1);
-            for (int x = xa + lane; x <= xb; x += 32) mask[(size_t)y * mpitch + x] = 255;
+            if (xa > xb) continue;
+            const int w0 = xa >> 5, w1 = xb >> 5;
+            for (int ww = w0; ww <= w1; ++ww) {
+                const unsigned from = ww == w0 ? (xa & 31) : 0, to = ww == w1 ? (xb & 31) : 31;
+                const unsigned m = (to == 31 ? 0xffffffffu : ((1u << (to + 1)) - 1u)) & ~((1u << from) - 1u);
+                bits[y * wpr + ww] |= m;
+            }
         }
         __syncwarp();
     };
@@ -266,8 +274,7 @@ __global__ void __launch_bounds__(32) replenish_select_kernel(const short* __res
     const float* K = K9 ? K9 + (size_t)b * 9 : nullptr;
     for (int i = 0; i < needed && i < nk; ++i) {
         const int x = kp[i * 2], y = kp[i * 2 + 1];
-        const int taken = *reinterpret_cast<volatile uint8_t*>(mask + (size_t)y * mpitch + x);
-        if (taken) { ++needed; continue; }                                                       // too close to a feature (:282-286)
+        if (bits[y * wpr + (x >> 5)] >> (x & 31) & 1u) { ++needed; continue; }                     // too close to a feature (:282-286)
         if (x < kill_pad || y < kill_pad || w - x < kill_pad || h - y < kill_pad) { ++needed; continue; }   // Frame::isPixelInBox (:290-295)
         __syncwarp();
         draw(x, y);
@@ -290,7 +297,7 @@ extern "C" {
 int ekfvio_fast_destroy(ekfvio_fast* f) {
     if (!f) return 0;
     cudaSetDevice(f->device);
-    cudaFree(f->d_score); cudaFree(f->d_mask); cudaFree(f->d_img); cudaFree(f->d_kp); cudaFree(f->d_resp); cudaFree(f->d_count);
+    cudaFree(f->d_score); cudaFree(f->d_img); cudaFree(f->d_kp); cudaFree(f->d_resp); cudaFree(f->d_count);
     cudaFree(f->d_exist); cudaFree(f->d_nexist); cudaFree(f->d_needed); cudaFree(f->d_K9); cudaFree(f->d_new_px); cudaFree(f->d_new_metric);
     cudaFree(f->d_nnew);
     delete f;
@@ -312,7 +319,6 @@ int ekfvio_fast_create(ekfvio_fast** out, int device, int width, int height, int
     f->max_existing = 512;
     const size_t plane = (size_t)f->spitch * height * max_batch;
     cudaError_t e = cudaMalloc((void**)&f->d_score, plane);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_mask, plane);
     if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_img, plane);
     if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_kp, (size_t)max_batch * max_keypoints * 2 * sizeof(short));
     if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_resp, (size_t)max_batch * max_keypoints * sizeof(int));
@@ -356,12 +362,11 @@ int ekfvio_fast_select(ekfvio_fast* f, const short* d_kp_xy, const int* d_count,
     if (batch <= 0 || batch > f->max_batch || min_dist < 0 || min_dist > 1024 || max_new <= 0) return fail_msg("ekfvio_fast_select: bad arguments");
     CU(cudaSetDevice(f->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t mstride = (size_t)f->spitch * f->height;
-    CU(cudaMemsetAsync(f->d_mask, 0, mstride * batch, st));
-    replenish_select_kernel<<<batch, 32, (2 * min_dist + 1) * sizeof(int), st>>>(d_kp_xy, d_count, f->max_keypoints, d_existing_px, d_n_existing,
-                                                                                 max_existing, d_needed, min_dist, kill_pad, d_K9, f->d_mask,
-                                                                                 f->spitch, mstride, f->width, f->height, d_new_px, d_new_metric,
-                                                                                 d_n_new, max_new);
+    const size_t sm = ((size_t)(2 * min_dist + 1) + (size_t)f->height * ((f->width + 31) / 32)) * sizeof(int);
+    if (sm > 200 * 1024) return fail_msg("ekfvio_fast_select: check image does not fit in shared memory");
+    if (sm > 48 * 1024) CU(cudaFuncSetAttribute(replenish_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    replenish_select_kernel<<<batch, 32, sm, st>>>(d_kp_xy, d_count, f->max_keypoints, d_existing_px, d_n_existing, max_existing, d_needed, min_dist,
+                                                   kill_pad, d_K9, f->width, f->height, d_new_px, d_new_metric, d_n_new, max_new);
     CU(cudaGetLastError());
     f->launches += 1;
     return 0;
