@@ -229,6 +229,48 @@ def bench_ekf(args, rank, world, local):
     return res
 
 
+def bench_replenish(args, rank, world, local, prev, pts):
+    """SURVEY.md §8(f)1 — EKFVIO::replenishFeatures for a batch of frames: cv::FAST(50, nms) + check image + greedy
+    scan with 60 features already in the state and 40 wanted (NUM_FEATURES 100).  Frames resident in HBM; e2e from host."""
+    import torch
+    from ekf_vio_b200 import capi
+    B, K, W = prev.shape[0], args.steps, args.warmup
+    det = capi.FastDetector(640, 480, B, 4096, device=local)
+    d = torch.from_numpy(prev).cuda()
+    kp = torch.zeros(B, 4096, 2, dtype=torch.int16, device="cuda"); cnt = torch.zeros(B, dtype=torch.int32, device="cuda")
+    needed = torch.full((B,), 40, dtype=torch.int32, device="cuda")
+    ex_h = np.ascontiguousarray(pts[:, :60]); nex_h = np.full(B, 60, np.int32)
+    ex = torch.from_numpy(ex_h).cuda(); nex = torch.from_numpy(nex_h).cuda()
+    new_px = torch.zeros(B, 128, 2, dtype=torch.int16, device="cuda"); n_new = torch.zeros(B, dtype=torch.int32, device="cuda")
+
+    def step():
+        det.detect(d, 50, True, kp, None, cnt)
+        det.select(kp, cnt, ex, nex, needed, 30, 11, None, new_px, None, n_new)
+
+    for _ in range(W):
+        step()
+    barrier(world)
+    l0 = det.launches
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(K):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    launches = det.launches - l0
+    frames = sum_over_ranks(float(B), world)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        det.replenish_h(prev, 50, ex_h, nex_h, np.full(B, 40, np.int32))
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    res = {"metric": "frames replenished/s at 640x480 (FAST-9/16 + NMS + greedy min-distance scan)", "value": frames * K / (ms * 1e-3), "unit": "frames/s",
+           "ms_per_step": ms / K, "keypoints_per_frame": float(cnt.float().mean().item()), "new_per_frame": float(n_new.float().mean().item()),
+           "gpu_launches": int(launches), "e2e": {"value": frames * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(prev.nbytes + ex_h.nbytes)}}
+    det.close()
+    return res
+
+
 def bench_klt(args, rank, world, local):
     import torch
     from ekf_vio_b200 import capi, workload
@@ -319,6 +361,7 @@ def bench_klt(args, rank, world, local):
                      "level0_achieved": bytes_l0 / (ms_l0 * 1e-3) / 1e9},
     }
     trk.close()
+    res["replenish"] = bench_replenish(args, rank, world, local, prev, pts)
     return res
 
 
@@ -380,8 +423,17 @@ def cpu_baseline_klt(pairs: int = 8, reps: int = 3):
     for _ in range(reps):
         tracked += once()
     sec = time.perf_counter() - t0
+    # replenishFeatures' detector on the same frames (cv::FAST(50, nms); the scalar scan behind it is negligible)
+    fd = cv2.FastFeatureDetector_create(threshold=50, nonmaxSuppression=True)
+    fd.detect(prev[0])
+    t1 = time.perf_counter()
+    for _ in range(reps):
+        for i in range(pairs):
+            fd.detect(prev[i])
+    fast_fps = reps * pairs / (time.perf_counter() - t1)
     return {"value": tracked / sec, "unit": "features/s", "cores": int(cores), "kind": "reference",
-            "sample": f"cv2 {cv2.__version__} calcOpticalFlowPyrLK, {pairs} pairs x {reps} reps, 200 points each, {cores} threads"}
+            "sample": f"cv2 {cv2.__version__} calcOpticalFlowPyrLK, {pairs} pairs x {reps} reps, 200 points each, {cores} threads",
+            "replenish_frames_per_s": fast_fps}
 
 
 def run_reference(args):
