@@ -108,6 +108,7 @@ SIGNATURES = {
     "ekfvio_fast_replenish_h": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "ekfvio_fast_launch_count": (C.c_longlong, [c_void_p]),
+    "ekfvio_frame_resize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "ekfvio_batch_enable_timing": (c_int, [c_void_p, c_int]),
     "ekfvio_batch_get_timing": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ekfvio_measure_fp64_peak": (c_int, [c_int, C.POINTER(c_double), C.POINTER(c_double)]),
@@ -390,3 +391,13 @@ class FastDetector:
     @property
     def launches(self) -> int:
         return int(lib.ekfvio_fast_launch_count(self._h))
+
+
+def frame_resize(src, inv_scale: int, dst=None):
+    """Frame::Frame's cv::resize (Frame.cpp:19) for a batch: src uint8 cuda [batch,H,pitch] -> [batch,H//s,W//s] (pitch = width)."""
+    import torch
+    batch, h, w = src.shape
+    if dst is None:
+        dst = torch.empty(batch, h // inv_scale, w // inv_scale, dtype=torch.uint8, device=src.device)
+    _check(lib.ekfvio_frame_resize(_ptr(src), int(src.shape[2]), w, h, batch, int(inv_scale), _ptr(dst), int(dst.shape[2]), _stream()))
+    return dst

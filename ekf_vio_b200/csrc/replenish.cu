@@ -290,9 +290,70 @@ __global__ void __launch_bounds__(32) replenish_select_kernel(const short* __res
     if (lane == 0) n_new[b] = min(accepted, max_new);
 }
 
+// Frame::Frame (Frame.cpp:15-21): cv::resize(img, scaled, Size(cols / inv_scale, rows / inv_scale)) with the
+// default INTER_LINEAR on 8-bit images.  OpenCV's arithmetic: inv_scale 1 copies; 2 takes the
+// "area fast" path (a+b+c+d+2)>>2; otherwise 11-bit fixed-point coefficients per output column / row
+// (float source coordinate (d+0.5)*scale-0.5 computed in double, narrowed to float, floor, weights
+// rounded to 1/2048), horizontal pass in int, vertical pass ((b0*(r0>>4))>>16) + ((b1*(r1>>4))>>16) + 2 >> 2.
+__device__ __forceinline__ void resize_coeff(int d, double scale, int sn, int& s0, int& a0, int& a1) {
+    float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);    // no FMA contraction: OpenCV rounds the product first
+    int s = (int)floorf(f);
+    f -= (float)s;
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= sn - 1) { s = sn - 1; f = 0.f; }
+    s0 = s;
+    a0 = __float2int_rn(__fmul_rn(1.f - f, 2048.f));
+    a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+}
+
+__global__ void __launch_bounds__(256) frame_resize_kernel(const uint8_t* __restrict__ src, int spitch, size_t sstride, int sw, int sh,
+                                                           uint8_t* __restrict__ dst, int dpitch, size_t dstride, int dw, int dh, int inv_scale,
+                                                           double scale_x, double scale_y) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), b = blockIdx.z;
+    if (x >= dw || y >= dh) return;
+    const uint8_t* S = src + (size_t)b * sstride;
+    int out;
+    if (inv_scale == 1) {
+        out = S[(size_t)y * spitch + x];
+    } else if (inv_scale == 2) {
+        const uint8_t* r0 = S + (size_t)(2 * y) * spitch + 2 * x;
+        const uint8_t* r1 = r0 + spitch;
+        out = (r0[0] + r0[1] + r1[0] + r1[1] + 2) >> 2;
+    } else {
+        int sx, ax0, ax1, sy, ay0, ay1;
+        resize_coeff(x, scale_x, sw, sx, ax0, ax1);
+        resize_coeff(y, scale_y, sh, sy, ay0, ay1);
+        const int sx1 = min(sx + 1, sw - 1), sy1 = min(sy + 1, sh - 1);
+        const uint8_t* r0 = S + (size_t)sy * spitch;
+        const uint8_t* r1 = S + (size_t)sy1 * spitch;
+        const int h0 = r0[sx] * ax0 + r0[sx1] * ax1, h1 = r1[sx] * ax0 + r1[sx1] * ax1;
+        out = (((ay0 * (h0 >> 4)) >> 16) + ((ay1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        out = min(max(out, 0), 255);
+    }
+    dst[(size_t)b * dstride + (size_t)y * dpitch + x] = (uint8_t)out;
+}
+
 }  // namespace
 
 extern "C" {
+
+int ekfvio_frame_resize(const uint8_t* d_src, int src_pitch, int src_width, int src_height, int batch, int inv_scale, uint8_t* d_dst,
+                        int dst_pitch, void* stream) {
+    if (!d_src || !d_dst || src_width <= 0 || src_height <= 0 || batch <= 0 || inv_scale <= 0) return fail_msg("ekfvio_frame_resize: bad arguments");
+    const int dw = src_width / inv_scale, dh = src_height / inv_scale;
+    if (dw <= 0 || dh <= 0 || src_pitch < src_width || dst_pitch < dw) return fail_msg("ekfvio_frame_resize: bad sizes");
+    // resize.cpp: inv_scale_x = dsize.width / ssize.width; scale_x = 1. / inv_scale_x
+    const double scale_x = 1.0 / ((double)dw / src_width), scale_y = 1.0 / ((double)dh / src_height);
+    // the area-fast substitution needs exact 2x in both directions (resize.cpp: is_area_fast && iscale == 2)
+    int mode = inv_scale;
+    if (inv_scale == 2 && (dw * 2 != src_width || dh * 2 != src_height)) mode = 3 /* any value > 2: general path */;
+    dim3 grid((dw + 31) / 32, (dh + 7) / 8, batch);
+    frame_resize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_src, src_pitch, (size_t)src_pitch * src_height, src_width, src_height, d_dst,
+                                                               dst_pitch, (size_t)dst_pitch * dh, dw, dh, mode, scale_x, scale_y);
+    CU(cudaGetLastError());
+    return 0;
+}
+
 
 int ekfvio_fast_destroy(ekfvio_fast* f) {
     if (!f) return 0;

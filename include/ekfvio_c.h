@@ -252,6 +252,14 @@ int ekfvio_fast_replenish_h(ekfvio_fast* f, const uint8_t* h_imgs, int pitch, in
 
 long long ekfvio_fast_launch_count(const ekfvio_fast* f);
 
+/* Frame::Frame (Frame.cpp:15-21): cv::resize(img, scaled, Size(cols / inv_scale, rows / inv_scale)), default
+ * INTER_LINEAR, for a batch of 8-bit images d_src[batch][src_height][src_pitch] ->
+ * d_dst[batch][src_height / inv_scale][dst_pitch]; bit-identical to OpenCV (area-fast path at exactly 2x,
+ * 11-bit fixed-point bilinear otherwise).  The K scaling of Frame.cpp:26-30 is four host divisions and stays
+ * with the caller.  Asynchronous on `stream`. */
+int ekfvio_frame_resize(const uint8_t* d_src, int src_pitch, int src_width, int src_height, int batch, int inv_scale, uint8_t* d_dst,
+                        int dst_pitch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

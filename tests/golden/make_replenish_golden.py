@@ -50,4 +50,8 @@ for name in ("gray0", "gray_moved", "gray_shear"):
         kp2 = det.detect(img)
         out[f"{name}_kp_thr{thr}_nonms"] = np.array([[int(k.pt[0]), int(k.pt[1])] for k in kp2], np.int16)
     print(name, len(kps), "keypoints;", len(new_a), "new from empty;", len(new_b), "new with 60 existing")
+# Frame::Frame's cv::resize (Frame.cpp:19) at the reference's default INVERSE_IMAGE_SCALE 4 and at 2, 3, 5
+for s in (2, 3, 4, 5):
+    out[f"gray0_resize{s}"] = cv2.resize(g["gray0"], (W // s, H // s))
+out["gray0_crop_resize2"] = cv2.resize(np.ascontiguousarray(g["gray0"][:479, :639]), (639 // 2, 479 // 2))   # 2x but not area-fast
 np.savez_compressed("tests/golden/replenish_golden.npz", **out)

@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import replenish_oracle as R  # noqa: E402
+import frame_oracle as FO  # noqa: E402
 
 NAMES = ("gray0", "gray_moved", "gray_shear")
 
@@ -124,3 +125,27 @@ def test_bad_arguments_fail_loudly(cuda):
     with pytest.raises(RuntimeError):
         det.replenish_h(np.zeros((2, 48, 64), np.uint8), 50, None, None, np.array([1, 1]))   # batch above capacity
     det.close()
+
+
+def test_frame_resize_bit_exact(cuda, gold):
+    """Frame::Frame's cv::resize (Frame.cpp:19): cv2 golden at 2x (area-fast), 3x, 4x (the default), 5x; oracle on ragged sizes."""
+    import torch
+    from ekf_vio_b200 import capi
+    G, I = gold
+    g0 = I["gray0"]
+    d = torch.from_numpy(np.stack([g0, I["gray_moved"]])).cuda()
+    for s in (1, 2, 3, 4, 5):
+        out = capi.frame_resize(d, s).cpu().numpy()
+        ref = g0 if s == 1 else G[f"gray0_resize{s}"]
+        np.testing.assert_array_equal(out[0], ref)
+        np.testing.assert_array_equal(out[1], FO.resize(I["gray_moved"], s))
+    crop = torch.from_numpy(np.ascontiguousarray(g0[:479, :639])[None]).cuda()
+    np.testing.assert_array_equal(capi.frame_resize(crop, 2).cpu().numpy()[0], G["gray0_crop_resize2"])
+    rng = np.random.default_rng(5)
+    for (w, h) in [(752, 480), (641, 479), (97, 33), (1280, 720)]:
+        img = rng.integers(0, 256, (3, h, w)).astype(np.uint8)
+        dd = torch.from_numpy(img).cuda()
+        for s in (2, 3, 4, 7):
+            out = capi.frame_resize(dd, s).cpu().numpy()
+            for b in range(3):
+                np.testing.assert_array_equal(out[b], FO.resize(img[b], s))

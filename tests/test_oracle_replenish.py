@@ -9,6 +9,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import replenish_oracle as R  # noqa: E402
+import frame_oracle as FO  # noqa: E402
 
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "replenish_golden.npz"))
 IMGS = np.load(os.path.join(ROOT, "tests", "golden", "klt_config2.npz"))
@@ -47,3 +48,20 @@ def test_pixel2metric_uses_linear_indices_of_K():
     kp = np.array([[100, 50]], np.int32)
     px, metric = R.select_new_features(kp, [], 640, 480, 1, K9=K.T.reshape(-1))
     np.testing.assert_allclose(metric[0], [100 / 300.0, 50 / 310.0], rtol=1e-6)
+
+
+def test_frame_resize_matches_cv2_golden():
+    g0 = IMGS["gray0"]
+    for s in (2, 3, 4, 5):
+        np.testing.assert_array_equal(FO.resize(g0, s), GOLD[f"gray0_resize{s}"])
+    np.testing.assert_array_equal(FO.resize(np.ascontiguousarray(g0[:479, :639]), 2), GOLD["gray0_crop_resize2"])
+    np.testing.assert_array_equal(FO.resize(g0, 1), g0)
+
+
+def test_frame_resize_matches_cv2_on_random_sizes_when_available():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    for (w, h) in [(752, 480), (1280, 720), (641, 479), (97, 33)]:
+        img = rng.integers(0, 256, (h, w)).astype(np.uint8)
+        for s in (2, 3, 4, 7):
+            np.testing.assert_array_equal(FO.resize(img, s), cv2.resize(img, (w // s, h // s)))
