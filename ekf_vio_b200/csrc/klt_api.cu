@@ -36,6 +36,8 @@ int ekfvio_klt_destroy(ekfvio_klt* k) {
     cudaSetDevice(k->device);
     cudaFree(k->d_slots); cudaFree(k->d_prev_pts); cudaFree(k->d_next_pts); cudaFree(k->d_status); cudaFree(k->d_err); cudaFree(k->d_npts);
     cudaFreeHost(k->h_img); cudaFreeHost(k->h_pts);
+    if (k->copy_st) cudaStreamDestroy(k->copy_st);
+    for (int i = 0; i < 4; ++i) if (k->ev_chunk[i]) cudaEventDestroy(k->ev_chunk[i]);
     delete[] k->slot_has_derivs; delete[] k->slot_batch;
     delete k;
     return 0;
@@ -86,6 +88,8 @@ int ekfvio_klt_create(ekfvio_klt** out, int device, int width, int height, int m
     if (e == cudaSuccess) e = cudaMalloc((void**)&k->d_npts, max_batch * sizeof(int));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&k->h_img, 2 * P.lv[0].img_stride * max_batch);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&k->h_pts, npt * 6 * sizeof(float) + max_batch * sizeof(int));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&k->copy_st, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&k->ev_chunk[i], cudaEventDisableTiming);
     if (e != cudaSuccess) { ekfvio_klt_destroy(k); return ekfvio::fail("ekfvio_klt_create alloc", e); }
     size_t smem = track_smem_bytes(win);
     (void)smem;
@@ -112,7 +116,7 @@ long long ekfvio_klt_launch_count(const ekfvio_klt* k) { return k ? k->launches 
 
 // Builds one or two slots level by level; both slots share each level's launch.
 static int build_slots(ekfvio_klt* k, int nslots, const int* slots, const uint8_t* const* imgs, int pitch, int batch, const int* with_derivs,
-                       cudaStream_t st) {
+                       cudaStream_t st, int first = 0, int total = -1) {   // images [first, first + batch) of a batch of `total`
     const Pyr& P = k->pyr;
     for (int l = 0; l < P.levels; ++l) {
         const Level& L = P.lv[l];
@@ -124,10 +128,12 @@ static int build_slots(ekfvio_klt* k, int nslots, const int* slots, const uint8_
             if (s >= nslots) continue;
             uint8_t* base = k->d_slots + (size_t)slots[s] * k->slot_bytes;
             J.batch = batch;
-            if (l == 0 && imgs[s]) { J.src = imgs[s]; J.spitch = pitch; J.sstride = (size_t)pitch * k->height; J.copy_dst = base + L.img_off; }
-            else { J.src = base + L.img_off; J.spitch = L.pitch; J.sstride = L.img_stride; }
-            if (with_derivs[s]) J.deriv = reinterpret_cast<short2*>(base + L.der_off);
-            if (l + 1 < P.levels) J.down = base + P.lv[l + 1].img_off;
+            if (l == 0 && imgs[s]) {
+                J.src = imgs[s] + (size_t)first * pitch * k->height; J.spitch = pitch; J.sstride = (size_t)pitch * k->height;
+                J.copy_dst = base + L.img_off + (size_t)first * L.img_stride;
+            } else { J.src = base + L.img_off + (size_t)first * L.img_stride; J.spitch = L.pitch; J.sstride = L.img_stride; }
+            if (with_derivs[s]) J.deriv = reinterpret_cast<short2*>(base + L.der_off + (size_t)first * L.der_stride);
+            if (l + 1 < P.levels) J.down = base + P.lv[l + 1].img_off + (size_t)first * P.lv[l + 1].img_stride;
             any = any || J.copy_dst || J.deriv || J.down;
         }
         if (!any) continue;
@@ -138,7 +144,7 @@ static int build_slots(ekfvio_klt* k, int nslots, const int* slots, const uint8_
         k->timer.end(st);
         k->launches += 1;
     }
-    for (int s = 0; s < nslots; ++s) { k->slot_has_derivs[slots[s]] = with_derivs[s] != 0; k->slot_batch[slots[s]] = batch; }
+    for (int s = 0; s < nslots; ++s) { k->slot_has_derivs[slots[s]] = with_derivs[s] != 0; k->slot_batch[slots[s]] = total < 0 ? batch : total; }
     return 0;
 }
 
@@ -168,7 +174,7 @@ int ekfvio_klt_track(ekfvio_klt* k, int prev_slot, int next_slot, const float* d
     CU(cudaSetDevice(k->device));
     k->timer.begin(4, (cudaStream_t)stream);
     CU(launch_track(k->pyr, k->d_slots + (size_t)prev_slot * k->slot_bytes, k->d_slots + (size_t)next_slot * k->slot_bytes, d_prev_pts, d_next_pts,
-                    d_status, d_err, d_npts, k->max_points, batch, k->prm, (cudaStream_t)stream));
+                    d_status, d_err, d_npts, k->max_points, 0, batch, k->prm, (cudaStream_t)stream));
     k->timer.end((cudaStream_t)stream);
     k->launches += 1;
     return 0;
@@ -191,27 +197,6 @@ int ekfvio_klt_track_pair_h(ekfvio_klt* k, const uint8_t* h_prev, const uint8_t*
     const Level& L0 = k->pyr.lv[0];
     uint8_t* s0 = k->d_slots;                   // slot 0 <- prev
     uint8_t* s1 = k->d_slots + k->slot_bytes;   // slot 1 <- next
-    // frames go straight into level 0 of the slots (no staging copy on the device).  Page-locked caller
-    // buffers are DMA'd from where they are; pageable ones go through the tracker's pinned staging area.
-    for (int which = 0; which < 2; ++which) {
-        const uint8_t* h = which ? h_next : h_prev;
-        uint8_t* dst = (which ? s1 : s0) + L0.img_off;
-        cudaPointerAttributes attr;
-        const bool pinned = cudaPointerGetAttributes(&attr, h) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-        if (!pinned) cudaGetLastError();
-        if (pinned && L0.img_stride == (size_t)L0.pitch * k->height) {
-            CU(cudaMemcpy2DAsync(dst, L0.pitch, h, pitch, k->width, (size_t)k->height * batch, cudaMemcpyHostToDevice, st));
-        } else if (pinned) {
-            for (int b = 0; b < batch; ++b)
-                CU(cudaMemcpy2DAsync(dst + (size_t)b * L0.img_stride, L0.pitch, h + (size_t)b * k->height * pitch, pitch, k->width, k->height, cudaMemcpyHostToDevice, st));
-        } else {
-            uint8_t* stage = k->h_img + (size_t)which * L0.img_stride * k->max_batch;
-            for (int b = 0; b < batch; ++b)
-                for (int y = 0; y < k->height; ++y)
-                    memcpy(stage + (size_t)b * L0.img_stride + (size_t)y * L0.pitch, h + ((size_t)b * k->height + y) * pitch, (size_t)k->width);
-            CU(cudaMemcpyAsync(dst, stage, L0.img_stride * batch, cudaMemcpyHostToDevice, st));
-        }
-    }
     size_t npt = (size_t)batch * k->max_points;
     float* hp = k->h_pts;
     memcpy(hp, h_prev_pts, npt * 2 * sizeof(float));
@@ -223,10 +208,50 @@ int ekfvio_klt_track_pair_h(ekfvio_klt* k, const uint8_t* h_prev, const uint8_t*
     CU(cudaMemcpyAsync(k->d_npts, hn, batch * sizeof(int), cudaMemcpyHostToDevice, st));
     CU(cudaMemsetAsync(k->d_status, 0, npt, st));
     CU(cudaMemsetAsync(k->d_err, 0, npt * sizeof(float), st));
-    int rc = ekfvio_klt_build_pyramid_pair(k, 0, nullptr, 1, nullptr, 0, batch, 0, stream);
-    if (rc) return rc;
-    rc = ekfvio_klt_track(k, 0, 1, k->d_prev_pts, k->d_next_pts, k->d_status, k->d_err, k->d_npts, batch, stream);
-    if (rc) return rc;
+    // Frames go straight into level 0 of the slots (no staging copy on the device).  Page-locked caller
+    // buffers are DMA'd from where they are; pageable ones go through the tracker's pinned staging area.
+    // The batch is cut into chunks: a copy stream uploads chunk c+1 while the caller's stream builds the
+    // pyramids of chunk c and tracks its points, so the PCIe transfer hides the kernels.
+    cudaPointerAttributes attr;
+    bool pinned[2];
+    for (int which = 0; which < 2; ++which) {
+        pinned[which] = cudaPointerGetAttributes(&attr, which ? h_next : h_prev) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (!pinned[which]) cudaGetLastError();
+    }
+    const int nchunks = batch >= 32 ? 4 : 1, per = (batch + nchunks - 1) / nchunks;
+    CU(cudaEventRecord(k->ev_chunk[0], st));                  // the slots may still be read by earlier work on the caller's stream
+    CU(cudaStreamWaitEvent(k->copy_st, k->ev_chunk[0], 0));
+    const int slots[2] = {0, 1};
+    const uint8_t* none[2] = {nullptr, nullptr};
+    const int wd[2] = {1, 0};
+    for (int c = 0, first = 0; first < batch; ++c, first += per) {
+        const int nb = batch - first < per ? batch - first : per;
+        for (int which = 0; which < 2; ++which) {
+            const uint8_t* h = (which ? h_next : h_prev) + (size_t)first * k->height * pitch;
+            uint8_t* dst = (which ? s1 : s0) + L0.img_off + (size_t)first * L0.img_stride;
+            if (pinned[which] && L0.img_stride == (size_t)L0.pitch * k->height) {
+                CU(cudaMemcpy2DAsync(dst, L0.pitch, h, pitch, k->width, (size_t)k->height * nb, cudaMemcpyHostToDevice, k->copy_st));
+            } else if (pinned[which]) {
+                for (int b = 0; b < nb; ++b)
+                    CU(cudaMemcpy2DAsync(dst + (size_t)b * L0.img_stride, L0.pitch, h + (size_t)b * k->height * pitch, pitch, k->width, k->height,
+                                         cudaMemcpyHostToDevice, k->copy_st));
+            } else {
+                uint8_t* stage = k->h_img + (size_t)which * L0.img_stride * k->max_batch + (size_t)first * L0.img_stride;
+                for (int b = 0; b < nb; ++b)
+                    for (int y = 0; y < k->height; ++y)
+                        memcpy(stage + (size_t)b * L0.img_stride + (size_t)y * L0.pitch, h + ((size_t)b * k->height + y) * pitch, (size_t)k->width);
+                CU(cudaMemcpyAsync(dst, stage, L0.img_stride * nb, cudaMemcpyHostToDevice, k->copy_st));
+            }
+        }
+        CU(cudaEventRecord(k->ev_chunk[c & 3], k->copy_st));
+        CU(cudaStreamWaitEvent(st, k->ev_chunk[c & 3], 0));
+        int rc = build_slots(k, 2, slots, none, 0, nb, wd, st, first, batch);
+        if (rc) return rc;
+        k->timer.begin(4, st);
+        CU(launch_track(k->pyr, s0, s1, k->d_prev_pts, k->d_next_pts, k->d_status, k->d_err, k->d_npts, k->max_points, first, nb, k->prm, st));
+        k->timer.end(st);
+        k->launches += 1;
+    }
     float* ho = hp + npt * 2;  // reuse: next pts | err | status
     CU(cudaMemcpyAsync(ho, k->d_next_pts, npt * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(ho + npt * 2, k->d_err, npt * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -61,4 +61,6 @@ struct ekfvio_klt {
     float* h_pts = nullptr;           // pinned: max_batch*max_points*(2+2+1) floats + status bytes
     long long launches = 0;
     KernelTimer timer;
+    cudaStream_t copy_st = nullptr;   // uploads of the host-buffer entry point, chunk by chunk
+    cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
 };

@@ -292,10 +292,10 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
                                                                const float* __restrict__ prev_pts, float* __restrict__ next_pts,
                                                                uint8_t* __restrict__ status, float* __restrict__ err, const int* __restrict__ npts,
                                                                int max_points, int win, int max_count, double epsilon, double min_eig,
-                                                               int use_initial_flow) {
+                                                               int use_initial_flow, int first_image) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.y;
+    const int b = blockIdx.y + first_image;      // (a launch may cover a sub-range of the batch: chunked uploads)
     const int pt = blockIdx.x * WARPS + warp;
     if (pt >= npts[b]) return;
     const int jw1 = win + 1, tarea = jw1 * jw1;
@@ -540,14 +540,15 @@ cudaError_t launch_level(const LevelJob& j0, const LevelJob& j1, int w, int h, i
 size_t track_smem_bytes(int win) { return track_warp_bytes(win) * WARPS; }
 
 cudaError_t launch_track(const Pyr& pyr, const uint8_t* prev_slot, const uint8_t* next_slot, const float* prev_pts, float* next_pts,
-                         uint8_t* status, float* err, const int* npts, int max_points, int batch, const ekfvio_klt_params& prm, cudaStream_t st) {
+                         uint8_t* status, float* err, const int* npts, int max_points, int first_image, int batch, const ekfvio_klt_params& prm,
+                         cudaStream_t st) {
     int mc = prm.max_iterations < 0 ? 0 : (prm.max_iterations > 100 ? 100 : prm.max_iterations);
     double eps = prm.epsilon < 0 ? 0 : (prm.epsilon > 10 ? 10 : prm.epsilon);
     eps *= eps;
     dim3 grid((max_points + WARPS - 1) / WARPS, batch);
     klt_track_kernel<<<grid, WARPS * 32, track_smem_bytes(prm.window_size), st>>>(pyr, prev_slot, next_slot, prev_pts, next_pts, status, err, npts,
                                                                                  max_points, prm.window_size, mc, eps, prm.min_eigen,
-                                                                                 prm.use_initial_flow);
+                                                                                 prm.use_initial_flow, first_image);
     return cudaGetLastError();
 }
 
