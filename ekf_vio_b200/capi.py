@@ -57,7 +57,7 @@ class KltParams(C.Structure):
 class BatchView(C.Structure):
     _fields_ = [
         ("d_mu", c_void_p), ("d_feat", c_void_p), ("d_P", c_void_p), ("d_nfeat", c_void_p), ("d_status", c_void_p),
-        ("ldP", C.c_int), ("num_filters", C.c_int), ("max_features", C.c_int),
+        ("ldP", C.c_int), ("num_filters", C.c_int), ("max_features", C.c_int), ("d_klt_last", c_void_p),
     ]
 
 
@@ -108,6 +108,13 @@ SIGNATURES = {
     "ekfvio_fast_replenish_h": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "ekfvio_fast_launch_count": (C.c_longlong, [c_void_p]),
+    "ekfvio_vio_default_params": (None, [c_void_p]),
+    "ekfvio_vio_create": (c_int, [C.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "ekfvio_vio_destroy": (c_int, [c_void_p]),
+    "ekfvio_vio_add_frame": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "ekfvio_vio_filters": (c_void_p, [c_void_p]),
+    "ekfvio_vio_frame_count": (c_int, [c_void_p]),
+    "ekfvio_vio_launch_count": (C.c_longlong, [c_void_p]),
     "ekfvio_frame_resize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "ekfvio_batch_enable_timing": (c_int, [c_void_p, c_int]),
     "ekfvio_batch_get_timing": (c_int, [c_void_p, c_void_p, c_void_p]),
@@ -401,3 +408,48 @@ def frame_resize(src, inv_scale: int, dst=None):
         dst = torch.empty(batch, h // inv_scale, w // inv_scale, dtype=torch.uint8, device=src.device)
     _check(lib.ekfvio_frame_resize(_ptr(src), int(src.shape[2]), w, h, batch, int(inv_scale), _ptr(dst), int(dst.shape[2]), _stream()))
     return dst
+
+
+class VioParams(C.Structure):
+    _fields_ = [("num_features", c_int), ("fast_threshold", c_int), ("min_new_feature_dist", c_int)]
+
+
+class VioLoop:
+    """EKFVIO::addFrame (EKFVIO.cpp:139-196) for S sequences on the device: process -> KLT -> update -> replenish."""
+
+    def __init__(self, num_sequences: int, width: int, height: int, num_features: int = 100, fast_threshold: int = 50, min_dist: int = 30,
+                 device: int = 0, ekf_params: Params | None = None):
+        self._h = c_void_p()
+        vp = VioParams(num_features, fast_threshold, min_dist)
+        ep = ekf_params if ekf_params is not None else default_params()
+        _check(lib.ekfvio_vio_create(C.byref(self._h), device, num_sequences, width, height, C.addressof(ep), None, C.addressof(vp)))
+        self.S, self.num_features = num_sequences, num_features
+        # a non-owning EkfBatch over the loop's filters, for state read-out
+        self.filters = EkfBatch.__new__(EkfBatch)
+        self.filters._h = c_void_p(lib.ekfvio_vio_filters(self._h))
+        self.filters.F, self.filters.nmax, self.filters.Nmax, self.filters.device = num_sequences, num_features, 22 + 3 * num_features, device
+        self.filters.close = lambda: None
+
+    def add_frame(self, frames, K9, dt=None):
+        """frames uint8 cuda [S,H,pitch]; K9 float32 cuda [S,9] column-major; dt float64 cuda [S] (None on the first frame)."""
+        _check(lib.ekfvio_vio_add_frame(self._h, _ptr(frames), int(frames.shape[2]), _ptr(K9), _ptr(dt), _stream()))
+
+    @property
+    def frame_count(self) -> int:
+        return int(lib.ekfvio_vio_frame_count(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(lib.ekfvio_vio_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            self.filters._h = c_void_p()
+            lib.ekfvio_vio_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

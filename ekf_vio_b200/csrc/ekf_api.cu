@@ -260,7 +260,7 @@ int ekfvio_measure_fp64_peak(int device, double* dmma_tflops, double* dfma_tflop
 
 int ekfvio_batch_get_view(ekfvio_batch* b, ekfvio_batch_view* v) {
     v->d_mu = b->d_mu; v->d_feat = b->d_feat; v->d_P = b->d_P[b->cur]; v->d_nfeat = b->d_nfeat; v->d_status = b->d_status;
-    v->ldP = b->ldP; v->num_filters = b->F; v->max_features = b->nmax;
+    v->ldP = b->ldP; v->num_filters = b->F; v->max_features = b->nmax; v->d_klt_last = b->d_klt_last;
     return 0;
 }
 

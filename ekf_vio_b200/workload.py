@@ -117,3 +117,23 @@ def klt_pairs(first_seq: int, num_pairs: int, w: int = 640, h: int = 480, npts: 
         pts[i, :, 1] = rng.uniform(40, h - 40, npts)
         flow[i] = (tx, ty)
     return prev, nxt, pts, flow
+
+
+def vio_sequences(first_seq: int, num_seq: int, num_frames: int, w: int = 640, h: int = 480, speed: float = 3.0):
+    """frames [T, S, h, w] u8: sequence g = first_seq + i pans over its texture with a constant velocity
+    (|v| <= speed px/frame, drawn from Philox(key=g)) — the camera-translation case of the frame loop."""
+    m = 64
+    assert speed * num_frames < m, "pan leaves the texture margin"
+    frames = np.zeros((num_frames, num_seq, h, w), np.uint8)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    textures = {}
+    for i in range(num_seq):
+        g = first_seq + i
+        rng = np.random.Generator(np.random.Philox(key=2_000_003 + g))
+        tkey = g % 8
+        if tkey not in textures:
+            textures[tkey] = texture(np.random.Generator(np.random.Philox(key=7_000_001 + tkey)), h + 2 * m, w + 2 * m)
+        vx, vy = rng.uniform(-speed, speed, 2)
+        for t in range(num_frames):
+            frames[t, i] = np.clip(np.rint(_bilinear(textures[tkey], xx - vx * t + m, yy - vy * t + m)), 0, 255).astype(np.uint8)
+    return frames

@@ -125,6 +125,7 @@ typedef struct ekfvio_batch_view {
     int* d_status;      /* [F] */
     int ldP;            /* leading dimension of P (>= Nmax, multiple of 8) */
     int num_filters, max_features;
+    double* d_klt_last; /* [F][nmax][2] last KLT result per feature (Feature::last_result_from_klt_tracker) */
 } ekfvio_batch_view;
 int ekfvio_batch_get_view(ekfvio_batch* b, ekfvio_batch_view* view);
 
@@ -251,6 +252,34 @@ int ekfvio_fast_replenish_h(ekfvio_fast* f, const uint8_t* h_imgs, int pitch, in
                             short* h_new_px, float* h_new_metric, int* h_n_new, int max_new, short* h_kp_xy, int* h_count, void* stream);
 
 long long ekfvio_fast_launch_count(const ekfvio_fast* f);
+
+/* ------------------------------------------------------------------------------------------------
+ * Frame loop — EKFVIO::addFrame (EKFVIO.cpp:139-196) for one new frame of each of S independent
+ * sequences, entirely on the device: first frame -> replenishFeatures; afterwards process(dt) (:163),
+ * updateStateWithNewImage (:169 = KLTTracker::findNewFeaturePositions with prev = metric2Pixel(last KLT
+ * result), initial flow = Feature::getPixel of the predicted state, :201-217, then
+ * updateWithFeaturePositions), replenishFeatures (:172).  Every frame's pyramid is built once (with
+ * derivatives) and serves as "previous" for the next frame.  The ROS glue around it (publishers,
+ * tf, frame buffer bookkeeping) stays with the caller.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ekfvio_vio ekfvio_vio;
+typedef struct ekfvio_vio_params {
+    int num_features;          /* NUM_FEATURES, Params.h:46 (100) — also the filters' feature capacity */
+    int fast_threshold;        /* FAST_THRESHOLD, Params.h:24 (50) */
+    int min_new_feature_dist;  /* MIN_NEW_FEATURE_DIST, Params.h:43 (30) */
+} ekfvio_vio_params;
+void ekfvio_vio_default_params(ekfvio_vio_params* p);
+int ekfvio_vio_create(ekfvio_vio** out, int device, int num_sequences, int width, int height, const ekfvio_params* ekf_params,
+                      const ekfvio_klt_params* klt_params, const ekfvio_vio_params* vio_params);
+int ekfvio_vio_destroy(ekfvio_vio* v);
+/* d_frames[S][height][pitch] 8-bit frames at the working resolution (Frame::Frame's resize: ekfvio_frame_resize),
+ * d_K9[S][9] the frames' scaled K as column-major float 3x3, d_dt[S] seconds since the previous frame
+ * (ignored for the first frame).  Asynchronous on `stream`. */
+int ekfvio_vio_add_frame(ekfvio_vio* v, const uint8_t* d_frames, int pitch, const float* d_K9, const double* d_dt, void* stream);
+/* The filters (state read-out, checkpointing) and the number of frames added so far. */
+ekfvio_batch* ekfvio_vio_filters(ekfvio_vio* v);
+int ekfvio_vio_frame_count(const ekfvio_vio* v);
+long long ekfvio_vio_launch_count(const ekfvio_vio* v);
 
 /* Frame::Frame (Frame.cpp:15-21): cv::resize(img, scaled, Size(cols / inv_scale, rows / inv_scale)), default
  * INTER_LINEAR, for a batch of 8-bit images d_src[batch][src_height][src_pitch] ->
