@@ -271,6 +271,37 @@ def bench_replenish(args, rank, world, local, prev, pts):
     return res
 
 
+def bench_vio_loop(args, rank, world, local):
+    """SURVEY.md §8(f)3 — EKFVIO::addFrame on the device: one call advances S sequences by one 640x480 frame
+    (pyramid, process, KLT on <= 100 features, update, FAST replenishment).  Frames resident in HBM."""
+    import torch
+    from ekf_vio_b200 import capi, workload
+    S, T = 64, max(args.warmup + 4, 8)
+    frames = workload.vio_sequences(rank * S, 8, T, 640, 480, speed=2.0)
+    frames = np.ascontiguousarray(np.concatenate([frames] * (S // 8), axis=1))
+    K9 = np.zeros((S, 9), np.float32); K9[:, 0] = 400.0; K9[:, 4] = 400.0; K9[:, 6] = 320.0; K9[:, 7] = 240.0; K9[:, 8] = 1.0
+    loop = capi.VioLoop(S, 640, 480, device=local)
+    d_frames = torch.from_numpy(frames).cuda(); dK = torch.from_numpy(K9).cuda(); ddt = torch.full((S,), DT, dtype=torch.float64, device="cuda")
+    warm = args.warmup + 1
+    for t in range(warm):
+        loop.add_frame(d_frames[t], dK, None if t == 0 else ddt)
+    barrier(world)
+    l0 = loop.launches
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for t in range(warm, T):
+        loop.add_frame(d_frames[t], dK, ddt)
+    e1.record(); torch.cuda.synchronize()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    st = loop.filters.get_state(want_P=False)
+    res = {"metric": "sequence-frames/s through the device frame loop (640x480, NUM_FEATURES 100)", "value": sum_over_ranks(float(S), world) * (T - warm) / (ms * 1e-3),
+           "unit": "frames/s", "ms_per_frame_step": ms / (T - warm), "sequences_per_gpu": S, "gpu_launches": int(loop.launches - l0),
+           "features_per_sequence": float(st["nfeat"].mean()), "status_nonzero": int((st["status"] != 0).sum())}
+    loop.close()
+    return res
+
+
 def bench_klt(args, rank, world, local):
     import torch
     from ekf_vio_b200 import capi, workload
@@ -362,6 +393,7 @@ def bench_klt(args, rank, world, local):
     }
     trk.close()
     res["replenish"] = bench_replenish(args, rank, world, local, prev, pts)
+    res["vio_loop"] = bench_vio_loop(args, rank, world, local)
     return res
 
 
