@@ -104,6 +104,9 @@ def dist_setup(gpus: int):
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION in this image) goes away
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local
 
