@@ -63,6 +63,7 @@ class BatchView(C.Structure):
 
 FLAG_FORCE_GENERAL_PATH = 0x1
 FLAG_FRESH_DQ_CACHE = 0x2
+FLAG_LITERAL_JOSEPH = 0x4
 
 # name -> (restype, argtypes); every symbol include/ekfvio_c.h declares
 SIGNATURES = {

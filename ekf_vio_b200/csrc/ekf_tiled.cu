@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
     double* s_y = Ss + NB * NB * 64;       // NB*8
     int* s_idx = reinterpret_cast<int*>(s_y + NB * 8);   // NB*8
     __shared__ short s_inv[NW * 16];
+    __shared__ double s_v[NB * 8];         // inv(L) y (symmetric filters)
 
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m = p.m[f];
@@ -293,6 +294,11 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
     double* feat_g = p.feat + (size_t)f * nmax * 3;
     const int nb = (m + 7) >> 3;
     const int r = lane >> 2, q = lane & 3;
+    // Symmetric Sigma and R (the normal case): the Joseph form equals Sigma - Z Z' with Z = Sigma(:,idx) inv(L)',
+    // so the forward substitution is all that is needed — K = Z inv(L) and W = Sigma(:,idx) - K S are only
+    // formed for filters that are not symmetric or when the literal evaluation is requested.  K y = Z (inv(L) y):
+    // y rides through the forward substitution as row N of the strips.
+    const bool schur = p.asym[f] == 0 && !(p.flags & EKFVIO_FLAG_LITERAL_JOSEPH);
 
     {   // L and inverse tiles: straight copy from scratch
         const double* Lg = p.L + (size_t)f * (NT + NB) * 64;
@@ -318,6 +324,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
             bool ok = row < N && a < m && jb < nb;
             k0[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a]] : 0.0;
             k1[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a + 1]] : 0.0;
+            if (schur && row == N && jb < nb) { k0[rt][jb] = s_y[a]; k1[rt][jb] = s_y[a + 1]; }   // (s_y is zero beyond m)
         }
     }
     // inverse measurement map: state row -> measurement index (or -1); identity tail rows of Ss
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
     __syncthreads();
 
     CLK_MARK(4);
-    if (i0 < N) {
+    if (i0 < N + (schur ? 1 : 0)) {
 #pragma unroll
         for (int rt = 0; rt < 2; ++rt) {
             const int row = i0 + rt * 8 + r;
@@ -385,6 +392,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
         }
         CLK_MARK(5);
         // backward: K L = Z
+        if (!schur)
 #pragma unroll
         for (int jr = 0; jr < NB; ++jr) {
             const int jb = NB - 1 - jr;
@@ -416,7 +424,21 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
                 }
             }
         }
-        // sparseView (:580), mu += K y (:600), K to global
+        if (schur) {   // v = inv(L) y is row N of Z: publish it (s_y is free: y has been consumed by the gathers)
+#pragma unroll
+            for (int rt = 0; rt < 2; ++rt) {
+                if (i0 + rt * 8 + r == N) {
+#pragma unroll
+                    for (int jb = 0; jb < NB; ++jb)
+                        if (jb < nb) { s_v[jb * 8 + 2 * q] = k0[rt][jb]; s_v[jb * 8 + 2 * q + 1] = k1[rt][jb]; }
+                }
+            }
+        }
+    }
+    if (schur) __syncthreads();
+    if (i0 < N) {
+        const double* s_yv = schur ? s_v : s_y;
+        // sparseView (:580), mu += K y (:600), K (or Z) to global
 #pragma unroll
         for (int rt = 0; rt < 2; ++rt) {
             const int row = i0 + rt * 8 + r;
@@ -424,8 +446,8 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
 #pragma unroll
             for (int jb = 0; jb < NB; ++jb) {
                 if (jb < nb) {
-                    double a = prune(k0[rt][jb]), b = prune(k1[rt][jb]);
-                    dot += a * s_y[jb * 8 + 2 * q] + b * s_y[jb * 8 + 2 * q + 1];
+                    double a = schur ? k0[rt][jb] : prune(k0[rt][jb]), b = schur ? k1[rt][jb] : prune(k1[rt][jb]);   // sparseView applies to K
+                    dot += a * s_yv[jb * 8 + 2 * q] + b * s_yv[jb * 8 + 2 * q + 1];
                     if (row < ld) *reinterpret_cast<double2*>(Kf + kw_at(ld, row, jb * 8 + 2 * q)) = make_double2(a, b);
                 }
             }
@@ -436,7 +458,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
     }
     CLK_MARK(6);
     __syncthreads();   // every strip has contributed its rows of S, and K is in global memory
-    if (i0 < N) {
+    if (i0 < N && !schur) {
         // W = Sigma(:,idx) - K S with the full S
         double w0[2][NB], w1[2][NB];
 #pragma unroll
@@ -543,13 +565,16 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
     // Persistent CTA: filters f = blockIdx.x, blockIdx.x + gridDim.x, ...  The cp.async stage stream
     // runs on across the two phases of a filter and into the next filter, so the pipeline never
     // drains: while a filter's result is being stored, the first panels of the next one are in flight.
+    // schur: the gain kernel left Z = Sigma(:,idx) inv(L)' in the K panel and Sigma' = Sigma - Z Z' is one phase;
+    // otherwise (EKFVIO_FLAG_LITERAL_JOSEPH) the K and W panels go through the two phases of the Joseph form.
+    const bool schur = !(p.flags & EKFVIO_FLAG_LITERAL_JOSEPH);
     struct Meta { int f, N, m, nch, nv; const double* Pi; const double* Kf; const double* Wf; };
     auto meta = [&](int f) {
         Meta M; M.f = f;
         if (f < p.F && p.asym[f] == 0) {
             M.N = BASE + 3 * p.nfeat[f]; M.m = p.m[f];
         } else { M.N = 0; M.m = 0; }                        // nothing to do (asymmetric filters: ekf_joseph_tiled)
-        M.nch = (M.m + SKC - 1) / SKC; M.nv = 2 * M.nch;
+        M.nch = (M.m + SKC - 1) / SKC; M.nv = schur ? M.nch : 2 * M.nch;
         M.Pi = Pin + (size_t)f * ld * ld; M.Kf = p.K + (size_t)f * ld * ldK; M.Wf = p.W + (size_t)f * ld * ldK;
         return M;
     };
@@ -558,8 +583,8 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
         if (v < M.nv) {
             double* A = sms + (gs % SNST) * STAGE;
             double* B = A + A_DOUBLES;
-            const int phase = v >= M.nch, k0 = (phase ? v - M.nch : v) * SKC, m = M.m;
-            const double* Am = phase ? M.Wf : M.Kf;
+            const int phase = schur ? 1 : (v >= M.nch), k0 = ((phase && !schur) ? v - M.nch : v) * SKC, m = M.m;
+            const double* Am = (phase && !schur) ? M.Wf : M.Kf;
             for (int t = tid; t < ROWS * (SKC / 2); t += NW * 32) {   // A panel: rows of K or W
                 int row = t / (SKC / 2), seg = t % (SKC / 2);
                 double* dst = &A[row * SLDA + seg * 2];
@@ -637,7 +662,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
             const double* A = sms + (gc % SNST) * STAGE;
             const double* B = A + A_DOUBLES;
             ++gc;
-            const bool phase1 = v >= cur.nch;
+            const bool phase1 = schur || v >= cur.nch;
 #pragma unroll
             for (int kk = 0; kk < SKC / 4; ++kk) {
                 double fa0[IPW], fa1[IPW], fb0[IPW], fb1[IPW];

@@ -43,6 +43,9 @@ extern "C" {
  * (SURVEY.md §8a E1..E6).  Each fix is opt-in. */
 #define EKFVIO_FLAG_FORCE_GENERAL_PATH 0x1u /* always use the general (non-tiled) kernels */
 #define EKFVIO_FLAG_FRESH_DQ_CACHE 0x2u     /* fix E2: never reuse a dq_inv computed for another dt */
+#define EKFVIO_FLAG_LITERAL_JOSEPH 0x4u     /* evaluate (I-KH) Sigma (I-KH)' + K R K' term by term even where Sigma and R are
+                                             * symmetric; by default such filters use the algebraically identical
+                                             * Sigma - Z Z', Z = Sigma(:,idx) inv(L)', S = L L'  */
 
 typedef struct ekfvio_params {
     double default_point_depth;               /* Params.h:83   DEFAULT_POINT_DEPTH = 0.5 */
