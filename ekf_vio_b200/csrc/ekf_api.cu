@@ -193,7 +193,7 @@ int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, c
         b->timer.begin(3, st);
         CU(launch_gain_tiled(1, pp, b->d_P[b->cur], d_z, d_R, d_pass, st));
         b->timer.end(st);
-        b->launches += 1;
+        b->launches += (b->prm.flags & EKFVIO_FLAG_LITERAL_JOSEPH) ? 1 : 2;   // forward-only kernel + full solve (each skips the other's filters)
     } else {
         if (!b->d_S && gain_general_smem_doubles(b->mmax) == 0) {
             size_t bytes = (size_t)b->F * ((size_t)b->mmax * b->mmax + b->mmax) * sizeof(double);

@@ -256,6 +256,32 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
 
     chol_tiles<NWC>(Ls, Li, nb, &s_bad);
     if (tid == 0 && s_bad) atomicOr(&p.status[f], 1);
+    __syncthreads();
+    // Symmetric filters (ekf_fwd_tiled): v = inv(L) y replaces y, so that K y = Z v needs no K.  Block forward
+    // substitution by one warp: t = y_jb - sum_k L(jb,k) v_k, v_jb = inv(L_jb,jb) t (explicit inverse tiles).
+    if (warp == 0 && p.asym[f] == 0 && !(p.flags & EKFVIO_FLAG_LITERAL_JOSEPH)) {
+        __shared__ double s_vv[NB * 8], s_t[8];
+        const int r = lane >> 2, q = lane & 3;
+        for (int jb = 0; jb < nb; ++jb) {
+            double acc = 0.0;
+            for (int kb = 0; kb < jb; ++kb) {
+                const double* T = Ls + tile_of(jb, kb);
+                acc += T[tsw(r, 2 * q)] * s_vv[kb * 8 + 2 * q] + T[tsw(r, 2 * q + 1)] * s_vv[kb * 8 + 2 * q + 1];
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            const int a = jb * 8 + r;
+            if (q == 0) s_t[r] = (a < m ? y_g[a] : 0.0) - acc;
+            __syncwarp();
+            const double* I8 = Li + jb * 64;
+            double vv = I8[tsw(r, 2 * q)] * s_t[2 * q] + I8[tsw(r, 2 * q + 1)] * s_t[2 * q + 1];
+            vv += __shfl_xor_sync(0xffffffffu, vv, 1);
+            vv += __shfl_xor_sync(0xffffffffu, vv, 2);
+            if (q == 0) s_vv[a] = vv;
+            __syncwarp();
+        }
+        for (int a = lane; a < m; a += 32) y_g[a] = s_vv[a];
+    }
     // factor and inverse tiles to global scratch (same swizzled layout)
     double* Lg = p.L + (size_t)f * (NT + NB) * 64;
     const int used = nb * (nb + 1) / 2 * 64;
@@ -276,11 +302,11 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
     double* s_y = Ss + NB * NB * 64;       // NB*8
     int* s_idx = reinterpret_cast<int*>(s_y + NB * 8);   // NB*8
     __shared__ short s_inv[NW * 16];
-    __shared__ double s_v[NB * 8];         // inv(L) y (symmetric filters)
 
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m = p.m[f];
     if (m == 0) return;
+    if (p.asym[f] == 0 && !(p.flags & EKFVIO_FLAG_LITERAL_JOSEPH)) return;   // symmetric filters: ekf_fwd_tiled
 #ifdef EKFVIO_PROFILE_CLOCKS
     long long t_prev = clock64();
 #endif
@@ -294,11 +320,6 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
     double* feat_g = p.feat + (size_t)f * nmax * 3;
     const int nb = (m + 7) >> 3;
     const int r = lane >> 2, q = lane & 3;
-    // Symmetric Sigma and R (the normal case): the Joseph form equals Sigma - Z Z' with Z = Sigma(:,idx) inv(L)',
-    // so the forward substitution is all that is needed — K = Z inv(L) and W = Sigma(:,idx) - K S are only
-    // formed for filters that are not symmetric or when the literal evaluation is requested.  K y = Z (inv(L) y):
-    // y rides through the forward substitution as row N of the strips.
-    const bool schur = p.asym[f] == 0 && !(p.flags & EKFVIO_FLAG_LITERAL_JOSEPH);
 
     {   // L and inverse tiles: straight copy from scratch
         const double* Lg = p.L + (size_t)f * (NT + NB) * 64;
@@ -324,7 +345,6 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
             bool ok = row < N && a < m && jb < nb;
             k0[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a]] : 0.0;
             k1[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a + 1]] : 0.0;
-            if (schur && row == N && jb < nb) { k0[rt][jb] = s_y[a]; k1[rt][jb] = s_y[a + 1]; }   // (s_y is zero beyond m)
         }
     }
     // inverse measurement map: state row -> measurement index (or -1); identity tail rows of Ss
@@ -339,7 +359,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
     __syncthreads();
 
     CLK_MARK(4);
-    if (i0 < N + (schur ? 1 : 0)) {
+    if (i0 < N) {
 #pragma unroll
         for (int rt = 0; rt < 2; ++rt) {
             const int row = i0 + rt * 8 + r;
@@ -392,7 +412,6 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
         }
         CLK_MARK(5);
         // backward: K L = Z
-        if (!schur)
 #pragma unroll
         for (int jr = 0; jr < NB; ++jr) {
             const int jb = NB - 1 - jr;
@@ -424,21 +443,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
                 }
             }
         }
-        if (schur) {   // v = inv(L) y is row N of Z: publish it (s_y is free: y has been consumed by the gathers)
-#pragma unroll
-            for (int rt = 0; rt < 2; ++rt) {
-                if (i0 + rt * 8 + r == N) {
-#pragma unroll
-                    for (int jb = 0; jb < NB; ++jb)
-                        if (jb < nb) { s_v[jb * 8 + 2 * q] = k0[rt][jb]; s_v[jb * 8 + 2 * q + 1] = k1[rt][jb]; }
-                }
-            }
-        }
-    }
-    if (schur) __syncthreads();
-    if (i0 < N) {
-        const double* s_yv = schur ? s_v : s_y;
-        // sparseView (:580), mu += K y (:600), K (or Z) to global
+        // sparseView (:580), mu += K y (:600), K to global
 #pragma unroll
         for (int rt = 0; rt < 2; ++rt) {
             const int row = i0 + rt * 8 + r;
@@ -446,8 +451,8 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
 #pragma unroll
             for (int jb = 0; jb < NB; ++jb) {
                 if (jb < nb) {
-                    double a = schur ? k0[rt][jb] : prune(k0[rt][jb]), b = schur ? k1[rt][jb] : prune(k1[rt][jb]);   // sparseView applies to K
-                    dot += a * s_yv[jb * 8 + 2 * q] + b * s_yv[jb * 8 + 2 * q + 1];
+                    double a = prune(k0[rt][jb]), b = prune(k1[rt][jb]);
+                    dot += a * s_y[jb * 8 + 2 * q] + b * s_y[jb * 8 + 2 * q + 1];
                     if (row < ld) *reinterpret_cast<double2*>(Kf + kw_at(ld, row, jb * 8 + 2 * q)) = make_double2(a, b);
                 }
             }
@@ -458,7 +463,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
     }
     CLK_MARK(6);
     __syncthreads();   // every strip has contributed its rows of S, and K is in global memory
-    if (i0 < N && !schur) {
+    if (i0 < N) {
         // W = Sigma(:,idx) - K S with the full S
         double w0[2][NB], w1[2][NB];
 #pragma unroll
@@ -517,6 +522,119 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
     }
 }
 
+// Symmetric Sigma and R (the normal case): the Joseph form (I-KH) Sigma (I-KH)' + K R K' equals
+// Sigma - Z Z' with Z = Sigma(:,idx) inv(L)', S = L L', and K y = Z (inv(L) y).  Only the forward
+// substitution is needed; neither K nor W = Sigma(:,idx) - K S is formed.  Two CTAs per filter (six
+// 16-row strips each, strips in registers as in ekf_solve_tiled) and two CTAs per SM, so that one CTA's
+// factor copy and gathers overlap the other's substitution.  v = inv(L) y comes from ekf_chol_tiled (in p.y).
+template <int NW, int NB>
+__global__ void __launch_bounds__(NW * 32, 2) ekf_fwd_tiled(EkfPtrs p, const double* __restrict__ Pin) {
+    extern __shared__ __align__(16) double smf[];
+    constexpr int NT = NB * (NB + 1) / 2;
+    double* Ls = smf;                      // NT tiles
+    double* Li = Ls + NT * 64;             // NB inverse diagonal tiles
+    double* s_v = Li + NB * 64;            // NB*8: inv(L) y
+    int* s_idx = reinterpret_cast<int*>(s_v + NB * 8);   // NB*8
+
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = p.m[f];
+    if (m == 0 || p.asym[f] != 0) return;  // asymmetric filters: ekf_solve_tiled
+    const int n = p.nfeat[f], N = BASE + 3 * n;
+    const int ld = p.ldP, ldK = p.ldK, nmax = p.nmax;
+    const double* Pi = Pin + (size_t)f * ld * ld;
+    double* Zf = p.K + (size_t)f * ld * ldK;
+    double* mu_g = p.mu + (size_t)f * BASE;
+    double* feat_g = p.feat + (size_t)f * nmax * 3;
+    const int nb = (m + 7) >> 3;
+    const int r = lane >> 2, q = lane & 3;
+    {
+        const double* Lg = p.L + (size_t)f * (NT + NB) * 64;
+        const int used = nb * (nb + 1) / 2 * 64;
+        for (int e = tid * 2; e < used; e += NW * 64) cp_async16(Ls + e, Lg + e);
+        for (int e = tid * 2; e < nb * 64; e += NW * 64) cp_async16(Li + e, Lg + NT * 64 + e);
+        cp_async_commit();
+        const int* idx_g = p.idx + (size_t)f * p.mmax;
+        const double* v_g = p.y + (size_t)f * p.mmax;
+        for (int a = tid; a < NB * 8; a += NW * 32) { s_idx[a] = a < m ? idx_g[a] : 0; s_v[a] = a < m ? v_g[a] : 0.0; }
+    }
+    __syncthreads();
+    const int i0 = (blockIdx.y * NW + warp) * 16;
+    double k0[2][NB], k1[2][NB];
+#pragma unroll
+    for (int rt = 0; rt < 2; ++rt) {
+        const int row = i0 + rt * 8 + r;
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) {
+            int a = jb * 8 + 2 * q;
+            bool ok = row < N && a < m && jb < nb;
+            k0[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a]] : 0.0;
+            k1[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a + 1]] : 0.0;
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    if (i0 < N) {
+        // forward: Z L' = C
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) {
+            if (jb < nb) {
+                const double* I8 = Li + jb * 64;
+                const double b0 = I8[tsw(r, q)], b1 = I8[tsw(r, 4 + q)];   // B[k][col] = inv(L)[col][k]
+                double za[2][2];
+#pragma unroll
+                for (int rt = 0; rt < 2; ++rt) {
+                    double a0, a1;
+                    cfrag_to_afrag(k0[rt][jb], k1[rt][jb], lane, a0, a1);
+                    double t0 = 0.0, t1 = 0.0;
+                    dmma884(t0, t1, a0, b0);
+                    dmma884(t0, t1, a1, b1);
+                    k0[rt][jb] = t0; k1[rt][jb] = t1;
+                    cfrag_to_afrag(t0, t1, lane, za[rt][0], za[rt][1]);
+                }
+#pragma unroll
+                for (int j2 = 0; j2 < NB; ++j2) {
+                    if (j2 > jb && j2 < nb) {
+                        const double* T = Ls + tile_of(j2, jb);          // B[k][col] = L(j2,jb)[col][k]
+                        const double l0 = T[tsw(r, q)], l1 = T[tsw(r, 4 + q)];
+#pragma unroll
+                        for (int rt = 0; rt < 2; ++rt) {
+                            dmma884(k0[rt][j2], k1[rt][j2], -za[rt][0], l0);
+                            dmma884(k0[rt][j2], k1[rt][j2], -za[rt][1], l1);
+                        }
+                    }
+                }
+            }
+        }
+        // mu += K y = Z v (:600); Z to the gain panel for the covariance kernel
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt) {
+            const int row = i0 + rt * 8 + r;
+            double dot = 0.0;
+#pragma unroll
+            for (int jb = 0; jb < NB; ++jb) {
+                if (jb < nb) {
+                    const double a = k0[rt][jb], b = k1[rt][jb];
+                    dot += a * s_v[jb * 8 + 2 * q] + b * s_v[jb * 8 + 2 * q + 1];
+                    if (row < ld) *reinterpret_cast<double2*>(Zf + kw_at(ld, row, jb * 8 + 2 * q)) = make_double2(a, b);
+                }
+            }
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            if (q == 0 && row < N) { if (row < BASE) mu_g[row] += dot; else feat_g[row - BASE] += dot; }
+        }
+    }
+    if (blockIdx.y == 0) {                 // the base rows (quaternion) all live in the first CTA's strips
+        __syncthreads();
+        if (tid == 0) {  // renormalise the quaternion (:605-609) and flag non-finite states
+            double qn = sqrt(mu_g[3] * mu_g[3] + mu_g[4] * mu_g[4] + mu_g[5] * mu_g[5] + mu_g[6] * mu_g[6]);
+            mu_g[3] /= qn; mu_g[4] /= qn; mu_g[5] /= qn; mu_g[6] /= qn;
+            bool fin = true;
+            for (int i = 0; i < BASE; ++i) fin = fin && isfinite(mu_g[i]);
+            if (!fin) atomicOr(&p.status[f], 2);
+        }
+    }
+}
+
 template <int NW, int NB>
 cudaError_t launch_gain_tiled_t(int which, const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, cudaStream_t st) {
     static bool configured = false;
@@ -530,7 +648,20 @@ cudaError_t launch_gain_tiled_t(int which, const EkfPtrs& p, const double* Pin, 
         configured = true;
     }
     if (which == 0) ekf_chol_tiled<NB><<<p.F, 128, sm_c, st>>>(p, Pin, z, R, pass);
-    else ekf_solve_tiled<NW, NB><<<p.F, NW * 32, sm_s, st>>>(p, Pin, R);
+    else {
+        // symmetric filters: forward substitution only, two CTAs per filter; the others (and all of them under
+        // EKFVIO_FLAG_LITERAL_JOSEPH): the full solve.  Each kernel skips the filters of the other.
+        constexpr int NWF = (NW + 1) / 2;
+        const size_t sm_f = (size_t)((NT + NB) * 64 + NB * 8) * sizeof(double) + NB * 8 * sizeof(int);
+        static bool configured_f = false;
+        if (!configured_f) {
+            cudaError_t e = cudaFuncSetAttribute(ekf_fwd_tiled<NWF, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
+            if (e != cudaSuccess) return e;
+            configured_f = true;
+        }
+        if (!(p.flags & EKFVIO_FLAG_LITERAL_JOSEPH)) ekf_fwd_tiled<NWF, NB><<<dim3(p.F, 2), NWF * 32, sm_f, st>>>(p, Pin);
+        ekf_solve_tiled<NW, NB><<<p.F, NW * 32, sm_s, st>>>(p, Pin, R);
+    }
     return cudaGetLastError();
 }
 
@@ -598,7 +729,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
                     if (k0 + k < m && seg * 2 < ld) cp_async16(dst, M.Pi + (size_t)sidx[k0 + k] * ld + seg * 2);
                     else { dst[0] = 0.0; dst[1] = 0.0; }
                 }
-            } else {                                                  // B panel: rows of K
+            } else if (!schur) {                                      // B panel: rows of K (Z Z': the A panel serves as both operands)
                 for (int t = tid; t < ROWS * (SKC / 2); t += NW * 32) {
                     int row = t / (SKC / 2), seg = t % (SKC / 2);
                     double* dst = &B[row * SLDA + seg * 2];
@@ -660,7 +791,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
             else { issue(nxt, issued_next, s_idx[ib ^ 1]); ++issued_next; }
 #endif
             const double* A = sms + (gc % SNST) * STAGE;
-            const double* B = A + A_DOUBLES;
+            const double* B = schur ? A : A + A_DOUBLES;
             ++gc;
             const bool phase1 = schur || v >= cur.nch;
 #pragma unroll
