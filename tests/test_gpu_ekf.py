@@ -46,7 +46,9 @@ def torch_inputs(z, R, passed):
             torch.from_numpy(np.ascontiguousarray(passed, np.uint8)).cuda())
 
 
-PATHS = [pytest.param(0, id="default"), pytest.param(1, id="general")]
+# default: symmetric filters go through Sigma - Z Z' (forward substitution only); literal: the Joseph form term by
+# term on the tiled kernels (EKFVIO_FLAG_LITERAL_JOSEPH); general: the kernels that assume nothing.
+PATHS = [pytest.param(0, id="default"), pytest.param(4, id="literal-joseph"), pytest.param(1, id="general")]
 
 
 @pytest.mark.parametrize("flags", PATHS)
