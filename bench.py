@@ -118,9 +118,6 @@ def dist_setup(gpus: int):
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION in this image) goes away
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local
 
@@ -485,7 +482,7 @@ def cpu_baseline_klt(pairs: int = 8, reps: int = 3):
             "replenish_frames_per_s": fast_fps}
 
 
-def run_reference(args):
+def run_reference(args, result_out=sys.stdout):
     """--impl reference: the reference's CPU path for the same metric/config, on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -508,10 +505,20 @@ def run_reference(args):
         "klt": {"metric": "KLT features tracked/s at 640x480", "value": kl["value"], "unit": "features/s", "cpu_baseline": kl},
     }
     del cb
-    print(json.dumps(line))
+    print(json.dumps(line), file=result_out, flush=True)
+
+
+def claim_stdout():
+    """stdout must carry exactly one JSON line, but libraries write to fd 1 from C (NCCL's version banner at
+    communicator creation): everything is sent to stderr and the result line goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
 
 
 def main():
+    result_out = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -525,7 +532,7 @@ def main():
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, result_out)
         return
 
     import torch
@@ -580,7 +587,7 @@ def main():
             if not args.skip_cpu:
                 klt["cpu_baseline"] = cpu_baseline_klt()
             line["klt"] = klt
-        print(json.dumps(line))
+        print(json.dumps(line), file=result_out, flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
