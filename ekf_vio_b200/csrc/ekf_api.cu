@@ -74,9 +74,9 @@ int ekfvio_batch_create(ekfvio_batch** out, int device, int num_filters, int max
     b->device = device;
     b->F = num_filters; b->nmax = max_features;
     b->Nmax = BASE + 3 * max_features;
-    b->ldP = (b->Nmax + 7) / 8 * 8;
     b->mmax = 2 * max_features > 0 ? 2 * max_features : 2;
     b->large = b->Nmax > 176 || b->mmax > 104;                    // beyond the register-resident tiled path
+    b->ldP = (b->Nmax + (b->large ? 1 : 0) + 7) / 8 * 8;          // (large path: one spare panel row carries y through the forward substitution)
     b->ldK = b->large ? (b->mmax + 63) / 64 * 64 : (b->mmax + 15) / 16 * 16;    // K / W panels are chunk-major in 16-column chunks (kw_at)
     if (params) b->prm = *params; else ekfvio_default_params(&b->prm);
     size_t F = b->F, nm = b->nmax > 0 ? b->nmax : 1;
@@ -179,7 +179,7 @@ int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, c
     if (b->large && !general) {   // blocked multi-CTA-per-filter path for large states
         LargePtrs lp;
         lp.S = b->d_LS; lp.L = b->d_LL; lp.T = b->d_LT;
-        lp.mp = (b->mmax + 63) / 64 * 64; lp.nblk = lp.mp / 64; lp.nrt_max = (b->Nmax + 63) / 64;
+        lp.mp = (b->mmax + 63) / 64 * 64; lp.nblk = lp.mp / 64; lp.nrt_max = (b->Nmax + 1 + 63) / 64;
         CU(launch_update_large(pp, lp, b->d_P[b->cur], b->d_P[b->cur ^ 1], d_z, d_R, d_pass, st, &b->launches, &b->timer));
         CU(cudaEventRecord(b->ev_state, st)); CU(cudaEventRecord(b->ev_inputs_free, st));
         b->state_ev_valid = b->inputs_ev_valid = true;

@@ -27,6 +27,11 @@ constexpr int BLK = 64;             // column block
 constexpr int NB8 = 8;              // 8x8 tiles per block side
 constexpr int NT8 = NB8 * (NB8 + 1) / 2;
 
+// Symmetric filters take the reduced update Sigma' = Sigma - Z Z', Z = Sigma(:,idx) inv(L)' (see ekf_tiled.cu /
+// DESIGN.md section 2): y rides through the forward substitution as panel row N (v = inv(L) y), the backward
+// substitution, W and the second phase of the covariance update are skipped.
+__device__ __forceinline__ bool reduced_update(const EkfPtrs& p, int f) { return p.asym[f] == 0 && !(p.flags & EKFVIO_FLAG_LITERAL_JOSEPH); }
+
 // ---- measurement map + residual (one warp per filter) ---------------------------------------
 __global__ void ekf_large_idx(EkfPtrs p, const double* __restrict__ z, const double* __restrict__ Rin, const uint8_t* __restrict__ pass) {
     const int f = blockIdx.x, lane = threadIdx.x;
@@ -110,12 +115,17 @@ __global__ void __launch_bounds__(256) ekf_large_gather(EkfPtrs p, LargePtrs lp,
             __syncwarp();
         }
     }
-    const int Ne = ((N + BLK - 1) / BLK) * BLK < ld ? ((N + BLK - 1) / BLK) * BLK : ld;
+    const bool red = reduced_update(p, f);
+    const double* y = p.y + (size_t)f * p.mmax;
+    const int Nr = N + (red ? 1 : 0);                            // reduced update: row N of the panel is y
+    const int Ne = ((Nr + BLK - 1) / BLK) * BLK < ld ? ((Nr + BLK - 1) / BLK) * BLK : ld;
     for (int i = part; i < Ne; i += nparts) {                    // C rows (zero beyond N / m)
         for (int b = tid; b < me; b += 256) {
             double v = (i < N && b < m) ? Pi[(size_t)i * ld + idx[b]] : 0.0;
+            if (red && i == N && b < m) v = y[b];
             size_t o = kw_at(ld, i, b);
-            Kf[o] = v; Wf[o] = v;
+            Kf[o] = v;
+            if (!red) Wf[o] = v;
         }
     }
 }
@@ -165,8 +175,9 @@ __global__ void __launch_bounds__(256) ekf_large_trsm(EkfPtrs p, LargePtrs lp, i
     if (jb * BLK >= m) return;
     const int N = BASE + 3 * p.nfeat[f], ld = p.ldP, mp = lp.mp;
     const int me = ((m + BLK - 1) / BLK) * BLK;
+    if (MODE == 2 && reduced_update(p, f)) return;
     const int row_begin = MODE == 0 ? (jb + 1) * BLK : 0;
-    const int row_end = MODE == 0 ? me : N;
+    const int row_end = MODE == 0 ? me : (MODE == 1 && reduced_update(p, f) ? N + 1 : N);
     const int i0 = row_begin + (blockIdx.x * 8 + warp) * 16;
     if (row_begin + blockIdx.x * 128 >= row_end) return;
     const double* Tg = lp.T + ((size_t)f * lp.nblk + jb) * (NT8 + NB8) * 64;
@@ -280,15 +291,19 @@ __global__ void __launch_bounds__(256) ekf_large_finalize(EkfPtrs p) {
     const int nbase_rounds = part == 0 ? (BASE + 7) / 8 : 0;
     const int nfrows = N - BASE;
     const int nfeat_rounds = (nfrows + 8 * nparts - 1) / (8 * nparts);
+    const bool red = reduced_update(p, f);                       // then the panel holds Z and its row N is v = inv(L) y
     for (int r = 0; r < nbase_rounds + nfeat_rounds; ++r) {
         const int i = r < nbase_rounds ? r * 8 + warp : BASE + ((r - nbase_rounds) * nparts + part) * 8 + warp;
         if (r < nbase_rounds ? i >= BASE : i >= N) continue;
         double dot = 0.0;
         for (int k = lane; k < m; k += 32) {
             size_t o = kw_at(ld, i, k);
-            double v = prune(Kf[o]);
-            Kf[o] = v;
-            dot += v * y[k];
+            if (red) dot += Kf[o] * Kf[kw_at(ld, N, k)];
+            else {
+                double v = prune(Kf[o]);
+                Kf[o] = v;
+                dot += v * y[k];
+            }
         }
         for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
         if (lane == 0) { if (i < BASE) mu_g[i] += dot; else feat_g[i - BASE] += dot; }
@@ -323,6 +338,8 @@ __global__ void __launch_bounds__(256) ekf_large_gemm(EkfPtrs p, LargePtrs lp, c
     const int N = BASE + 3 * p.nfeat[f], ld = p.ldP, mp = lp.mp;
     const int nblk = (m + BLK - 1) / BLK, nrt = (N + BLK - 1) / BLK;
     if (op != OP_JOSEPH && (m == 0 || jb >= nblk)) return;
+    const bool red = reduced_update(p, f);
+    if (red && (op == OP_BWDUPD || op == OP_W)) return;
     if (op == OP_JOSEPH && sym >= 0 && (p.asym[f] != 0) != (sym == 0)) return;   // sym=1: symmetric filters, sym=0: the others, sym=-1: all
     const double* Lg = lp.L + (size_t)f * mp * mp;
     const double* Sg = lp.S + (size_t)f * mp * mp;
@@ -348,7 +365,7 @@ __global__ void __launch_bounds__(256) ekf_large_gemm(EkfPtrs p, LargePtrs lp, c
         C0 = Lg; D = const_cast<double*>(Lg); cmode = 0; cld = mp; ci0 = ti * BLK; cj0 = tj * BLK; row_lim = nblk * BLK; col_lim = nblk * BLK;
     } else if (op == OP_FWDUPD || op == OP_BWDUPD) {   // K(:,j') -= Z(:,jb) L(j',jb)'  |  Z(:,j') -= K(:,jb) L(jb,j')
         ti = blockIdx.x; tj = op == OP_FWDUPD ? jb + 1 + blockIdx.y : blockIdx.y;
-        if (ti >= nrt || (op == OP_FWDUPD ? tj >= nblk : tj >= jb)) return;
+        if (ti >= (N + (red ? 1 : 0) + BLK - 1) / BLK || (op == OP_FWDUPD ? tj >= nblk : tj >= jb)) return;   // (reduced update: row N carries y)
         A[0] = {Kf, 1, ld, ti * BLK, jb * BLK, nullptr};
         if (op == OP_FWDUPD) B[0] = {Lg, 0, mp, tj * BLK, jb * BLK, nullptr};
         else B[0] = {Lg, 2, mp, tj * BLK, jb * BLK, nullptr};
@@ -376,6 +393,7 @@ __global__ void __launch_bounds__(256) ekf_large_gemm(EkfPtrs p, LargePtrs lp, c
         nphase = 2; Kd[0] = Kd[1] = ((m + GKC - 1) / GKC) * GKC;
         A[0] = {Kf, 1, ld, ti * BLK, 0, nullptr}; B[0] = {Pi, 2, ld, tj * BLK, 0, idx};
         A[1] = {Wf, 1, ld, ti * BLK, 0, nullptr}; B[1] = {Kf, 1, ld, tj * BLK, 0, nullptr};
+        if (red) { nphase = 1; B[0] = {Kf, 1, ld, tj * BLK, 0, nullptr}; }          // Sigma - Z Z'
         C0 = Pi; D = Po; cmode = 0; cld = ld; ci0 = ti * BLK; cj0 = tj * BLK; row_lim = N; col_lim = N;
     }
 
@@ -518,7 +536,7 @@ cudaError_t launch_update_large(const EkfPtrs& p, const LargePtrs& lp, const dou
         }
     }
     mark(mark_ctx, 3, st);
-    const int rowgrp = (p.Nmax + 127) / 128;
+    const int rowgrp = (p.Nmax + 1 + 127) / 128;                 // + the y row of the reduced update
     for (int jb = 0; jb < nblk; ++jb) {
         ekf_large_trsm<1><<<dim3(rowgrp, F), 256, 0, st>>>(p, lp, jb); ++n;
         if (jb + 1 < nblk) { ekf_large_gemm<<<dim3(nrt, nblk - jb - 1, F), 256, sm, st>>>(p, lp, nullptr, nullptr, OP_FWDUPD, jb, 0); ++n; }

@@ -300,13 +300,16 @@ def test_capacities_of_every_alignment(cuda, nmax):
         assert_close(gpu_state(b, 1), orc2.state(), what=f"nmax={nmax} filter 1 step {s}")
 
 
-@pytest.mark.parametrize("n,frac,asym", [(60, 1.0, False), (64, 0.6, True), (150, 0.8, False)])
-def test_large_state_blocked_path(cuda, n, frac, asym):
-    """n > 51 takes the blocked multi-CTA path (ekf_large.cu): 64-wide column blocks, ragged m, asymmetric R."""
+@pytest.mark.parametrize("flags", [pytest.param(0, id="default"), pytest.param(4, id="literal-joseph")])
+@pytest.mark.parametrize("n,frac,asym", [(60, 1.0, False), (64, 0.6, True), (150, 0.8, False), (78, 1.0, False), (54, 0.7, False)])
+def test_large_state_blocked_path(cuda, n, frac, asym, flags):
+    """n > 51 takes the blocked multi-CTA path (ekf_large.cu): 64-wide column blocks, ragged m, asymmetric R;
+    n = 78 (N = 256, a multiple of the tile) and n = 54 (N = 184, a multiple of the row alignment) put the
+    reduced update's y row on a tile / alignment boundary."""
     rng = np.random.default_rng(n)
     uv = rng.uniform(-0.9, 0.9, (n, 2))
     orc = O.OracleFilter(); orc.add_features(uv)
-    b = make_batch(2, n)
+    b = make_batch(2, n, flags)
     b.add_features_h(np.array([n, n], np.int32), np.stack([uv, uv]))
     mu = orc.state()["mu"]; mu[7:10] = [0.15, -0.1, 0.05]; mu[10:13] = [0.03, 0.07, -0.04]
     st = orc.state(); orc.set_state(mu=mu, feat=st["feat"], Pm=st["P"])
