@@ -282,7 +282,7 @@ __device__ __forceinline__ void seg_taps(const uint8_t* Jt, int JS, int r, int s
 
 // LKTrackerInvoker for every level, one warp per point.  The win x win patch is cut into row
 // segments of 7 pixels (8 slots each); a lane owns segments lane, lane + 32, ...  Per-warp shared memory:
-//   Cp[nseg*8] int32: 256 - 512 * (patch intensity), the rounding constant and the patch value folded
+//   Cp[2][nseg*4] int32 (slots 0-3 of every segment, then slots 4-7: consecutive lanes read consecutive 16-byte vectors): 256 - 512 * (patch intensity), the rounding constant and the patch value folded
 //                     into the accumulator the IDP2A chain starts from, so diff = chain >> 9;
 //   dI[nseg*8] short2 (Ix, Iy of the patch; zero in unused slots),
 //   Dt[(win+1)^2] short2 (staged derivative tile), Jt[(win+1) x stride] u8 (staged I or J tile).
@@ -391,10 +391,10 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
                     } else { cw[k] = 0; dw[k] = 0u; }
                 }
                 cw[7] = 0; dw[7] = 0u;
-                *reinterpret_cast<int4*>(Cp + sI * 8) = make_int4(cw[0], cw[1], cw[2], cw[3]);
-                *reinterpret_cast<int4*>(Cp + sI * 8 + 4) = make_int4(cw[4], cw[5], cw[6], cw[7]);
-                *reinterpret_cast<uint4*>(dI + sI * 8) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
-                *reinterpret_cast<uint4*>(dI + sI * 8 + 4) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+                *reinterpret_cast<int4*>(Cp + sI * 4) = make_int4(cw[0], cw[1], cw[2], cw[3]);
+                *reinterpret_cast<int4*>(Cp + (nseg + sI) * 4) = make_int4(cw[4], cw[5], cw[6], cw[7]);
+                *reinterpret_cast<uint4*>(dI + sI * 4) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+                *reinterpret_cast<uint4*>(dI + (nseg + sI) * 4) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
                 r += qstep; sg += rstep;
                 if (sg >= SPR) { sg -= SPR; ++r; }
             }
@@ -427,8 +427,8 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
             {
                 const unsigned wt = ((unsigned)w00 & 0xffffu) | ((unsigned)w01 << 16), wb = ((unsigned)w10 & 0xffffu) | ((unsigned)w11 << 16);
                 for (int sI = lane, r = r_first, sg = sg_first; sI < nseg; sI += 32) {
-                    const int4 c0 = *reinterpret_cast<const int4*>(Cp + sI * 8), c1 = *reinterpret_cast<const int4*>(Cp + sI * 8 + 4);
-                    const uint4 d0 = *reinterpret_cast<const uint4*>(dI + sI * 8), d1 = *reinterpret_cast<const uint4*>(dI + sI * 8 + 4);
+                    const int4 c0 = *reinterpret_cast<const int4*>(Cp + sI * 4), c1 = *reinterpret_cast<const int4*>(Cp + (nseg + sI) * 4);
+                    const uint4 d0 = *reinterpret_cast<const uint4*>(dI + sI * 4), d1 = *reinterpret_cast<const uint4*>(dI + (nseg + sI) * 4);
                     const int c[SEG] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z};
                     const unsigned dw[SEG] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z};
                     int v[SEG];
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
                 {
                     const unsigned wt = ((unsigned)w00 & 0xffffu) | ((unsigned)w01 << 16), wb = ((unsigned)w10 & 0xffffu) | ((unsigned)w11 << 16);
                     for (int sI = lane, r = r_first, sg = sg_first; sI < nseg; sI += 32) {
-                        const int4 c0 = *reinterpret_cast<const int4*>(Cp + sI * 8), c1 = *reinterpret_cast<const int4*>(Cp + sI * 8 + 4);
+                        const int4 c0 = *reinterpret_cast<const int4*>(Cp + sI * 4), c1 = *reinterpret_cast<const int4*>(Cp + (nseg + sI) * 4);
                         const int c[SEG] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z};
                         int v[SEG];
                         seg_taps(Jt, JS, r, sg, wt, wb, c, v);
