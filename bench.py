@@ -290,13 +290,14 @@ def bench_vio_loop(args, rank, world, local):
     (pyramid, process, KLT on <= 100 features, update, FAST replenishment).  Frames resident in HBM."""
     import torch
     from ekf_vio_b200 import capi, workload
-    S, T = 64, max(args.warmup + 4, 8)
+    S = 64
+    warm = max(args.warmup + 1, 5)            # frames 0-4: eager frames and the two graph captures (one per pyramid-slot parity)
+    T = warm + 6
     frames = workload.vio_sequences(rank * S, 8, T, 640, 480, speed=2.0)
     frames = np.ascontiguousarray(np.concatenate([frames] * (S // 8), axis=1))
     K9 = np.zeros((S, 9), np.float32); K9[:, 0] = 400.0; K9[:, 4] = 400.0; K9[:, 6] = 320.0; K9[:, 7] = 240.0; K9[:, 8] = 1.0
     loop = capi.VioLoop(S, 640, 480, device=local)
     d_frames = torch.from_numpy(frames).cuda(); dK = torch.from_numpy(K9).cuda(); ddt = torch.full((S,), DT, dtype=torch.float64, device="cuda")
-    warm = args.warmup + 1
     for t in range(warm):
         loop.add_frame(d_frames[t], dK, None if t == 0 else ddt)
     barrier(world)

@@ -36,6 +36,13 @@ static EkfPtrs ptrs(const ekfvio_batch* b) {
     return p;
 }
 
+// Event records that order the private copy stream must not become part of a caller's stream capture
+// (the frame loop replays its enqueue sequence as a CUDA graph): while capturing, fall back to plain stream order.
+static bool stream_is_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus s = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(st, &s) == cudaSuccess && s != cudaStreamCaptureStatusNone;
+}
+
 extern "C" {
 
 const char* ekfvio_last_error(void) { return ekfvio::g_last_error.c_str(); }
@@ -152,8 +159,8 @@ int ekfvio_batch_process(ekfvio_batch* b, const double* d_dt, void* stream) {
     b->timer.begin(0, (cudaStream_t)stream);
     CU(launch_process_general(ptrs(b), b->d_P[b->cur], b->d_P[b->cur ^ 1], d_dt, 0, nullptr, (cudaStream_t)stream, &b->launches));
     b->timer.end((cudaStream_t)stream);
-    CU(cudaEventRecord(b->ev_state, (cudaStream_t)stream));
-    b->state_ev_valid = true;
+    if (stream_is_capturing((cudaStream_t)stream)) b->state_ev_valid = false;
+    else { CU(cudaEventRecord(b->ev_state, (cudaStream_t)stream)); b->state_ev_valid = true; }
     b->cur ^= 1;
     return 0;
 }
@@ -181,8 +188,8 @@ int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, c
         lp.S = b->d_LS; lp.L = b->d_LL; lp.T = b->d_LT;
         lp.mp = (b->mmax + 63) / 64 * 64; lp.nblk = lp.mp / 64; lp.nrt_max = (b->Nmax + 1 + 63) / 64;
         CU(launch_update_large(pp, lp, b->d_P[b->cur], b->d_P[b->cur ^ 1], d_z, d_R, d_pass, st, &b->launches, &b->timer));
-        CU(cudaEventRecord(b->ev_state, st)); CU(cudaEventRecord(b->ev_inputs_free, st));
-        b->state_ev_valid = b->inputs_ev_valid = true;
+        if (stream_is_capturing(st)) b->state_ev_valid = b->inputs_ev_valid = false;
+        else { CU(cudaEventRecord(b->ev_state, st)); CU(cudaEventRecord(b->ev_inputs_free, st)); b->state_ev_valid = b->inputs_ev_valid = true; }
         b->cur ^= 1;
         return 0;
     }
@@ -205,8 +212,8 @@ int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, c
     }
     // the gain kernels have consumed z / R / pass and written the new state: the next upload and the
     // state download may proceed while the covariance update runs
-    CU(cudaEventRecord(b->ev_state, st)); CU(cudaEventRecord(b->ev_inputs_free, st));
-    b->state_ev_valid = b->inputs_ev_valid = true;
+    if (stream_is_capturing(st)) b->state_ev_valid = b->inputs_ev_valid = false;
+    else { CU(cudaEventRecord(b->ev_state, st)); CU(cudaEventRecord(b->ev_inputs_free, st)); b->state_ev_valid = b->inputs_ev_valid = true; }
     b->timer.begin(2, st);
     {
         const bool tiled = !(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | 0x200u)) && joseph_tiled_supported(pp);

@@ -34,6 +34,13 @@ struct ekfvio_vio {
     double* d_z = nullptr; double* d_R = nullptr; uint8_t* d_pass = nullptr;
     short* d_kp = nullptr; int* d_count = nullptr; float* d_exist = nullptr; int* d_needed = nullptr;
     short* d_new_px = nullptr; float* d_new_metric = nullptr; int* d_nnew = nullptr; double* d_uv = nullptr; int* d_k = nullptr;
+    // CUDA graph replay: fixed-address copies of the per-call inputs and one executable graph per pyramid-slot parity
+    uint8_t* d_frames_in = nullptr; float* d_K_in = nullptr; double* d_dt_in = nullptr;
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};
+    long long graph_launches[2] = {0, 0};    // kernel launches one replay stands for
+    int parity_seen[2] = {0, 0};
+    cudaStream_t own_st = nullptr;           // capture is not allowed on the legacy default stream: graph frames of such callers run here
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
 
 namespace {
@@ -100,6 +107,7 @@ void ekfvio_vio_default_params(ekfvio_vio_params* p) {
     p->num_features = 100;           // Params.h:46
     p->fast_threshold = 50;          // Params.h:24
     p->min_new_feature_dist = 30;    // Params.h:43
+    p->use_cuda_graph = 1;
 }
 
 int ekfvio_vio_destroy(ekfvio_vio* v) {
@@ -110,6 +118,11 @@ int ekfvio_vio_destroy(ekfvio_vio* v) {
     cudaFree(v->d_measured); cudaFree(v->d_cov); cudaFree(v->d_passed); cudaFree(v->d_z); cudaFree(v->d_R); cudaFree(v->d_pass);
     cudaFree(v->d_kp); cudaFree(v->d_count); cudaFree(v->d_exist); cudaFree(v->d_needed); cudaFree(v->d_new_px); cudaFree(v->d_new_metric);
     cudaFree(v->d_nnew); cudaFree(v->d_uv); cudaFree(v->d_k);
+    cudaFree(v->d_frames_in); cudaFree(v->d_K_in); cudaFree(v->d_dt_in);
+    for (int i = 0; i < 2; ++i) if (v->graph[i]) cudaGraphExecDestroy(v->graph[i]);
+    if (v->own_st) cudaStreamDestroy(v->own_st);
+    if (v->ev_in) cudaEventDestroy(v->ev_in);
+    if (v->ev_out) cudaEventDestroy(v->ev_out);
     delete v;
     return 0;
 }
@@ -141,15 +154,18 @@ int ekfvio_vio_create(ekfvio_vio** out, int device, int num_sequences, int width
     VALLOC(v->d_kp, S * 4096 * 2 * sizeof(short)); VALLOC(v->d_count, S * sizeof(int)); VALLOC(v->d_exist, np * 2 * sizeof(float));
     VALLOC(v->d_needed, S * sizeof(int)); VALLOC(v->d_new_px, np * 2 * sizeof(short)); VALLOC(v->d_new_metric, np * 2 * sizeof(float));
     VALLOC(v->d_nnew, S * sizeof(int)); VALLOC(v->d_uv, np * 2 * sizeof(double)); VALLOC(v->d_k, S * sizeof(int));
+    VALLOC(v->d_frames_in, S * (size_t)width * height); VALLOC(v->d_K_in, S * 9 * sizeof(float)); VALLOC(v->d_dt_in, S * sizeof(double));
 #undef VALLOC
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&v->own_st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ev_in, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v->ev_out, cudaEventDisableTiming);
     if (e != cudaSuccess) { ekfvio_vio_destroy(v); return ekfvio::fail("ekfvio_vio_create", e); }
     *out = v;
     return 0;
 }
 
-int ekfvio_vio_add_frame(ekfvio_vio* v, const uint8_t* d_frames, int pitch, const float* d_K9, const double* d_dt, void* stream) {
-    if (!v || !d_frames || !d_K9 || (v->frames > 0 && !d_dt)) return fail_msg("ekfvio_vio_add_frame: null argument");
-    CU(cudaSetDevice(v->device));
+// The launch sequence of one frame (run eagerly, or recorded into a graph).
+static int enqueue_frame(ekfvio_vio* v, const uint8_t* d_frames, int pitch, const float* d_K9, const double* d_dt, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int S = v->S, nmax = v->nmax;
     ekfvio_batch_view view;
@@ -183,6 +199,53 @@ int ekfvio_vio_add_frame(ekfvio_vio* v, const uint8_t* d_frames, int pitch, cons
     CU(cudaMemcpyAsync(v->d_K_prev, d_K9, (size_t)S * 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     v->launches += 2;
     v->cur_slot = new_slot;
+    v->frames += 1;
+    return 0;
+}
+
+int ekfvio_vio_add_frame(ekfvio_vio* v, const uint8_t* d_frames, int pitch, const float* d_K9, const double* d_dt, void* stream) {
+    if (!v || !d_frames || !d_K9 || (v->frames > 0 && !d_dt)) return fail_msg("ekfvio_vio_add_frame: null argument");
+    if (pitch < v->width) return fail_msg("ekfvio_vio_add_frame: pitch smaller than the frame width");
+    CU(cudaSetDevice(v->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // The first frame and the first frame of each pyramid-slot parity run eagerly (they also configure the kernels);
+    // the second frame of a parity is recorded into a graph, later ones replay it.  Replays read their inputs from
+    // fixed buffers, so the caller's frame / K / dt arrays are copied there first.
+    const int parity = v->cur_slot;
+    if (!v->prm.use_cuda_graph || v->frames == 0 || !v->parity_seen[parity]) {
+        if (v->frames > 0) v->parity_seen[parity] = 1;
+        return enqueue_frame(v, d_frames, pitch, d_K9, d_dt, stream);
+    }
+    const bool legacy = st == nullptr || st == cudaStreamLegacy;   // cannot be captured: hop onto the loop's own stream
+    cudaStream_t caller = st;
+    if (legacy) {
+        CU(cudaEventRecord(v->ev_in, caller));
+        st = v->own_st; stream = (void*)st;
+        CU(cudaStreamWaitEvent(st, v->ev_in, 0));
+    }
+    CU(cudaMemcpy2DAsync(v->d_frames_in, v->width, d_frames, pitch, v->width, (size_t)v->height * v->S, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(v->d_K_in, d_K9, (size_t)v->S * 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(v->d_dt_in, d_dt, (size_t)v->S * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (!v->graph[parity]) {
+        const long long before = ekfvio_vio_launch_count(v);
+        const int frames = v->frames, slot = v->cur_slot;
+        CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_frame(v, v->d_frames_in, v->width, v->d_K_in, v->d_dt_in, stream);
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(st, &g);
+        v->frames = frames; v->cur_slot = slot;              // the recorded frame has not run yet
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return ekfvio::fail("cudaStreamEndCapture", e);
+        v->graph_launches[parity] = ekfvio_vio_launch_count(v) - before;
+        v->launches -= v->graph_launches[parity];            // counted again by the launch below
+        e = cudaGraphInstantiate(&v->graph[parity], g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return ekfvio::fail("cudaGraphInstantiate", e);
+    }
+    CU(cudaGraphLaunch(v->graph[parity], st));
+    if (legacy) { CU(cudaEventRecord(v->ev_out, st)); CU(cudaStreamWaitEvent(caller, v->ev_out, 0)); }
+    v->launches += v->graph_launches[parity];
+    v->cur_slot ^= 1;
     v->frames += 1;
     return 0;
 }

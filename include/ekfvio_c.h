@@ -270,6 +270,8 @@ typedef struct ekfvio_vio_params {
     int num_features;          /* NUM_FEATURES, Params.h:46 (100) — also the filters' feature capacity */
     int fast_threshold;        /* FAST_THRESHOLD, Params.h:24 (50) */
     int min_new_feature_dist;  /* MIN_NEW_FEATURE_DIST, Params.h:43 (30) */
+    int use_cuda_graph;        /* 1: after the first frames the per-frame launch sequence is captured once per pyramid-slot
+                                * parity and replayed as a CUDA graph (one launch advances all sequences by a frame) */
 } ekfvio_vio_params;
 void ekfvio_vio_default_params(ekfvio_vio_params* p);
 int ekfvio_vio_create(ekfvio_vio** out, int device, int num_sequences, int width, int height, const ekfvio_params* ekf_params,

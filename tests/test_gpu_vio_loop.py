@@ -69,16 +69,18 @@ def host_composed(frames, K9, dts, num_features, thr=50, min_dist=30, kill_pad=1
     return out
 
 
-def test_frame_loop_equals_host_composition_and_tracks(cuda):
+@pytest.mark.parametrize("graph", [True, False], ids=["cuda-graph", "eager"])
+def test_frame_loop_equals_host_composition_and_tracks(cuda, graph):
+    """T = 8 frames: eager first frames, one graph capture per pyramid-slot parity (frames 3, 4), replays (5-7)."""
     import torch
     from ekf_vio_b200 import capi, workload
-    S, T, w, h, NF = 3, 5, 320, 240, 40
+    S, T, w, h, NF = 3, 8, 320, 240, 40
     frames = workload.vio_sequences(0, S, T, w, h, speed=2.0)
     K9 = np.zeros((S, 9), np.float32); K9[:, 0] = 200.0; K9[:, 4] = 200.0; K9[:, 6] = 160.0; K9[:, 7] = 120.0; K9[:, 8] = 1.0   # column-major
     dts = np.full((T, S), 0.05)
     ref = host_composed(frames, K9, dts, NF)
 
-    loop = capi.VioLoop(S, w, h, num_features=NF)
+    loop = capi.VioLoop(S, w, h, num_features=NF, use_cuda_graph=graph)
     dK = torch.from_numpy(K9).cuda()
     for t in range(T):
         loop.add_frame(torch.from_numpy(frames[t]).cuda(), dK, None if t == 0 else torch.from_numpy(dts[t]).cuda())
