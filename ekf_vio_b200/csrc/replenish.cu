@@ -1,5 +1,5 @@
 // EKFVIO::replenishFeatures (EKFVIO.cpp:224-311) for batches of frames on sm_100a:
-//   cv::FAST(img, kp, FAST_THRESHOLD, true)   -> fast_score_kernel + fast_nms_compact_kernel
+//   cv::FAST(img, kp, FAST_THRESHOLD, true)   -> fast_score_kernel + fast_nms_mask_kernel + fast_compact_kernel
 //   checkImg / cv::circle / greedy scan        -> replenish_select_kernel
 // plus the C-ABI layer of the `ekfvio_fast_*` entry points (include/ekfvio_c.h).
 // Integer work throughout; results are bit-identical to OpenCV's (keypoint set, order, response,
@@ -26,6 +26,8 @@ struct ekfvio_fast {
     int device = 0, width = 0, height = 0, max_batch = 0, max_keypoints = 0;
     int spitch = 0;                 // pitch of the score plane (multiple of 16)
     uint8_t* d_score = nullptr;     // [max_batch][height][spitch]  cornerScore + 1, 0 = not a corner
+    unsigned* d_masks = nullptr;    // [max_batch][height][ceil(width/32)] keypoint bit masks
+    int* d_rowcnt = nullptr;        // [max_batch][height]
     // staging for the host-buffer entry point
     uint8_t* d_img = nullptr; short* d_kp = nullptr; int* d_resp = nullptr; int* d_count = nullptr;
     float* d_exist = nullptr; int* d_nexist = nullptr; int* d_needed = nullptr; float* d_K9 = nullptr;
@@ -146,40 +148,46 @@ __global__ void __launch_bounds__(256) fast_score_kernel(const uint8_t* __restri
 
 // Non-maximum suppression (a corner survives iff its score is strictly greater than its 8
 // neighbours', fast.cpp) and compaction in OpenCV's order: rows top to bottom, x ascending.
-// One CTA per image: warps take rows, a 32-bit ballot word per 32 pixels; row counts are scanned
-// and every warp then writes its rows' keypoints at their final positions.
-__global__ void __launch_bounds__(512) fast_nms_compact_kernel(const uint8_t* __restrict__ score, int spitch, size_t sstride, int w, int h, int nonmax,
-                                                               short* __restrict__ kp_xy, int* __restrict__ response, int* __restrict__ count,
-                                                               int max_kp) {
-    extern __shared__ int sm_i[];
-    const int wpr = (w + 31) >> 5;             // ballot words per row
-    int* row_cnt = sm_i;                       // [h] -> exclusive prefix after the scan
-    unsigned* masks = reinterpret_cast<unsigned*>(sm_i + h);   // [h][wpr]
-    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const uint8_t* S = score + (size_t)b * sstride;
-    for (int y = warp; y < h; y += nw) {
-        const uint8_t* r1 = S + (size_t)y * spitch;
-        int cnt = 0;
-        for (int wi = 0; wi < wpr; ++wi) {
-            const int x = wi * 32 + lane;
-            bool keep = false;
-            if (x < w) {
-                const int s = r1[x];
-                if (s) {
-                    keep = true;
-                    if (nonmax) {          // s > 0 implies 3 <= x < w-3, 3 <= y < h-3: all neighbours exist
-                        const uint8_t* r0 = r1 - spitch;
-                        const uint8_t* r2 = r1 + spitch;
-                        keep = s > r0[x - 1] && s > r0[x] && s > r0[x + 1] && s > r1[x - 1] && s > r1[x + 1] && s > r2[x - 1] && s > r2[x] && s > r2[x + 1];
-                    }
+// Two launches.  fast_nms_mask_kernel: a warp per row (grid over rows and images) writes a 32-bit ballot word
+// per 32 pixels and the row's keypoint count.  fast_compact_kernel: one CTA per image scans the row counts and
+// every warp writes its rows' keypoints at their final positions (deterministic order without atomics).
+__global__ void __launch_bounds__(256) fast_nms_mask_kernel(const uint8_t* __restrict__ score, int spitch, size_t sstride, int w, int h, int nonmax,
+                                                            unsigned* __restrict__ masks, int* __restrict__ row_cnt) {
+    const int wpr = (w + 31) >> 5;
+    const int b = blockIdx.y, lane = threadIdx.x & 31, y = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (y >= h) return;
+    const uint8_t* r1 = score + (size_t)b * sstride + (size_t)y * spitch;
+    unsigned* mrow = masks + ((size_t)b * h + y) * wpr;
+    int cnt = 0;
+    for (int wi = 0; wi < wpr; ++wi) {
+        const int x = wi * 32 + lane;
+        bool keep = false;
+        if (x < w) {
+            const int s = r1[x];
+            if (s) {
+                keep = true;
+                if (nonmax) {              // s > 0 implies 3 <= x < w-3, 3 <= y < h-3: all neighbours exist
+                    const uint8_t* r0 = r1 - spitch;
+                    const uint8_t* r2 = r1 + spitch;
+                    keep = s > r0[x - 1] && s > r0[x] && s > r0[x + 1] && s > r1[x - 1] && s > r1[x + 1] && s > r2[x - 1] && s > r2[x] && s > r2[x + 1];
                 }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (lane == 0) masks[y * wpr + wi] = m;
-            cnt += __popc(m);
         }
-        if (lane == 0) row_cnt[y] = cnt;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) mrow[wi] = m;
+        cnt += __popc(m);
     }
+    if (lane == 0) row_cnt[(size_t)b * h + y] = cnt;
+}
+
+__global__ void __launch_bounds__(512) fast_compact_kernel(const uint8_t* __restrict__ score, int spitch, size_t sstride, int w, int h,
+                                                           const unsigned* __restrict__ masks, const int* __restrict__ row_cnt_g,
+                                                           short* __restrict__ kp_xy, int* __restrict__ response, int* __restrict__ count, int max_kp) {
+    extern __shared__ int row_cnt[];           // [h] -> exclusive prefix after the scan
+    const int wpr = (w + 31) >> 5;
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const uint8_t* S = score + (size_t)b * sstride;
+    for (int y = threadIdx.x; y < h; y += blockDim.x) row_cnt[y] = row_cnt_g[(size_t)b * h + y];
     __syncthreads();
     if (warp == 0) {                           // exclusive scan of the row counts
         int carry = 0;
@@ -199,8 +207,12 @@ __global__ void __launch_bounds__(512) fast_nms_compact_kernel(const uint8_t* __
     int* rs = response ? response + (size_t)b * max_kp : nullptr;
     for (int y = warp; y < h; y += nw) {
         int base = row_cnt[y];
+        if (base >= max_kp) continue;
+        const int next = y + 1 < h ? row_cnt[y + 1] : base + 1;   // rows without keypoints need no mask reads
+        if (y + 1 < h && next == base) continue;
+        const unsigned* mrow = masks + ((size_t)b * h + y) * wpr;
         for (int wi = 0; wi < wpr; ++wi) {
-            const unsigned m = masks[y * wpr + wi];
+            const unsigned m = mrow[wi];
             if (m >> lane & 1u) {
                 const int idx = base + __popc(m & ((1u << lane) - 1u));
                 if (idx < max_kp) {
@@ -358,7 +370,7 @@ int ekfvio_frame_resize(const uint8_t* d_src, int src_pitch, int src_width, int 
 int ekfvio_fast_destroy(ekfvio_fast* f) {
     if (!f) return 0;
     cudaSetDevice(f->device);
-    cudaFree(f->d_score); cudaFree(f->d_img); cudaFree(f->d_kp); cudaFree(f->d_resp); cudaFree(f->d_count);
+    cudaFree(f->d_score); cudaFree(f->d_masks); cudaFree(f->d_rowcnt); cudaFree(f->d_img); cudaFree(f->d_kp); cudaFree(f->d_resp); cudaFree(f->d_count);
     cudaFree(f->d_exist); cudaFree(f->d_nexist); cudaFree(f->d_needed); cudaFree(f->d_K9); cudaFree(f->d_new_px); cudaFree(f->d_new_metric);
     cudaFree(f->d_nnew);
     delete f;
@@ -368,8 +380,9 @@ int ekfvio_fast_destroy(ekfvio_fast* f) {
 int ekfvio_fast_create(ekfvio_fast** out, int device, int width, int height, int max_batch, int max_keypoints) {
     if (!out || width < 7 || height < 7 || max_batch <= 0 || max_keypoints <= 0) return fail_msg("ekfvio_fast_create: bad arguments");
     if (width > 32767 || height > 32767) return fail_msg("ekfvio_fast_create: image larger than 32767 pixels on a side");
-    const size_t nms_smem = ((size_t)height + (size_t)height * ((width + 31) / 32)) * sizeof(int);
-    if (nms_smem > 200 * 1024) return fail_msg("ekfvio_fast_create: image too large for the single-CTA compaction (height * (1 + width/32) * 4 bytes must be <= 200 KB)");
+    const size_t nms_smem = (size_t)height * sizeof(int);
+    if (nms_smem > 200 * 1024) return fail_msg("ekfvio_fast_create: image too tall for the row-count scan");
+    if ((size_t)(height * ((width + 31) / 32) + 2 * 1024 + 1) * sizeof(int) > 200 * 1024) return fail_msg("ekfvio_fast_create: image too large for the shared-memory check image of the greedy scan (height * width / 8 bytes must be <= 190 KB)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail_msg("ekfvio_fast_create: no CUDA device (this library has no CPU path)");
     CU(cudaSetDevice(device));
@@ -381,6 +394,8 @@ int ekfvio_fast_create(ekfvio_fast** out, int device, int width, int height, int
     const size_t plane = (size_t)f->spitch * height * max_batch;
     cudaError_t e = cudaMalloc((void**)&f->d_score, plane);
     if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_img, plane);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_masks, (size_t)max_batch * height * ((width + 31) / 32) * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_rowcnt, (size_t)max_batch * height * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_kp, (size_t)max_batch * max_keypoints * 2 * sizeof(short));
     if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_resp, (size_t)max_batch * max_keypoints * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_count, (size_t)max_batch * sizeof(int));
@@ -391,7 +406,7 @@ int ekfvio_fast_create(ekfvio_fast** out, int device, int width, int height, int
     if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_new_px, (size_t)max_batch * f->max_existing * 2 * sizeof(short));
     if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_new_metric, (size_t)max_batch * f->max_existing * 2 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_nnew, (size_t)max_batch * sizeof(int));
-    if (e == cudaSuccess && nms_smem > 48 * 1024) e = cudaFuncSetAttribute(fast_nms_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem);
+    if (e == cudaSuccess && nms_smem > 48 * 1024) e = cudaFuncSetAttribute(fast_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem);
     if (e != cudaSuccess) { ekfvio_fast_destroy(f); return ekfvio::fail("ekfvio_fast_create", e); }
     *out = f;
     return 0;
@@ -408,11 +423,13 @@ int ekfvio_fast_detect(ekfvio_fast* f, const uint8_t* d_imgs, int pitch, int bat
     dim3 grid((f->width + FTW - 1) / FTW, (f->height + FTH - 1) / FTH, batch);
     fast_score_kernel<<<grid, 256, 0, st>>>(d_imgs, pitch, (size_t)pitch * f->height, f->width, f->height, threshold, f->d_score, f->spitch, sstride);
     CU(cudaGetLastError());
-    const size_t sm = ((size_t)f->height + (size_t)f->height * ((f->width + 31) / 32)) * sizeof(int);
-    fast_nms_compact_kernel<<<batch, 512, sm, st>>>(f->d_score, f->spitch, sstride, f->width, f->height, nonmax, d_kp_xy, d_response, d_count,
-                                                    f->max_keypoints);
+    fast_nms_mask_kernel<<<dim3((f->height + 7) / 8, batch), 256, 0, st>>>(f->d_score, f->spitch, sstride, f->width, f->height, nonmax, f->d_masks,
+                                                                           f->d_rowcnt);
     CU(cudaGetLastError());
-    f->launches += 2;
+    fast_compact_kernel<<<batch, 512, (size_t)f->height * sizeof(int), st>>>(f->d_score, f->spitch, sstride, f->width, f->height, f->d_masks, f->d_rowcnt,
+                                                                             d_kp_xy, d_response, d_count, f->max_keypoints);
+    CU(cudaGetLastError());
+    f->launches += 3;
     return 0;
 }
 
