@@ -30,6 +30,7 @@ static EkfPtrs ptrs(const ekfvio_batch* b) {
     p.klt_last = b->d_klt_last; p.status = b->d_status; p.idx = b->d_idx; p.y = b->d_y; p.m = b->d_m; p.K = b->d_K; p.W = b->d_W; p.L = b->d_L; p.asym = b->d_asym;
     p.F = b->F; p.nmax = b->nmax; p.Nmax = b->Nmax; p.ldP = b->ldP; p.ldK = b->ldK; p.mmax = b->mmax;
     p.flags = b->prm.flags;
+    p.sigma_lower = b->upper_stale ? 1 : 0;
     p.depth = b->prm.default_point_depth; p.depth_var = b->prm.default_point_depth_variance;
     p.uv_var = b->prm.default_point_homogenous_variance;
     p.gain_smem_doubles = gain_general_smem_doubles(b->mmax);
@@ -41,6 +42,17 @@ static EkfPtrs ptrs(const ekfvio_batch* b) {
 static bool stream_is_capturing(cudaStream_t st) {
     cudaStreamCaptureStatus s = cudaStreamCaptureStatusNone;
     return cudaStreamIsCapturing(st, &s) == cudaSuccess && s != cudaStreamCaptureStatusNone;
+}
+
+// Sigma of symmetric filters after a lower-mode process(): mirror the part below the diagonal blocks into the stale part
+// above them before anyone but the reduced tiled update reads the matrix.
+static int ensure_full_sigma(ekfvio_batch* b, cudaStream_t st) {
+    if (!b->upper_stale) return 0;
+    cudaError_t e = launch_mirror_lower(ptrs(b), b->d_P[b->cur], st);
+    if (e != cudaSuccess) return ekfvio::fail("launch_mirror_lower", e);
+    b->upper_stale = false;
+    b->launches += 1;
+    return 0;
 }
 
 extern "C" {
@@ -120,6 +132,11 @@ int ekfvio_batch_create(ekfvio_batch** out, int device, int num_filters, int max
         ekfvio_batch_destroy(b);
         return fail_msg("cudaMallocHost failed");
     }
+    {
+        const EkfPtrs pp = ptrs(b);
+        b->lower_ok = !(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | EKFVIO_FLAG_LITERAL_JOSEPH | 0x100u | 0x200u | 0x400u | 0x2000u)) && !b->large &&
+                      gain_tiled_supported(pp) && joseph_sym_supported(pp) && process_lower_capable(pp);
+    }
     if (cudaStreamCreateWithFlags(&b->copy_st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_inputs_free, cudaEventDisableTiming) != cudaSuccess ||
@@ -141,6 +158,7 @@ long long ekfvio_batch_launch_count(const ekfvio_batch* b) { return b ? b->launc
 int ekfvio_batch_reset(ekfvio_batch* b, void* stream) {
     CU(cudaSetDevice(b->device));
     b->state_ev_valid = false;   // state written on the caller's stream: downloads order behind that stream
+    b->upper_stale = false;
     CU(launch_reset(ptrs(b), b->d_P[b->cur], (cudaStream_t)stream));
     b->launches += 1;
     return 0;
@@ -156,9 +174,12 @@ int ekfvio_batch_add_features(ekfvio_batch* b, const int* d_k, const double* d_u
 
 int ekfvio_batch_process(ekfvio_batch* b, const double* d_dt, void* stream) {
     CU(cudaSetDevice(b->device));
+    if (ensure_full_sigma(b, (cudaStream_t)stream)) return 1;     // (two process() calls in a row)
     b->timer.begin(0, (cudaStream_t)stream);
-    CU(launch_process_general(ptrs(b), b->d_P[b->cur], b->d_P[b->cur ^ 1], d_dt, 0, nullptr, (cudaStream_t)stream, &b->launches));
+    CU(launch_process_general(ptrs(b), b->d_P[b->cur], b->d_P[b->cur ^ 1], d_dt, 0, nullptr, (cudaStream_t)stream, &b->launches, b->lower_ok ? 1 : 0));
     b->timer.end((cudaStream_t)stream);
+    b->upper_stale = b->lower_ok;
+    b->last_stream = (cudaStream_t)stream;
     if (stream_is_capturing((cudaStream_t)stream)) b->state_ev_valid = false;
     else { CU(cudaEventRecord(b->ev_state, (cudaStream_t)stream)); b->state_ev_valid = true; }
     b->cur ^= 1;
@@ -174,7 +195,7 @@ int ekfvio_batch_process_dt(ekfvio_batch* b, double dt, void* stream) {
 
 int ekfvio_batch_linearize(ekfvio_batch* b, const double* d_dt, double* d_F, void* stream) {
     CU(cudaSetDevice(b->device));
-    CU(launch_process_general(ptrs(b), b->d_P[b->cur], nullptr, d_dt, 1, d_F, (cudaStream_t)stream, &b->launches));
+    CU(launch_process_general(ptrs(b), b->d_P[b->cur], nullptr, d_dt, 1, d_F, (cudaStream_t)stream, &b->launches, 0));
     return 0;
 }
 
@@ -227,12 +248,14 @@ int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, c
     }
     b->timer.end(st);
     b->cur ^= 1;
+    b->upper_stale = false;     // the covariance kernels write the whole matrix
     b->launches += 2;
     return 0;
 }
 
 int ekfvio_batch_check_sigma(ekfvio_batch* b, int* d_neg_diag, double* d_max_asym, void* stream) {
     CU(cudaSetDevice(b->device));
+    if (ensure_full_sigma(b, (cudaStream_t)stream)) return 1;
     CU(launch_check_sigma(ptrs(b), b->d_P[b->cur], d_neg_diag, d_max_asym, (cudaStream_t)stream));
     b->launches += 1;
     return 0;
@@ -266,6 +289,7 @@ int ekfvio_measure_fp64_peak(int device, double* dmma_tflops, double* dfma_tflop
 }
 
 int ekfvio_batch_get_view(ekfvio_batch* b, ekfvio_batch_view* v) {
+    if (b->upper_stale) { CU(cudaSetDevice(b->device)); if (ensure_full_sigma(b, b->last_stream)) return 1; }   // zero-copy readers see the whole matrix (ordered behind the last process())
     v->d_mu = b->d_mu; v->d_feat = b->d_feat; v->d_P = b->d_P[b->cur]; v->d_nfeat = b->d_nfeat; v->d_status = b->d_status;
     v->ldP = b->ldP; v->num_filters = b->F; v->max_features = b->nmax; v->d_klt_last = b->d_klt_last;
     return 0;
@@ -274,6 +298,7 @@ int ekfvio_batch_get_view(ekfvio_batch* b, ekfvio_batch_view* v) {
 int ekfvio_batch_get_state(ekfvio_batch* b, double* h_mu, double* h_feat, double* h_P, int* h_nfeat, double* h_cache, uint8_t* h_flags,
                            double* h_klt_last, int* h_status) {
     CU(cudaSetDevice(b->device));
+    if (h_P && ensure_full_sigma(b, b->last_stream)) return 1;
     CU(cudaDeviceSynchronize());
     size_t F = b->F, nm = b->nmax;
     if (h_mu) CU(cudaMemcpy(h_mu, b->d_mu, F * BASE * sizeof(double), cudaMemcpyDeviceToHost));
@@ -300,6 +325,7 @@ int ekfvio_batch_set_state(ekfvio_batch* b, const double* h_mu, const double* h_
                            const double* h_cache, const uint8_t* h_flags, const double* h_klt_last) {
     CU(cudaSetDevice(b->device));
     b->state_ev_valid = false;
+    if (ensure_full_sigma(b, b->last_stream)) return 1;
     CU(cudaDeviceSynchronize());
     size_t F = b->F, nm = b->nmax;
     if (h_nfeat) {

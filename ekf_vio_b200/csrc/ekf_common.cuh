@@ -169,4 +169,9 @@ struct ekfvio_batch {
     cudaStream_t copy_st = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_inputs_free = nullptr, ev_state = nullptr;
     bool inputs_ev_valid = false, state_ev_valid = false;
+    // lower mode: process() of a batch on the reduced tiled update path leaves the feature rows of symmetric filters
+    // complete only up to their diagonal blocks; the update that follows restores the full matrix, any other reader
+    // of Sigma gets it mirrored first (ensure_full_sigma)
+    bool lower_ok = false, upper_stale = false;
+    cudaStream_t last_stream = nullptr;       // stream of the last process()
 };

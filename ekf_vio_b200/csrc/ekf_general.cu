@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(128) ekf_linearize_kernel(EkfPtrs p, const dou
 // mode 1: linearize only (dense F written to F_out, state untouched except the dq cache).
 __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const double* __restrict__ Pin, double* __restrict__ Pout,
                                                           const double* __restrict__ dts, int mode, double* __restrict__ F_out, int fused,
-                                                          int pre) {
+                                                          int pre, int lower) {
     extern __shared__ double sm[];
     const int f = blockIdx.x, tid = threadIdx.x;
     const int n = p.nfeat[f], N = BASE + 3 * n;
@@ -290,11 +290,17 @@ __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const do
         double* Own = Tw + 3 * (size_t)Npm;                           // [3][Np]
         for (int e = tid; e < 9 * N; e += blockDim.x) { int k = e / N, c = e - k * N; Pb[k * Np + c] = Pi[(size_t)(7 + k) * ld + c]; }
         const int ntask = 8 + n;
+        // Lower mode (symmetric filter whose next consumer is the reduced update): a feature row block is only
+        // needed up to its own diagonal block — columns c < BASE + 3 fi + 3 of T and of Sigma' — which removes
+        // almost half of both passes and of the traffic; rows 0..21 stay complete.  The upper part of the feature
+        // rows of the output is then stale (ekf_api.cu mirrors it on demand).
+        const bool low = lower && p.asym[f] == 0;
         auto prefetch = [&](int t) {
             if (t >= 8 && t < ntask) {
                 const double* own = Pi + (size_t)(BASE + 3 * (t - 8)) * ld;
-                for (int e = lane; e < 3 * (Np / 2); e += 32) {
-                    int r = e / (Np / 2), c2 = (e - r * (Np / 2)) * 2;
+                const int cn = low ? BASE + 3 * (t - 8) + 3 : N, half = ((cn + 3) & ~3) / 2;
+                for (int e = lane; e < 3 * half; e += 32) {
+                    int r = e / half, c2 = (e - r * half) * 2;
                     unsigned dst = (unsigned)__cvta_generic_to_shared(Own + r * Np + c2);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(own + (size_t)r * ld + c2) : "memory");
                 }
@@ -329,7 +335,8 @@ __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const do
                 for (int k = 0; k < 27; ++k) bb[k] = s.B[fi * 27 + k];
 #pragma unroll
                 for (int k = 0; k < 9; ++k) dd[k] = s.D[fi * 9 + k];
-                for (int c = lane; c < N; c += 32) {
+                const int cn = low ? r0 + 3 : N;
+                for (int c = lane; c < cn; c += 32) {
                     double o0 = Own[c], o1 = Own[Np + c], o2 = Own[2 * Np + c];
                     double a0 = dd[0] * o0 + dd[1] * o1 + dd[2] * o2;
                     double a1 = dd[3] * o0 + dd[4] * o1 + dd[5] * o2;
@@ -365,7 +372,8 @@ __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const do
                 for (int r = 0; r < 3; ++r)
 #pragma unroll
                     for (int k = 0; k < 9; ++k) tb[r][k] = Tw[r * Np + 7 + k];
-                for (int fj = lane; fj < n; fj += 32) {
+                const int nfj = (low && !base_task) ? fi + 1 : n;
+                for (int fj = lane; fj < nfj; fj += 32) {
                     double t3[3][3];
 #pragma unroll
                     for (int r = 0; r < 3; ++r)
@@ -738,6 +746,19 @@ __global__ void ekf_commit_state_kernel(EkfPtrs p) {
     if (n > 0 && tid < 7) p.cache[(size_t)f * 7 + tid] = stage[BASE + 3 * p.nmax + tid];
 }
 
+// Completes Sigma after a lower-mode process(): feature row r is valid up to column BASE + 3 fr + 2; the rest of the
+// row is the mirror image of the column below the diagonal.  (Symmetric filters only; the others were written in full.)
+__global__ void ekf_mirror_lower_kernel(EkfPtrs p, double* __restrict__ P0) {
+    const int f = blockIdx.y;
+    if (p.asym[f] != 0) return;
+    const int N = BASE + 3 * p.nfeat[f], ld = p.ldP;
+    double* P = P0 + (size_t)f * ld * ld;
+    for (int r = BASE + blockIdx.x; r < N; r += gridDim.x) {
+        const int ext = BASE + 3 * ((r - BASE) / 3) + 3;
+        for (int c = ext + threadIdx.x; c < N; c += blockDim.x) P[(size_t)r * ld + c] = P[(size_t)c * ld + r];
+    }
+}
+
 __global__ void ekf_fill_dt_kernel(double* dts, double dt, int F) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < F) dts[i] = dt;
@@ -795,8 +816,16 @@ static size_t proc_fused_smem_bytes(int nmax) {
     return proc_smem_bytes(nmax) + sizeof(double) + (9 + 6 * (PT / 32)) * Np * sizeof(double);
 }
 
+// the fused row-block kernel is the one that knows the lower mode
+bool process_lower_capable(const EkfPtrs& p) { return proc_fused_smem_bytes(p.nmax) <= 110 * 1024; }
+
+cudaError_t launch_mirror_lower(const EkfPtrs& p, double* P0, cudaStream_t st) {
+    ekf_mirror_lower_kernel<<<dim3(16, p.F), 128, 0, st>>>(p, P0);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_process_general(const EkfPtrs& p, const double* Pin, double* Pout, const double* dts, int mode, double* F_out, cudaStream_t st,
-                                   long long* launches) {
+                                   long long* launches, int lower) {
     size_t sm = proc_smem_bytes(p.nmax);
     const int fused = (mode == 0 && proc_fused_smem_bytes(p.nmax) <= 110 * 1024) ? 1 : 0;   // two CTAs per SM
     if (fused) sm = proc_fused_smem_bytes(p.nmax);
@@ -819,7 +848,7 @@ cudaError_t launch_process_general(const EkfPtrs& p, const double* Pin, double* 
         pre = 1;
         if (launches) *launches += 1;
     }
-    ekf_process_general<<<dim3(p.F, ysplit), PT, sm, st>>>(p, Pin, Pout, dts, mode, F_out, fused, pre);
+    ekf_process_general<<<dim3(p.F, ysplit), PT, sm, st>>>(p, Pin, Pout, dts, mode, F_out, fused, pre, (fused && lower) ? 1 : 0);
     if (ysplit > 1) ekf_commit_state_kernel<<<p.F, 128, 0, st>>>(p);
     if (launches) *launches += ysplit > 1 ? 2 : 1;
     return cudaGetLastError();

@@ -14,13 +14,17 @@ struct EkfPtrs {
     int* idx; double* y; int* m; double* K; double* W; double* L; int* asym;
     int F, nmax, Nmax, ldP, ldK, mmax;
     uint32_t flags;
+    int sigma_lower;   // the input Sigma of symmetric filters is valid only up to the diagonal block of each feature row (after a lower-mode process)
     double depth, depth_var, uv_var;
     size_t gain_smem_doubles;
 };
 
 // general path (ekf_general.cu)
+// lower != 0: symmetric filters get Sigma' only up to the diagonal block of each feature row (fused path; see ekf_general.cu)
 cudaError_t launch_process_general(const EkfPtrs& p, const double* Pin, double* Pout, const double* dts, int mode, double* F_out, cudaStream_t st,
-                                   long long* launches);
+                                   long long* launches, int lower);
+bool process_lower_capable(const EkfPtrs& p);
+cudaError_t launch_mirror_lower(const EkfPtrs& p, double* P0, cudaStream_t st);
 cudaError_t launch_gain_general(const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, double* Sg,
                                 cudaStream_t st);
 cudaError_t launch_joseph_general(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st);

@@ -185,7 +185,10 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
     int* idx_g = p.idx + (size_t)f * p.mmax;
     double* y_g = p.y + (size_t)f * p.mmax;
 
+    __shared__ int s_was_sym;
     if (warp == 0) {  // formFeatureMeasurementMap (:634-661) + bookkeeping of :506-529, ballot-compacted
+        if (lane == 0) s_was_sym = p.asym[f] == 0;
+        __syncwarp();
         int m = 0;
         for (int base = 0; base < n; base += 32) {
             int i = base + lane;
@@ -219,6 +222,19 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
         return;
     }
     const int nb = (m + 7) >> 3;
+    const bool sym_now = p.asym[f] == 0;
+    if (p.sigma_lower && s_was_sym && !sym_now) {
+        // the filter turns asymmetric with this update (asymmetric R): complete its Sigma, of which the last process()
+        // wrote the feature rows only up to their diagonal blocks
+        double* Pw = const_cast<double*>(Pi);
+        const int N = BASE + 3 * n;
+        for (int r = BASE + warp; r < N; r += 4) {
+            const int ext = BASE + 3 * ((r - BASE) / 3) + 3;
+            for (int c = ext + lane; c < N; c += 32) Pw[(size_t)r * ld + c] = Pw[(size_t)c * ld + r];
+        }
+        __syncthreads();
+    }
+    const bool low = p.sigma_lower && sym_now;     // then Sigma(idx[b], idx[a]) is read through its mirror image
 
     // lower(a,b), a >= b  <-  upper(S)(b,a) = Sigma(idx[b], idx[a]) + R(b,a)  (SimplicialLDLT::compute(S')
     // reads upper(S), :578); identity tail.  Four independent gathers in flight per thread.
@@ -240,7 +256,7 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
                     o[u] = t * 64 + tsw(rr, cc);
                     if (a >= b) {
                         if (a < m) {
-                            v[u] = Pi[(size_t)s_idx[b] * ld + s_idx[a]];
+                            v[u] = low ? Pi[(size_t)s_idx[a] * ld + s_idx[b]] : Pi[(size_t)s_idx[b] * ld + s_idx[a]];
                             if ((a >> 1) == (b >> 1)) v[u] += Rf[4 * ((s_idx[a] - BASE) / 3) + (b & 1) * 2 + (a & 1)];
                         } else {
                             v[u] = (a == b) ? 1.0 : 0.0;
@@ -563,12 +579,15 @@ __global__ void __launch_bounds__(NW * 32, 2) ekf_fwd_tiled(EkfPtrs p, const dou
 #pragma unroll
     for (int rt = 0; rt < 2; ++rt) {
         const int row = i0 + rt * 8 + r;
+        const int ext = (!p.sigma_lower || row < BASE) ? ld : BASE + 3 * ((row - BASE) / 3) + 3;   // columns valid in this row
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) {
             int a = jb * 8 + 2 * q;
             bool ok = row < N && a < m && jb < nb;
-            k0[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a]] : 0.0;
-            k1[rt][jb] = ok ? Pi[(size_t)row * ld + s_idx[a + 1]] : 0.0;
+            // lower mode: element (row, col) beyond the row's diagonal block is read as (col, row)
+            const int c0 = s_idx[a], c1 = s_idx[a + 1];
+            k0[rt][jb] = ok ? (c0 < ext ? Pi[(size_t)row * ld + c0] : Pi[(size_t)c0 * ld + row]) : 0.0;
+            k1[rt][jb] = ok ? (c1 < ext ? Pi[(size_t)row * ld + c1] : Pi[(size_t)c1 * ld + row]) : 0.0;
         }
     }
     cp_async_wait<0>();

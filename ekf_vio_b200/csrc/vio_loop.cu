@@ -26,6 +26,7 @@ struct ekfvio_vio {
     ekfvio_batch* ekf = nullptr;
     ekfvio_klt* klt = nullptr;
     ekfvio_fast* fast = nullptr;
+    ekfvio_batch_view view{};              // state pointers of the filters (stable for the batch's lifetime; d_P is not used here)
     int frames = 0, cur_slot = 0;          // pyramid slot of the most recent frame
     long long launches = 0;
     float* d_K_prev = nullptr;             // [S][9] K of the previous frame (metric2Pixel(lf, .))
@@ -142,6 +143,7 @@ int ekfvio_vio_create(ekfvio_vio** out, int device, int num_sequences, int width
     int rc = ekfvio_batch_create(&v->ekf, device, num_sequences, v->nmax, &ep);
     if (!rc) rc = ekfvio_klt_create(&v->klt, device, width, height, num_sequences, v->nmax, 2, &v->klt_prm);
     if (!rc) rc = ekfvio_fast_create(&v->fast, device, width, height, num_sequences, 4096);
+    if (!rc) rc = ekfvio_batch_get_view(v->ekf, &v->view);
     if (rc) { ekfvio_vio_destroy(v); return rc; }
     const size_t S = num_sequences, np = S * v->nmax;
     cudaError_t e = cudaSetDevice(device);
@@ -168,13 +170,12 @@ int ekfvio_vio_create(ekfvio_vio** out, int device, int num_sequences, int width
 static int enqueue_frame(ekfvio_vio* v, const uint8_t* d_frames, int pitch, const float* d_K9, const double* d_dt, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int S = v->S, nmax = v->nmax;
-    ekfvio_batch_view view;
+    const ekfvio_batch_view& view = v->view;
     const int new_slot = v->frames == 0 ? 0 : (v->cur_slot ^ 1);
     // this frame's pyramid, with derivatives: it is the "previous" frame of the next call
     RC(ekfvio_klt_build_pyramid(v->klt, new_slot, d_frames, pitch, S, 1, stream));
     if (v->frames > 0) {
         RC(ekfvio_batch_process(v->ekf, d_dt, stream));                                              // EKFVIO.cpp:163
-        RC(ekfvio_batch_get_view(v->ekf, &view));
         vio_points_kernel<<<S, 128, 0, st>>>(view.d_feat, view.d_klt_last, view.d_nfeat, nmax, v->d_K_prev, d_K9, v->d_prev_pts, v->d_next_pts,
                                              v->d_npts, nullptr, v->prm.num_features);
         CU(cudaGetLastError());
@@ -186,7 +187,6 @@ static int enqueue_frame(ekfvio_vio* v, const uint8_t* d_frames, int pitch, cons
         v->launches += 2;
     }
     // replenishFeatures (EKFVIO.cpp:172 / :153)
-    RC(ekfvio_batch_get_view(v->ekf, &view));
     vio_points_kernel<<<S, 128, 0, st>>>(view.d_feat, view.d_klt_last, view.d_nfeat, nmax, d_K9, d_K9, nullptr, v->d_exist, v->d_npts, v->d_needed,
                                          v->prm.num_features);
     CU(cudaGetLastError());

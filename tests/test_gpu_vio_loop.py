@@ -28,11 +28,16 @@ def host_composed(frames, K9, dts, num_features, thr=50, min_dist=30, kill_pad=1
         new_slot = 0 if t == 0 else cur ^ 1
         trk.build_pyramid(new_slot, d, True)
         if t > 0:
+            st = batch.get_state(want_P=False)                      # klt_last / nfeat: untouched by process()
             batch.process(torch.from_numpy(dts[t]).cuda())
-            st = batch.get_state(want_P=False)
+            # (the predicted features are read without asking for Sigma: a Sigma read between process() and update() would
+            # make the batch complete the matrix first and the update would then run from the other triangle — same
+            # result to rounding, but this test wants the loop bit for bit)
+            h_mu = np.zeros((S, 22)); h_feat = np.zeros((S, num_features, 3))
+            batch.read_mu_h(h_mu, h_feat)
             n = st["nfeat"]
             prev_pts = np.zeros((S, num_features, 2), np.float32); next_pts = np.zeros_like(prev_pts)
-            kl = st["klt_last"].astype(np.float32); ft = st["feat"].astype(np.float32)
+            kl = st["klt_last"].astype(np.float32); ft = h_feat.astype(np.float32)
             for s in range(S):
                 Kp, Kc = Kprev[s], K9[s]
                 prev_pts[s, :n[s], 0] = kl[s, :n[s], 0] * Kp[0] + Kp[2]; prev_pts[s, :n[s], 1] = kl[s, :n[s], 1] * Kp[4] + Kp[5]
