@@ -134,7 +134,7 @@ int ekfvio_batch_create(ekfvio_batch** out, int device, int num_filters, int max
     }
     {
         const EkfPtrs pp = ptrs(b);
-        b->lower_ok = !(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | EKFVIO_FLAG_LITERAL_JOSEPH | 0x100u | 0x200u | 0x400u | 0x2000u)) && !b->large &&
+        b->lower_ok = !(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | EKFVIO_FLAG_LITERAL_JOSEPH | 0x100u | 0x200u | 0x400u)) && !b->large &&
                       gain_tiled_supported(pp) && joseph_sym_supported(pp) && process_lower_capable(pp);
     }
     if (cudaStreamCreateWithFlags(&b->copy_st, cudaStreamNonBlocking) != cudaSuccess ||

@@ -803,12 +803,8 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
         for (int v = 0; v < cur.nv; ++v) {
             cp_async_wait<SNST - 2>();
             __syncthreads();
-#ifdef EXP_NO_STAGE
-            cp_async_commit(); ++gs; if (!(v + 2 < cur.nv)) ++issued_next;
-#else
             if (v + 2 < cur.nv) issue(cur, v + 2, s_idx[ib]);
             else { issue(nxt, issued_next, s_idx[ib ^ 1]); ++issued_next; }
-#endif
             const double* A = sms + (gc % SNST) * STAGE;
             const double* B = schur ? A : A + A_DOUBLES;
             ++gc;
@@ -823,7 +819,6 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
                     if (!phase1) { const double* Bi = B + boffg[it] + kk * 4 * SLDB; fb0[it] = Bi[0]; fb1[it] = Bi[8]; }
                     else { const double* Bi = B + boffk[it] + kk * 4; fb0[it] = Bi[0]; fb1[it] = Bi[8 * SLDA]; }
                 }
-#ifndef EXP_NO_MMA
 #pragma unroll
                 for (int it = 0; it < IPW; ++it) {
                     dmma884(c0[it][0], c1[it][0], -fa0[it], fb0[it]);
@@ -831,10 +826,6 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
                     dmma884(c0[it][2], c1[it][2], -fa1[it], fb0[it]);
                     dmma884(c0[it][3], c1[it][3], -fa1[it], fb1[it]);
                 }
-#else
-#pragma unroll
-                for (int it = 0; it < IPW; ++it) { c0[it][0] += fa0[it] * fb0[it]; c1[it][1] += fa1[it] * fb1[it]; }
-#endif
             }
         }
         while (issued_next < 2) { issue(nxt, issued_next, s_idx[ib ^ 1]); ++issued_next; }   // short filters (nv < 2)

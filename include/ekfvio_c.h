@@ -43,6 +43,9 @@ extern "C" {
  * (SURVEY.md §8a E1..E6).  Each fix is opt-in. */
 #define EKFVIO_FLAG_FORCE_GENERAL_PATH 0x1u /* always use the general (non-tiled) kernels */
 #define EKFVIO_FLAG_FRESH_DQ_CACHE 0x2u     /* fix E2: never reuse a dq_inv computed for another dt */
+/* Diagnostic bits (tools/diag_parity.py, tools/process_probe.py; no effect on results other than the path taken):
+ * 0x100 general gain kernel, 0x200 general covariance kernel, 0x400 tiled covariance kernel without the symmetric
+ * variant, 0x800 process() stops after linearisation + state propagation. */
 #define EKFVIO_FLAG_LITERAL_JOSEPH 0x4u     /* evaluate (I-KH) Sigma (I-KH)' + K R K' term by term even where Sigma and R are
                                              * symmetric; by default such filters use the algebraically identical
                                              * Sigma - Z Z', Z = Sigma(:,idx) inv(L)', S = L L'  */
