@@ -746,16 +746,16 @@ __global__ void ekf_commit_state_kernel(EkfPtrs p) {
     if (n > 0 && tid < 7) p.cache[(size_t)f * 7 + tid] = stage[BASE + 3 * p.nmax + tid];
 }
 
-// Completes Sigma after a lower-mode process(): feature row r is valid up to column BASE + 3 fr + 2; the rest of the
-// row is the mirror image of the column below the diagonal.  (Symmetric filters only; the others were written in full.)
+// Completes Sigma after a lower-mode process(): feature row r was written up to its diagonal block; everything right of
+// the diagonal becomes the mirror image of the column below it — the same elements the lower-mode readers take, so a
+// mirror pass never changes what the update computes.  (Symmetric filters only; the others were written in full.)
 __global__ void ekf_mirror_lower_kernel(EkfPtrs p, double* __restrict__ P0) {
     const int f = blockIdx.y;
     if (p.asym[f] != 0) return;
     const int N = BASE + 3 * p.nfeat[f], ld = p.ldP;
     double* P = P0 + (size_t)f * ld * ld;
     for (int r = BASE + blockIdx.x; r < N; r += gridDim.x) {
-        const int ext = BASE + 3 * ((r - BASE) / 3) + 3;
-        for (int c = ext + threadIdx.x; c < N; c += blockDim.x) P[(size_t)r * ld + c] = P[(size_t)c * ld + r];
+        for (int c = r + 1 + threadIdx.x; c < N; c += blockDim.x) P[(size_t)r * ld + c] = P[(size_t)c * ld + r];
     }
 }
 

@@ -229,8 +229,7 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
         double* Pw = const_cast<double*>(Pi);
         const int N = BASE + 3 * n;
         for (int r = BASE + warp; r < N; r += 4) {
-            const int ext = BASE + 3 * ((r - BASE) / 3) + 3;
-            for (int c = ext + lane; c < N; c += 32) Pw[(size_t)r * ld + c] = Pw[(size_t)c * ld + r];
+            for (int c = r + 1 + lane; c < N; c += 32) Pw[(size_t)r * ld + c] = Pw[(size_t)c * ld + r];
         }
         __syncthreads();
     }
@@ -579,7 +578,9 @@ __global__ void __launch_bounds__(NW * 32, 2) ekf_fwd_tiled(EkfPtrs p, const dou
 #pragma unroll
     for (int rt = 0; rt < 2; ++rt) {
         const int row = i0 + rt * 8 + r;
-        const int ext = (!p.sigma_lower || row < BASE) ? ld : BASE + 3 * ((row - BASE) / 3) + 3;   // columns valid in this row
+        // lower mode: a feature row is taken up to its diagonal only (what ekf_mirror_lower_kernel would copy above it is
+        // exactly what is read through the mirror image here, so results do not depend on whether a mirror pass ran)
+        const int ext = (!p.sigma_lower || row < BASE) ? ld : row + 1;
 #pragma unroll
         for (int jb = 0; jb < NB; ++jb) {
             int a = jb * 8 + 2 * q;

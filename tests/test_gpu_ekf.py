@@ -362,3 +362,30 @@ def test_long_run_keeps_sigma_symmetric_psd_and_paths_agree(cuda, n):
     assert rel(st0["P"], st1["P"]) <= 4 * TOL and rel(st0["mu"], st1["mu"]) <= 4 * TOL
     for b in batches:
         b.close()
+
+
+def test_sigma_reads_between_process_and_update_do_not_change_the_result(cuda):
+    """Lower mode: process() leaves the feature rows of a symmetric filter complete only up to the diagonal; a reader in
+    between (get_state, check_sigma) makes the batch mirror the matrix first.  Either way the update must produce the
+    same bits, and get_state must return a symmetric-to-rounding, complete matrix that matches the oracle."""
+    import torch
+    from ekf_vio_b200 import workload
+    F, n, steps = 6, 30, 4
+    uv, meas, _ = workload.ekf_streams(0, F, n, steps)
+    R = np.tile(np.array([1e-5, 0, 0, 1e-5]), (F, n, 1)); ps = np.ones((F, n), np.uint8)
+    a, b = make_batch(F, n), make_batch(F, n)
+    orc = O.OracleFilter(); orc.add_features(uv[0])
+    for x in (a, b):
+        x.add_features_h(np.full(F, n, np.int32), uv)
+    neg = torch.zeros(F, dtype=torch.int32, device="cuda"); asym = torch.zeros(F, dtype=torch.float64, device="cuda")
+    for s in range(steps):
+        a.process(0.05); b.process(0.05); orc.process(0.05)
+        mid = b.get_state()                                   # forces the mirror pass on b only
+        b.check_sigma(neg, asym)
+        assert rel(mid["P"][0], orc.state()["P"]) <= TOL
+        assert float(asym.max()) <= 1e-12                     # F Sigma F' is symmetric to rounding (own 3x3 blocks are computed twice)
+        a.update(*torch_inputs(meas[s], R, ps)); b.update(*torch_inputs(meas[s], R, ps)); orc.update(meas[s, 0], R[0], ps[0])
+        sa, sb = a.get_state(), b.get_state()
+        for key in ("mu", "feat", "P"):
+            np.testing.assert_array_equal(sa[key], sb[key], err_msg=f"{key} step {s}")
+        assert rel(sa["P"][0], orc.state()["P"]) <= TOL

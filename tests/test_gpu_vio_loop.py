@@ -30,9 +30,7 @@ def host_composed(frames, K9, dts, num_features, thr=50, min_dist=30, kill_pad=1
         if t > 0:
             st = batch.get_state(want_P=False)                      # klt_last / nfeat: untouched by process()
             batch.process(torch.from_numpy(dts[t]).cuda())
-            # (the predicted features are read without asking for Sigma: a Sigma read between process() and update() would
-            # make the batch complete the matrix first and the update would then run from the other triangle — same
-            # result to rounding, but this test wants the loop bit for bit)
+            # (state only: no need to make the batch complete Sigma between process() and update())
             h_mu = np.zeros((S, 22)); h_feat = np.zeros((S, num_features, 3))
             batch.read_mu_h(h_mu, h_feat)
             n = st["nfeat"]
