@@ -35,3 +35,22 @@ def test_flop_and_byte_accounting_matches_survey():
     assert abs(bench.flops_per_filter_step(50) / 1e6 - 17.24) < 0.02
     assert abs(bench.flops_per_filter_step(300) / 1e6 - 2822) < 2
     assert bench.KLT_BYTES_WITH_DERIVS == 408000 + 100800 + 1632000 and bench.KLT_BYTES_NO_DERIVS == 408000 + 100800
+
+
+def test_vio_sequences_are_pure_functions_of_the_sequence_index():
+    """Sharding the frame loop over ranks must not change any sequence: frames depend on the global index only."""
+    from ekf_vio_b200 import workload
+    a = workload.vio_sequences(0, 4, 3, 160, 120)
+    b = workload.vio_sequences(2, 2, 3, 160, 120)
+    assert a.shape == (3, 4, 120, 160) and a.dtype == np.uint8
+    np.testing.assert_array_equal(a[:, 2:], b)
+    assert (a[0, 0] != a[1, 0]).any() and a.std() > 5         # the camera pans over a textured scene
+
+
+def test_frame_oracle_scales_K_like_the_reference():
+    """Frame.cpp:24-30: fx, cx, fy, cy divided by inv_scale, K(2,2) = 1."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import frame_oracle as FO
+    K = FO.scale_K([400.0, 0, 320.0, 0, 410.0, 240.0, 0, 0, 1.0], 4)
+    np.testing.assert_allclose(K, np.array([[100.0, 0, 80.0], [0, 102.5, 60.0], [0, 0, 1.0]], np.float32))
