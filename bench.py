@@ -63,7 +63,8 @@ def ekf_config(F: int, n: int, world: int) -> dict:
     """The workload both arms (ours and --impl reference) are measured on: BASELINE.json configs[2]."""
     return {"workload": f"batched EKF: {F} filters/GPU x (22+3*{n})-dim state, process(dt)+update(all {n} measured) per step, dt={DT}",
             "l2": "working set per step (two 1.0 GB Sigma buffers + 1.3 GB gain panels at 4096 filters) is larger than the 126 MB L2; no flush needed",
-            "filters_total": F * world, "features": n}
+            "filters_total": F * world, "features": n,
+            "update_form": "library default: Joseph form of symmetric filters evaluated as Sigma - Z Z' (EKFVIO_FLAG_LITERAL_JOSEPH = term by term)"}
 
 
 KLT_BYTES_WITH_DERIVS = 2_140_800   # SURVEY.md §8d, 640x480 levels 0-3, read once + write levels 1-3 + int16x2 derivatives

@@ -32,11 +32,10 @@ constexpr int LDK = KC + 4;         // K-phase chunk: [JT*8][LDK]
 constexpr int BS_DOUBLES = (JT * 8 * LDK > KC * LDG) ? JT * 8 * LDK : KC * LDG;
 
 template <int NW>
-__global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const double* __restrict__ Pin, double* __restrict__ Pout, int only_asym) {
+__device__ __forceinline__ void joseph_tiled_filter(const EkfPtrs& p, const double* __restrict__ Pin, double* __restrict__ Pout, int f) {
     extern __shared__ __align__(16) double Bs_all[];   // NST * BS_DOUBLES
     __shared__ int s_idx[256];
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (only_asym && p.asym[f] == 0) return;              // symmetric filters went to ekf_joseph_sym
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = p.nfeat[f], N = BASE + 3 * n, m = p.m[f];
     const int ld = p.ldP, ldK = p.ldK;
     const double* Pi = Pin + (size_t)f * ld * ld;
@@ -140,6 +139,17 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const 
                     }
                 }
         }
+    }
+}
+
+// Persistent launch: a CTA walks over the filters and serves those the symmetric kernels leave out (only_asym) —
+// when there are none, the whole launch is a few flag reads.
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const double* __restrict__ Pin, double* __restrict__ Pout, int only_asym) {
+    for (int f = blockIdx.x; f < p.F; f += gridDim.x) {
+        if (only_asym && p.asym[f] == 0) continue;        // symmetric filters went to ekf_joseph_sym
+        joseph_tiled_filter<NW>(p, Pin, Pout, f);
+        __syncthreads();                                  // shared memory is reused by the next filter
     }
 }
 
@@ -308,7 +318,7 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
 // quaternion renormalisation.  One warp per 16-row strip, the strip lives in registers through both
 // triangular solves (right-looking over 8-wide column blocks).
 template <int NW, int NB>
-__global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const double* __restrict__ Pin, const double* __restrict__ Rin) {
+__device__ __forceinline__ void solve_tiled_filter(const EkfPtrs& p, const double* __restrict__ Pin, const double* __restrict__ Rin, int f) {
     extern __shared__ __align__(16) double smg[];
     constexpr int NT = NB * (NB + 1) / 2;
     double* Ls = smg;                      // NT tiles
@@ -318,10 +328,9 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
     int* s_idx = reinterpret_cast<int*>(s_y + NB * 8);   // NB*8
     __shared__ short s_inv[NW * 16];
 
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m = p.m[f];
     if (m == 0) return;
-    if (p.asym[f] == 0 && !(p.flags & EKFVIO_FLAG_LITERAL_JOSEPH)) return;   // symmetric filters: ekf_fwd_tiled
 #ifdef EKFVIO_PROFILE_CLOCKS
     long long t_prev = clock64();
 #endif
@@ -537,6 +546,15 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
     }
 }
 
+template <int NW, int NB>
+__global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const double* __restrict__ Pin, const double* __restrict__ Rin) {
+    for (int f = blockIdx.x; f < p.F; f += gridDim.x) {   // persistent: see ekf_joseph_tiled
+        if (p.asym[f] == 0 && !(p.flags & EKFVIO_FLAG_LITERAL_JOSEPH)) continue;   // symmetric filters: ekf_fwd_tiled
+        solve_tiled_filter<NW, NB>(p, Pin, Rin, f);
+        __syncthreads();
+    }
+}
+
 // Symmetric Sigma and R (the normal case): the Joseph form (I-KH) Sigma (I-KH)' + K R K' equals
 // Sigma - Z Z' with Z = Sigma(:,idx) inv(L)', S = L L', and K y = Z (inv(L) y).  Only the forward
 // substitution is needed; neither K nor W = Sigma(:,idx) - K S is formed.  Two CTAs per filter (six
@@ -680,7 +698,7 @@ cudaError_t launch_gain_tiled_t(int which, const EkfPtrs& p, const double* Pin, 
             configured_f = true;
         }
         if (!(p.flags & EKFVIO_FLAG_LITERAL_JOSEPH)) ekf_fwd_tiled<NWF, NB><<<dim3(p.F, 2), NWF * 32, sm_f, st>>>(p, Pin);
-        ekf_solve_tiled<NW, NB><<<p.F, NW * 32, sm_s, st>>>(p, Pin, R);
+        ekf_solve_tiled<NW, NB><<<p.F < 148 ? p.F : 148, NW * 32, sm_s, st>>>(p, Pin, R);
     }
     return cudaGetLastError();
 }
@@ -931,9 +949,10 @@ cudaError_t launch_joseph_tiled(const EkfPtrs& p, const double* Pin, double* Pou
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    if (strips <= 8) ekf_joseph_tiled<8><<<p.F, 8 * 32, sm, st>>>(p, Pin, Pout, only_asym);
-    else if (strips <= 11) ekf_joseph_tiled<11><<<p.F, 11 * 32, sm, st>>>(p, Pin, Pout, only_asym);
-    else ekf_joseph_tiled<16><<<p.F, 16 * 32, sm, st>>>(p, Pin, Pout, only_asym);
+    const int grid = p.F < 148 ? p.F : 148;                 // persistent CTAs (one per SM)
+    if (strips <= 8) ekf_joseph_tiled<8><<<grid, 8 * 32, sm, st>>>(p, Pin, Pout, only_asym);
+    else if (strips <= 11) ekf_joseph_tiled<11><<<grid, 11 * 32, sm, st>>>(p, Pin, Pout, only_asym);
+    else ekf_joseph_tiled<16><<<grid, 16 * 32, sm, st>>>(p, Pin, Pout, only_asym);
     return cudaGetLastError();
 }
 
