@@ -75,6 +75,7 @@ SIGNATURES = {
     "ekfvio_batch_max_features": (c_int, [c_void_p]),
     "ekfvio_batch_reset": (c_int, [c_void_p, c_void_p]),
     "ekfvio_batch_add_features": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "ekfvio_batch_remove_features": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ekfvio_batch_process": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ekfvio_batch_process_dt": (c_int, [c_void_p, c_double, c_void_p]),
     "ekfvio_batch_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -200,6 +201,10 @@ class EkfBatch:
 
     def linearize(self, dt, F_out):
         _check(lib.ekfvio_batch_linearize(self._h, _ptr(dt), _ptr(F_out), _stream()))
+
+    def remove_features(self, remove=None):
+        """remove: uint8 cuda [F, nmax] (non-zero = marginalise the feature out) or None = the features flagged as lost."""
+        _check(lib.ekfvio_batch_remove_features(self._h, _ptr(remove), _stream()))
 
     def check_sigma(self, neg, asym):
         _check(lib.ekfvio_batch_check_sigma(self._h, _ptr(neg), _ptr(asym), _stream()))

@@ -172,6 +172,17 @@ int ekfvio_batch_add_features(ekfvio_batch* b, const int* d_k, const double* d_u
     return 0;
 }
 
+int ekfvio_batch_remove_features(ekfvio_batch* b, const uint8_t* d_remove, void* stream) {
+    CU(cudaSetDevice(b->device));
+    if (b->nmax == 0) return 0;
+    if (ensure_full_sigma(b, (cudaStream_t)stream)) return 1;
+    b->state_ev_valid = false;
+    CU(launch_remove_features(ptrs(b), b->d_P[b->cur], b->d_P[b->cur ^ 1], d_remove, (cudaStream_t)stream));
+    b->cur ^= 1;
+    b->launches += 1;
+    return 0;
+}
+
 int ekfvio_batch_process(ekfvio_batch* b, const double* d_dt, void* stream) {
     CU(cudaSetDevice(b->device));
     if (ensure_full_sigma(b, (cudaStream_t)stream)) return 1;     // (two process() calls in a row)

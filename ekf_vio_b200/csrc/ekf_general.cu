@@ -714,6 +714,47 @@ __global__ void ekf_add_features_kernel(EkfPtrs p, double* P0, const int* __rest
     if (tid == 0) p.nfeat[f] = n0 + k;
 }
 
+// Feature removal (absent from the reference, which flags lost features — TightlyCoupledEKF.cpp:524-528 —
+// but never deletes them): the flagged features are marginalised out, i.e. their mean entries and their rows and columns
+// of Sigma are deleted and the survivors close ranks in order.  remove == nullptr: use the delete flags.
+__global__ void __launch_bounds__(256) ekf_remove_features_kernel(EkfPtrs p, const double* __restrict__ Pin, double* __restrict__ Pout,
+                                                                  const uint8_t* __restrict__ remove) {
+    extern __shared__ int keep[];              // [nmax] old index of surviving feature k'
+    __shared__ int s_n1;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int n0 = p.nfeat[f], ld = p.ldP;
+    const uint8_t* rm = (remove ? remove : p.dflags) + (size_t)f * p.nmax;
+    if (tid == 0) {
+        int k = 0;
+        for (int i = 0; i < n0; ++i) if (!rm[i]) keep[k++] = i;
+        s_n1 = k;
+    }
+    __syncthreads();
+    const int n1 = s_n1, N1 = BASE + 3 * n1;
+    const double* Pi = Pin + (size_t)f * ld * ld;
+    double* Po = Pout + (size_t)f * ld * ld;
+    for (int e = tid; e < N1 * N1; e += blockDim.x) {
+        const int i = e / N1, j = e - i * N1;
+        const int oi = i < BASE ? i : BASE + 3 * keep[(i - BASE) / 3] + (i - BASE) % 3;
+        const int oj = j < BASE ? j : BASE + 3 * keep[(j - BASE) / 3] + (j - BASE) % 3;
+        Po[(size_t)i * ld + j] = Pi[(size_t)oi * ld + oj];
+    }
+    // state vectors: survivors move down (keep[k] >= k, ascending: staged through registers so that no slot is
+    // overwritten before it has been read)
+    double* feat = p.feat + (size_t)f * p.nmax * 3;
+    double* kl = p.klt_last + (size_t)f * p.nmax * 2;
+    uint8_t* fl = p.dflags + (size_t)f * p.nmax;
+    for (int k0 = 0; k0 < n0; k0 += blockDim.x) {
+        const int k = k0 + tid;
+        double a = 0, b = 0, c = 0, u = 0, v = 0;
+        if (k < n1) { const int o = keep[k]; a = feat[3 * o]; b = feat[3 * o + 1]; c = feat[3 * o + 2]; u = kl[2 * o]; v = kl[2 * o + 1]; }
+        __syncthreads();
+        if (k < n0) { feat[3 * k] = a; feat[3 * k + 1] = b; feat[3 * k + 2] = c; kl[2 * k] = u; kl[2 * k + 1] = v; fl[k] = 0; }
+        __syncthreads();
+    }
+    if (tid == 0) p.nfeat[f] = n1;
+}
+
 __global__ void ekf_check_sigma_kernel(EkfPtrs p, const double* P0, int* neg, double* asym) {  // checkSigma (:699-714)
     const int f = blockIdx.x, tid = threadIdx.x;
     const int n = p.nfeat[f], N = BASE + 3 * n, ld = p.ldP;
@@ -883,6 +924,11 @@ cudaError_t launch_reset(const EkfPtrs& p, double* P0, cudaStream_t st) {
     ekf_reset_kernel<<<p.F, 128, 0, st>>>(p, P0);
     return cudaGetLastError();
 }
+cudaError_t launch_remove_features(const EkfPtrs& p, const double* Pin, double* Pout, const uint8_t* remove, cudaStream_t st) {
+    ekf_remove_features_kernel<<<p.F, 256, (size_t)(p.nmax > 0 ? p.nmax : 1) * sizeof(int), st>>>(p, Pin, Pout, remove);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_add_features(const EkfPtrs& p, double* P0, const int* ks, const double* uv, int kmax, cudaStream_t st) {
     ekf_add_features_kernel<<<p.F, 256, 0, st>>>(p, P0, ks, uv, kmax);
     return cudaGetLastError();

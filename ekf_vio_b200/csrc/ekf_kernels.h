@@ -31,6 +31,7 @@ cudaError_t launch_joseph_general(const EkfPtrs& p, const double* Pin, double* P
 size_t gain_general_smem_doubles(int mmax);
 cudaError_t launch_reset(const EkfPtrs& p, double* P0, cudaStream_t st);
 cudaError_t launch_add_features(const EkfPtrs& p, double* P0, const int* ks, const double* uv, int kmax, cudaStream_t st);
+cudaError_t launch_remove_features(const EkfPtrs& p, const double* Pin, double* Pout, const uint8_t* remove, cudaStream_t st);
 cudaError_t launch_check_sigma(const EkfPtrs& p, const double* P0, int* neg, double* asym, cudaStream_t st);
 cudaError_t launch_fill_dt(double* dts, double dt, int F, cudaStream_t st);
 cudaError_t launch_pack_P(const double* P0, double* dense, int ld, int Nmax, int F, int to_dense, cudaStream_t st);

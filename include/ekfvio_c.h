@@ -80,6 +80,12 @@ int ekfvio_batch_reset(ekfvio_batch* b, void* stream);
  * reported through status bit2 for that filter (nothing is appended to it). */
 int ekfvio_batch_add_features(ekfvio_batch* b, const int* d_k, const double* d_uv, int kmax, void* stream);
 
+/* Feature removal.  The reference only flags lost features (TightlyCoupledEKF.cpp:524-528, Feature::delete_flag)
+ * and never deletes them; this marginalises features out of the state: mean entries and rows/columns of Sigma are deleted, the
+ * survivors keep their order.  d_remove[F][nmax] non-zero = remove; NULL = remove the features whose delete flag the updates
+ * have set.  Not called by anything in the library (the frame loop keeps the reference's behaviour); parity unpinned. */
+int ekfvio_batch_remove_features(ekfvio_batch* b, const uint8_t* d_remove, void* stream);
+
 /* process(dt) (TightlyCoupledEKF.cpp:96-121): numericallyLinearizeProcess, convolveFeature on
  * every feature, convolveBaseState, Sigma = F Sigma F' + Q, prune.  d_dt[F]. */
 int ekfvio_batch_process(ekfvio_batch* b, const double* d_dt, void* stream);

@@ -389,3 +389,51 @@ def test_sigma_reads_between_process_and_update_do_not_change_the_result(cuda):
         for key in ("mu", "feat", "P"):
             np.testing.assert_array_equal(sa[key], sb[key], err_msg=f"{key} step {s}")
         assert rel(sa["P"][0], orc.state()["P"]) <= TOL
+
+
+@pytest.mark.parametrize("n", [12, 70])
+def test_feature_removal_marginalises_and_filter_continues(cuda, n):
+    """SURVEY.md §8f-4 (no counterpart in the reference: parity unpinned).  Removing features must delete their mean entries
+    and their rows/columns of Sigma, keep the survivors in order, and leave a filter that continues like an oracle
+    started from the reduced state — on the tiled (n = 12) and the blocked large-state path (n = 70)."""
+    import torch
+    rng = np.random.default_rng(100 + n)
+    uv = rng.uniform(-0.9, 0.9, (n, 2))
+    orc = O.OracleFilter(); orc.add_features(uv)
+    b = make_batch(2, n)
+    b.add_features_h(np.array([n, n - 3], np.int32), np.stack([uv, uv]))
+    mu = orc.state()["mu"]; mu[7:10] = [0.1, -0.05, 0.02]; mu[10:13] = [0.02, 0.03, -0.01]
+    st = orc.state(); orc.set_state(mu=mu, feat=st["feat"], Pm=st["P"])
+    b.set_state(mu=np.stack([mu, mu]))
+    R = np.tile(np.array([1e-5, 0, 0, 1e-5]), (2, n, 1))
+    passed = np.ones((2, n), np.uint8); passed[:, [1, 4, n - 1]] = 0          # three features are lost in this update
+    orc.process(0.05); b.process(0.05)
+    z = np.repeat((orc.state()["feat"][:, :2] + rng.normal(0, 1e-3, (n, 2)))[None], 2, 0)
+    orc.update(z[0], R[0], passed[0]); b.update(*torch_inputs(z, R, passed))
+    before = gpu_state(b, 0)
+    assert before["flags"][[1, 4, n - 1]].all()
+    b.remove_features()                                                       # NULL: the features flagged as lost
+    after = gpu_state(b, 0)
+    keepf = np.array([i for i in range(n) if i not in (1, 4, n - 1)])
+    keeps = np.concatenate([np.arange(22), (22 + 3 * keepf[:, None] + np.arange(3)).ravel()])
+    assert after["n"] == n - 3
+    np.testing.assert_array_equal(after["feat"], before["feat"][keepf])
+    np.testing.assert_array_equal(after["P"], before["P"][np.ix_(keeps, keeps)])
+    np.testing.assert_array_equal(after["mu"], before["mu"])
+    assert not after["flags"].any()
+    full = b.get_state()
+    np.testing.assert_array_equal(full["klt_last"][0, :n - 3], z[0][keepf])
+    # explicit mask on top: remove one more feature of filter 0 only; filter 1 (n - 3 features, none flagged... ) untouched
+    mask = np.zeros((2, n), np.uint8); mask[0, 2] = 1
+    n1_before = int(full["nfeat"][1])
+    b.remove_features(torch.from_numpy(mask).cuda())
+    assert gpu_state(b, 0)["n"] == n - 4 and gpu_state(b, 1)["n"] == n1_before
+    # the reduced filter continues like an oracle restarted from the reduced state
+    cur = gpu_state(b, 0)
+    orc2 = O.OracleFilter(); orc2.add_features(np.zeros((n - 4, 2)))
+    orc2.set_state(mu=cur["mu"], feat=cur["feat"], Pm=cur["P"])
+    R2 = R[:, :n - 4]; p2 = np.ones((2, n), np.uint8)
+    orc2.process(0.05); b.process(0.05)
+    z2 = np.zeros((2, n, 2)); z2[:, :n - 4] = orc2.state()["feat"][:, :2] + rng.normal(0, 1e-3, (n - 4, 2))
+    orc2.update(z2[0, :n - 4], R2[0], np.ones(n - 4, np.uint8)); b.update(*torch_inputs(z2, R, p2))
+    assert_close(gpu_state(b, 0), orc2.state(), what="after removal")
