@@ -75,6 +75,7 @@ SIGNATURES = {
     "ekfvio_batch_max_features": (c_int, [c_void_p]),
     "ekfvio_batch_reset": (c_int, [c_void_p, c_void_p]),
     "ekfvio_batch_add_features": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "ekfvio_batch_graph_replayed": (c_int, [c_void_p, c_int]),
     "ekfvio_batch_remove_features": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ekfvio_batch_process": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ekfvio_batch_process_dt": (c_int, [c_void_p, c_double, c_void_p]),
@@ -417,16 +418,17 @@ def frame_resize(src, inv_scale: int, dst=None):
 
 
 class VioParams(C.Structure):
-    _fields_ = [("num_features", c_int), ("fast_threshold", c_int), ("min_new_feature_dist", c_int), ("use_cuda_graph", c_int)]
+    _fields_ = [("num_features", c_int), ("fast_threshold", c_int), ("min_new_feature_dist", c_int), ("remove_lost_features", c_int),
+                ("use_cuda_graph", c_int)]
 
 
 class VioLoop:
     """EKFVIO::addFrame (EKFVIO.cpp:139-196) for S sequences on the device: process -> KLT -> update -> replenish."""
 
     def __init__(self, num_sequences: int, width: int, height: int, num_features: int = 100, fast_threshold: int = 50, min_dist: int = 30,
-                 device: int = 0, ekf_params: Params | None = None, use_cuda_graph: bool = True):
+                 device: int = 0, ekf_params: Params | None = None, use_cuda_graph: bool = True, remove_lost_features: bool = False):
         self._h = c_void_p()
-        vp = VioParams(num_features, fast_threshold, min_dist, int(use_cuda_graph))
+        vp = VioParams(num_features, fast_threshold, min_dist, int(remove_lost_features), int(use_cuda_graph))
         ep = ekf_params if ekf_params is not None else default_params()
         _check(lib.ekfvio_vio_create(C.byref(self._h), device, num_sequences, width, height, C.addressof(ep), None, C.addressof(vp)))
         self.S, self.num_features = num_sequences, num_features

@@ -172,6 +172,13 @@ int ekfvio_batch_add_features(ekfvio_batch* b, const int* d_k, const double* d_u
     return 0;
 }
 
+int ekfvio_batch_graph_replayed(ekfvio_batch* b, int sigma_buffer_flips) {
+    if (!b || sigma_buffer_flips < 0) return fail_msg("ekfvio_batch_graph_replayed: bad arguments");
+    b->cur ^= sigma_buffer_flips & 1;
+    b->state_ev_valid = b->inputs_ev_valid = false;
+    return 0;
+}
+
 int ekfvio_batch_remove_features(ekfvio_batch* b, const uint8_t* d_remove, void* stream) {
     CU(cudaSetDevice(b->device));
     if (b->nmax == 0) return 0;

@@ -108,6 +108,7 @@ void ekfvio_vio_default_params(ekfvio_vio_params* p) {
     p->num_features = 100;           // Params.h:46
     p->fast_threshold = 50;          // Params.h:24
     p->min_new_feature_dist = 30;    // Params.h:43
+    p->remove_lost_features = 0;     // the reference never removes features
     p->use_cuda_graph = 1;
 }
 
@@ -184,6 +185,7 @@ static int enqueue_frame(ekfvio_vio* v, const uint8_t* d_frames, int pitch, cons
         vio_measurement_kernel<<<S, 128, 0, st>>>(v->d_measured, v->d_cov, v->d_passed, view.d_nfeat, nmax, v->d_z, v->d_R, v->d_pass);
         CU(cudaGetLastError());
         RC(ekfvio_batch_update(v->ekf, v->d_z, v->d_R, v->d_pass, stream));                          // EKFVIO.cpp:217
+        if (v->prm.remove_lost_features) RC(ekfvio_batch_remove_features(v->ekf, nullptr, stream));   // (not in the reference)
         v->launches += 2;
     }
     // replenishFeatures (EKFVIO.cpp:172 / :153)
@@ -226,7 +228,9 @@ int ekfvio_vio_add_frame(ekfvio_vio* v, const uint8_t* d_frames, int pitch, cons
     CU(cudaMemcpy2DAsync(v->d_frames_in, v->width, d_frames, pitch, v->width, (size_t)v->height * v->S, cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(v->d_K_in, d_K9, (size_t)v->S * 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(v->d_dt_in, d_dt, (size_t)v->S * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    bool captured_now = false;                                   // (the capture pass already did the host-side bookkeeping)
     if (!v->graph[parity]) {
+        captured_now = true;
         const long long before = ekfvio_vio_launch_count(v);
         const int frames = v->frames, slot = v->cur_slot;
         CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -243,6 +247,7 @@ int ekfvio_vio_add_frame(ekfvio_vio* v, const uint8_t* d_frames, int pitch, cons
         if (e != cudaSuccess) return ekfvio::fail("cudaGraphInstantiate", e);
     }
     CU(cudaGraphLaunch(v->graph[parity], st));
+    if (!captured_now) RC(ekfvio_batch_graph_replayed(v->ekf, v->prm.remove_lost_features ? 3 : 2));   // process + update (+ remove) flip the Sigma buffers
     if (legacy) { CU(cudaEventRecord(v->ev_out, st)); CU(cudaStreamWaitEvent(caller, v->ev_out, 0)); }
     v->launches += v->graph_launches[parity];
     v->cur_slot ^= 1;

@@ -80,6 +80,11 @@ int ekfvio_batch_reset(ekfvio_batch* b, void* stream);
  * reported through status bit2 for that filter (nothing is appended to it). */
 int ekfvio_batch_add_features(ekfvio_batch* b, const int* d_k, const double* d_uv, int kmax, void* stream);
 
+/* For callers that capture these entry points into a CUDA graph (as ekfvio_vio_add_frame does) and replay it: a replay runs the
+ * kernels but none of the host-side bookkeeping of the calls it stands for.  Tell the batch how many Sigma buffer flips the
+ * replayed sequence contains (process, update and remove_features flip once each); its copy-stream events are invalidated. */
+int ekfvio_batch_graph_replayed(ekfvio_batch* b, int sigma_buffer_flips);
+
 /* Feature removal.  The reference only flags lost features (TightlyCoupledEKF.cpp:524-528, Feature::delete_flag)
  * and never deletes them; this marginalises features out of the state: mean entries and rows/columns of Sigma are deleted, the
  * survivors keep their order.  d_remove[F][nmax] non-zero = remove; NULL = remove the features whose delete flag the updates
@@ -279,6 +284,8 @@ typedef struct ekfvio_vio_params {
     int num_features;          /* NUM_FEATURES, Params.h:46 (100) — also the filters' feature capacity */
     int fast_threshold;        /* FAST_THRESHOLD, Params.h:24 (50) */
     int min_new_feature_dist;  /* MIN_NEW_FEATURE_DIST, Params.h:43 (30) */
+    int remove_lost_features;  /* 0 (reference behaviour: lost features stay in the state for ever); 1: features whose track was lost in
+                                * this frame's update are marginalised out (ekfvio_batch_remove_features) before replenishment */
     int use_cuda_graph;        /* 1: after the first frames the per-frame launch sequence is captured once per pyramid-slot
                                 * parity and replayed as a CUDA graph (one launch advances all sequences by a frame) */
 } ekfvio_vio_params;

@@ -120,3 +120,39 @@ def test_first_frame_only_replenishes(cuda):
         assert (st["feat"][s, :len(px), 2] == 2.0).all()                                        # inverse of DEFAULT_POINT_DEPTH 0.5
     assert (st["mu"][:, 3] == 1.0).all()
     loop.close()
+
+
+def test_frame_loop_with_feature_removal_keeps_tracking(cuda):
+    """remove_lost_features = 1 (not in the reference): features whose track is lost leave the state and replenishment
+    refills it; without it (the reference's behaviour) lost features pile up and the state only ever grows."""
+    import torch
+    from ekf_vio_b200 import capi, workload
+    S, T, w, h, NF = 2, 9, 320, 240, 30
+    frames = workload.vio_sequences(3, S, T, w, h, speed=6.0)           # fast pan: features leave through the kill-pad
+    K9 = np.zeros((S, 9), np.float32); K9[:, 0] = 200.0; K9[:, 4] = 200.0; K9[:, 8] = 1.0
+    dK = torch.from_numpy(K9).cuda(); ddt = torch.full((S,), 0.05, dtype=torch.float64, device="cuda")
+    out = {}
+    for rm in (False, True):
+        loop = capi.VioLoop(S, w, h, num_features=NF, remove_lost_features=rm)
+        for t in range(T):
+            loop.add_frame(torch.from_numpy(frames[t]).cuda(), dK, None if t == 0 else ddt)
+        out[rm] = loop.filters.get_state(want_P=False)
+        loop.close()
+    # graph replay and eager execution must agree bit for bit with removal on as well (T = 9 and T = 10: an odd and an even
+    # number of replays — removal makes a frame flip the Sigma buffers an odd number of times)
+    for T2 in (9, 10):
+        frames2 = workload.vio_sequences(3, S, T2, w, h, speed=6.0)
+        res = []
+        for graph in (True, False):
+            loop = capi.VioLoop(S, w, h, num_features=NF, remove_lost_features=True, use_cuda_graph=graph)
+            for t in range(T2):
+                loop.add_frame(torch.from_numpy(frames2[t]).cuda(), dK, None if t == 0 else ddt)
+            res.append(loop.filters.get_state())
+            loop.close()
+        for key in ("nfeat", "mu", "feat", "P", "klt_last"):
+            np.testing.assert_array_equal(res[0][key], res[1][key], err_msg=f"{key} T={T2}")
+    keep, drop = out[False], out[True]
+    assert keep["flags"].any(), "the pan was meant to lose some features"
+    assert not drop["flags"][:, :].any() or (drop["flags"].sum() < keep["flags"].sum())
+    assert (drop["status"] == 0).all() and np.isfinite(drop["mu"]).all()
+    assert (drop["nfeat"] <= NF).all() and (drop["nfeat"] > 0).all()
