@@ -133,7 +133,9 @@ int ekfvio_batch_check_sigma_h(ekfvio_batch* b, int* h_neg_diag, double* h_max_a
 int ekfvio_batch_read_mu_h(ekfvio_batch* b, double* h_mu, double* h_feat, void* stream);
 
 /* Device pointers of the live state, for zero-copy consumers (valid until destroy; P points at
- * the current buffer and may change after each process/update — query again). */
+ * the current buffer and may change after each process/update/remove_features — query again.  Between a process() and the
+ * update() that follows, a batch on the reduced update path holds the feature rows of Sigma only up to the diagonal; this
+ * call (like get_state and check_sigma) completes the matrix first, on the stream of that process()). */
 typedef struct ekfvio_batch_view {
     double* d_mu;       /* [F][22] */
     double* d_feat;     /* [F][nmax][3] */
