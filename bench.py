@@ -502,8 +502,8 @@ def run_reference(args, result_out=sys.stdout):
     kl = cpu_baseline_klt(pairs=8, reps=max(1, min(K, 5)))
     line = {
         "impl": "reference", "metric": "EKF filter-steps/s", "value": v, "unit": "filter-steps/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
-        "ms_per_step": 1e3 * args.filters / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {**ekf_config(args.filters, N_FEAT, 1),
+        "ms_per_step": 1e3 * args.filters * max(args.gpus, 1) / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {**ekf_config(args.filters, N_FEAT, max(args.gpus, 1)),
                    "note": "reference EKF cannot be compiled here (Eigen/ROS/OpenCV C++ headers absent): FP64 oracle port timed on a bounded sample"},
         "cpu_baseline": {**t, "value": v},
         "e2e": {"value": v, "unit": "filter-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
