@@ -119,6 +119,7 @@ SIGNATURES = {
     "ekfvio_vio_frame_count": (c_int, [c_void_p]),
     "ekfvio_vio_launch_count": (C.c_longlong, [c_void_p]),
     "ekfvio_frame_resize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "ekfvio_frame_resize_h": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int]),
     "ekfvio_batch_enable_timing": (c_int, [c_void_p, c_int]),
     "ekfvio_batch_get_timing": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ekfvio_measure_fp64_peak": (c_int, [c_int, C.POINTER(c_double), C.POINTER(c_double)]),
@@ -461,3 +462,12 @@ class VioLoop:
             self.close()
         except Exception:
             pass
+
+
+def frame_resize_h(src: np.ndarray, inv_scale: int) -> np.ndarray:
+    """Host arrays: uint8 [batch,H,W] -> [batch,H//s,W//s] (Frame::Frame's cv::resize, Frame.cpp:19)."""
+    src = np.ascontiguousarray(src, np.uint8)
+    batch, h, w = src.shape
+    dst = np.zeros((batch, h // inv_scale, w // inv_scale), np.uint8)
+    _check(lib.ekfvio_frame_resize_h(_ptr(src), w, w, h, batch, int(inv_scale), _ptr(dst), int(dst.shape[2])))
+    return dst

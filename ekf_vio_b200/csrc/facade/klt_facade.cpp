@@ -81,3 +81,26 @@ Eigen::Matrix2f KLTTracker::estimateUncertaintySampleBased(const Frame&, cv::Poi
     std::fprintf(stderr, "estimateUncertaintySampleBased: dead code in the reference (KLTTracker.cpp:111-175), not provided\n");
     std::abort();
 }
+
+
+// ---- Frame::Frame (Frame.cpp:15-41): resize on the device, scale K ---------------------------------------------------
+Frame::Frame(int inv_scale, const cv::Mat& full_img, const double k[9], const std::vector<double>& d, ros::Time _t) : t(_t) {
+    if (inv_scale <= 0 || !full_img.data || full_img.cols / inv_scale <= 0 || full_img.rows / inv_scale <= 0) {
+        std::fprintf(stderr, "Frame: bad image or inverse scale\n");
+        std::abort();
+    }
+    const int dw = full_img.cols / inv_scale, dh = full_img.rows / inv_scale;
+    std::vector<uint8_t> scaled((size_t)dw * dh);
+    if (ekfvio_frame_resize_h(full_img.data, (int)full_img.step, full_img.cols, full_img.rows, 1, inv_scale, scaled.data(), dw)) {
+        std::fprintf(stderr, "Frame: %s\n", ekfvio_last_error());
+        std::abort();
+    }
+    img = cv::Mat::copyOf(dh, dw, scaled.data(), (size_t)dw);
+    K.setZero();
+    K(0, 0) = (float)(k[0] / inv_scale);
+    K(0, 2) = (float)(k[2] / inv_scale);
+    K(1, 1) = (float)(k[4] / inv_scale);
+    K(1, 2) = (float)(k[5] / inv_scale);
+    K(2, 2) = 1.0f;
+    for (int i = 0; i < 5 && i < (int)d.size(); ++i) D(0, i) = (float)d[i];
+}

@@ -482,6 +482,26 @@ int ekfvio_fast_replenish_h(ekfvio_fast* f, const uint8_t* h_imgs, int pitch, in
     return 0;
 }
 
+int ekfvio_frame_resize_h(const uint8_t* h_src, int src_pitch, int src_width, int src_height, int batch, int inv_scale, uint8_t* h_dst,
+                          int dst_pitch) {
+    if (!h_src || !h_dst || src_width <= 0 || src_height <= 0 || batch <= 0 || inv_scale <= 0) return fail_msg("ekfvio_frame_resize_h: bad arguments");
+    const int dw = src_width / inv_scale, dh = src_height / inv_scale;
+    if (dw <= 0 || dh <= 0 || src_pitch < src_width || dst_pitch < dw) return fail_msg("ekfvio_frame_resize_h: bad sizes");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail_msg("ekfvio_frame_resize_h: no CUDA device (this library has no CPU path)");
+    uint8_t *d_src = nullptr, *d_dst = nullptr;
+    const size_t sb = (size_t)src_pitch * src_height * batch, db = (size_t)dst_pitch * dh * batch;
+    cudaError_t e = cudaMalloc((void**)&d_src, sb);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_dst, db);
+    if (e == cudaSuccess) e = cudaMemcpy(d_src, h_src, sb, cudaMemcpyHostToDevice);
+    int rc = 0;
+    if (e == cudaSuccess) rc = ekfvio_frame_resize(d_src, src_pitch, src_width, src_height, batch, inv_scale, d_dst, dst_pitch, nullptr);
+    if (e == cudaSuccess && rc == 0) e = cudaMemcpy(h_dst, d_dst, db, cudaMemcpyDeviceToHost);
+    cudaFree(d_src); cudaFree(d_dst);
+    if (e != cudaSuccess) return ekfvio::fail("ekfvio_frame_resize_h", e);
+    return rc;
+}
+
 long long ekfvio_fast_launch_count(const ekfvio_fast* f) { return f ? f->launches : 0; }
 
 }  // extern "C"

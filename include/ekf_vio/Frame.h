@@ -1,9 +1,11 @@
 /* Frame.h — image + intrinsics, as the tracker and Feature see it (reference
- * include/ekf_vio/Frame.h:24-43, Frame.cpp:15-55).  The resizing constructor (cv::resize,
- * Frame.cpp:19) is the caller's business here (SURVEY.md §8f "next"): construct from an already
- * scaled 8-bit image and a K already divided by inv_scale. */
+ * include/ekf_vio/Frame.h:24-43, Frame.cpp:15-55).  Two constructors: the reference's resizing one
+ * (Frame.cpp:15-41: cv::resize by 1/inv_scale on the device, bit-identical to OpenCV's INTER_LINEAR, K divided by
+ * inv_scale), and one that takes an already scaled 8-bit image. */
 #ifndef EKFVIO_FRAME_H_
 #define EKFVIO_FRAME_H_
+
+#include <vector>
 
 #include "compat.h"
 #include "Params.h"
@@ -25,6 +27,9 @@ public:
         K(1, 2) = (float)(k[5] / inv_scale);
         K(2, 2) = 1.0f;
     }
+    /* Frame.cpp:15-41: Frame(inv_scale, full-resolution image, CameraInfo::K, CameraInfo::D, stamp); defined in the facade
+     * library (ekfvio_frame_resize_h).  d may hold fewer than five coefficients (missing ones stay 0). */
+    Frame(int inv_scale, const cv::Mat& full_img, const double k[9], const std::vector<double>& d, ros::Time _t);
     /* Frame.cpp:44-55 */
     bool isPixelInBox(cv::Point2f px) const {
         return !(px.x < KILL_PAD || px.y < KILL_PAD || this->img.cols - px.x < KILL_PAD || this->img.rows - px.y < KILL_PAD);

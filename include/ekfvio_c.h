@@ -311,6 +311,9 @@ long long ekfvio_vio_launch_count(const ekfvio_vio* v);
  * with the caller.  Asynchronous on `stream`. */
 int ekfvio_frame_resize(const uint8_t* d_src, int src_pitch, int src_width, int src_height, int batch, int inv_scale, uint8_t* d_dst,
                         int dst_pitch, void* stream);
+/* The same with host buffers (upload, resize, download; synchronous) — what the Frame facade's resizing constructor calls. */
+int ekfvio_frame_resize_h(const uint8_t* h_src, int src_pitch, int src_width, int src_height, int batch, int inv_scale, uint8_t* h_dst,
+                          int dst_pitch);
 
 #ifdef __cplusplus
 }

@@ -144,6 +144,26 @@ int main(int argc, char** argv) {
         std::printf("\nklt_cov00:"); for (int i = 0; i < n; ++i) std::printf(" %.9g", unc[i](0, 0));
         std::printf("\n");
     }
+    {   // Frame::Frame with resizing (Frame.cpp:15-41): 2x takes OpenCV's area-fast path (a+b+c+d+2)>>2, 4x the 11-bit bilinear
+        const int w = 64, h = 48;
+        std::vector<uint8_t> im((size_t)w * h);
+        for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) im[(size_t)y * w + x] = (uint8_t)((x * 7 + y * 13 + (x * y) % 11) & 255);
+        const double k[9] = {400, 0, 32, 0, 410, 24, 0, 0, 1};
+        Frame f2(2, cv::Mat(h, w, im.data(), (size_t)w), k, std::vector<double>{0.1, 0.2}, ros::Time(1.0));
+        CHECK(f2.img.cols == 32 && f2.img.rows == 24);
+        CHECK(f2.K(0, 0) == 200.f && f2.K(0, 2) == 16.f && f2.K(1, 1) == 205.f && f2.K(1, 2) == 12.f && f2.K(2, 2) == 1.f);
+        CHECK(f2.D(0, 0) == 0.1f && f2.D(0, 1) == 0.2f && f2.D(0, 4) == 0.f);
+        for (int y = 0; y < 24; ++y)
+            for (int x = 0; x < 32; ++x) {
+                const int a = im[(size_t)(2 * y) * w + 2 * x], b = im[(size_t)(2 * y) * w + 2 * x + 1], c = im[(size_t)(2 * y + 1) * w + 2 * x],
+                          d = im[(size_t)(2 * y + 1) * w + 2 * x + 1];
+                CHECK(f2.img.data[(size_t)y * f2.img.step + x] == (uint8_t)((a + b + c + d + 2) >> 2));
+            }
+        Frame f4(4, cv::Mat(h, w, im.data(), (size_t)w), k, std::vector<double>(), ros::Time(1.0));
+        CHECK(f4.img.cols == 16 && f4.img.rows == 12 && f4.K(0, 0) == 100.f);
+        std::printf("frame_resize4:"); for (int i = 0; i < 16 * 12; ++i) std::printf(" %d", (int)f4.img.data[i]);
+        std::printf("\n");
+    }
     std::printf("facade_test: OK\n");
     return 0;
 }

@@ -126,3 +126,28 @@ def test_klt_tracker_facade_matches_cv2_golden(run):
     assert np.allclose(metric[passed, 0] * ctx["fx"], px[passed, 0], atol=1e-3)      # E1: principal point dropped
     assert np.allclose(d["klt_cov00"][passed], np.float32(1e-5) / ctx["fx"] ** 2, rtol=1e-5)
     assert (d["klt_cov00"][~passed] == 0).all()
+
+
+def test_frame_resizing_constructor_matches_the_frame_oracle(run):
+    """Frame::Frame(inv_scale, full image, K, D, t) (Frame.cpp:15-41) through the facade: 2x checked in the C++ program
+    against the area-fast formula, 4x (the reference's default INVERSE_IMAGE_SCALE) against the cv2-pinned oracle here."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import frame_oracle as FO
+    d, _ = run
+    y, x = np.mgrid[0:48, 0:64]
+    im = ((x * 7 + y * 13 + (x * y) % 11) & 255).astype(np.uint8)
+    np.testing.assert_array_equal(d["frame_resize4"].astype(np.uint8).reshape(12, 16), FO.resize(im, 4))
+
+
+def test_frame_resize_host_entry_point(cuda):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import frame_oracle as FO
+    from ekf_vio_b200 import capi
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, (2, 97, 131)).astype(np.uint8)
+    for s in (1, 2, 3, 4):
+        out = capi.frame_resize_h(img, s)
+        for b in range(2):
+            np.testing.assert_array_equal(out[b], FO.resize(img[b], s))
