@@ -870,7 +870,8 @@ cudaError_t launch_process_general(const EkfPtrs& p, const double* Pin, double* 
     size_t sm = proc_smem_bytes(p.nmax);
     const int fused = (mode == 0 && proc_fused_smem_bytes(p.nmax) <= 110 * 1024) ? 1 : 0;   // two CTAs per SM
     if (fused) sm = proc_fused_smem_bytes(p.nmax);
-    static size_t configured = 0;
+    static size_t configured_on[64] = {0};
+    size_t& configured = configured_on[current_device_slot()];
     if (sm > 48 * 1024 && sm > configured) {
         cudaError_t e = cudaFuncSetAttribute(ekf_process_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
@@ -903,7 +904,8 @@ size_t gain_general_smem_doubles(int mmax) {
 cudaError_t launch_gain_general(const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, double* Sg,
                                 cudaStream_t st) {
     size_t sm = p.gain_smem_doubles * sizeof(double);
-    static size_t configured = 0;
+    static size_t configured_on[64] = {0};
+    size_t& configured = configured_on[current_device_slot()];
     if (sm > 48 * 1024 && sm > configured) {
         cudaError_t e = cudaFuncSetAttribute(ekf_gain_general, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;

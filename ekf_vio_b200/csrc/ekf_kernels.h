@@ -8,6 +8,10 @@
 
 namespace ekfvio {
 
+// Function attributes (opt-in shared memory sizes) are per device: launchers keep their one-time set-up per device.
+// (Host-side state, like the reference not meant for concurrent use from several threads.)
+inline int current_device_slot() { int dev = 0; return (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) ? dev : 0; }
+
 // Plain device-pointer bundle passed by value to every EKF kernel.
 struct EkfPtrs {
     double* mu; double* feat; int* nfeat; double* cache; uint8_t* dflags; double* klt_last; int* status;

@@ -514,7 +514,8 @@ cudaError_t launch_update_large(const EkfPtrs& p, const LargePtrs& lp, const dou
                                 const uint8_t* pass, cudaStream_t st, long long* launches, KernelTimer* timer) {
     auto mark = [&](void*, int slot, cudaStream_t s) { if (timer) { timer->end(s); if (slot >= 0) timer->begin(slot, s); } };
     void* mark_ctx = nullptr;
-    static bool configured = false;
+    static bool configured_on[64] = {false};
+    bool& configured = configured_on[current_device_slot()];
     const size_t sm = (size_t)GNST * G_STAGE * sizeof(double);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(ekf_large_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);

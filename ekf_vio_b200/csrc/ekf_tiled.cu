@@ -675,7 +675,8 @@ __global__ void __launch_bounds__(NW * 32, 2) ekf_fwd_tiled(EkfPtrs p, const dou
 
 template <int NW, int NB>
 cudaError_t launch_gain_tiled_t(int which, const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, cudaStream_t st) {
-    static bool configured = false;
+    static bool configured_on[64] = {false};
+    bool& configured = configured_on[current_device_slot()];
     constexpr int NT = NB * (NB + 1) / 2;
     const size_t sm_c = (size_t)(NT + NB) * 64 * sizeof(double) + NB * 8 * sizeof(int);
     const size_t sm_s = (size_t)((NT + NB) * 64 + NB * NB * 64 + NB * 8) * sizeof(double) + NB * 8 * sizeof(int);
@@ -691,7 +692,8 @@ cudaError_t launch_gain_tiled_t(int which, const EkfPtrs& p, const double* Pin, 
         // EKFVIO_FLAG_LITERAL_JOSEPH): the full solve.  Each kernel skips the filters of the other.
         constexpr int NWF = (NW + 1) / 2;
         const size_t sm_f = (size_t)((NT + NB) * 64 + NB * 8) * sizeof(double) + NB * 8 * sizeof(int);
-        static bool configured_f = false;
+        static bool configured_f_on[64] = {false};
+        bool& configured_f = configured_f_on[current_device_slot()];
         if (!configured_f) {
             cudaError_t e = cudaFuncSetAttribute(ekf_fwd_tiled<NWF, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_f);
             if (e != cudaSuccess) return e;
@@ -902,7 +904,8 @@ cudaError_t launch_joseph_sym_t(const EkfPtrs& p, const double* Pin, double* Pou
     constexpr int A_DOUBLES = ROWS * SLDA;
     constexpr int B_DOUBLES = (SKC * (ROWS + 4) > A_DOUBLES) ? SKC * (ROWS + 4) : A_DOUBLES;
     const size_t sm = (size_t)(SNST * (A_DOUBLES + B_DOUBLES) + NW * 8 * 10) * sizeof(double);
-    static int sms_count = 0;
+    static int sms_count_on[64] = {0};
+    int& sms_count = sms_count_on[current_device_slot()];
     if (!sms_count) {
         cudaError_t e = cudaFuncSetAttribute(ekf_joseph_sym<NW, NBLK, IPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
@@ -941,7 +944,8 @@ cudaError_t launch_gain_tiled(int which, const EkfPtrs& p, const double* Pin, co
 cudaError_t launch_joseph_tiled(const EkfPtrs& p, const double* Pin, double* Pout, int only_asym, cudaStream_t st) {
     const int strips = (p.Nmax + 15) / 16;
     const size_t sm = (size_t)NST * BS_DOUBLES * sizeof(double);
-    static bool configured = false;
+    static bool configured_on[64] = {false};
+    bool& configured = configured_on[current_device_slot()];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(ekf_joseph_tiled<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_joseph_tiled<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
