@@ -201,9 +201,14 @@ def bench_ekf(args, rank, world, local):
     kms, kcnt = batch.timing()
     batch.enable_timing(False)
     acc = d_acc.cpu().numpy()
-    st = batch.get_state(want_P=False)
+    st = batch.get_state(want_P=True)
     bad = int((st["status"] != 0).sum())
     finite = bool(np.isfinite(st["mu"][st["status"] == 0]).all())       # filters the library itself flagged are counted in status_nonzero
+    # spot check of the timed batch itself against the FP64 oracle: filters 0, F/3, 2F/3, F-1 of this rank, same stream,
+    # all W+K steps free-running (the checker, not the thing measured)
+    spot = sorted({0, F // 3, (2 * F) // 3, F - 1})
+    oracle_rel = oracle_spot_check(st, spot, init_uv, meas, R, passed, n, total_steps) if not args.skip_cpu else None
+    st["P"] = None
 
     # ---- end-to-end arm: host buffers in, host state out, every step ----
     batch.reset()
@@ -240,11 +245,27 @@ def bench_ekf(args, rank, world, local):
         "kernel_ms": {"process": kms[0] / max(kcnt[0], 1), "gain_chol": kms[1] / max(kcnt[1], 1), "gain_solve": kms[3] / max(kcnt[3], 1),
                       "cov_update": kms[2] / max(kcnt[2], 1)},
         "kernel_share": {k: float(v) for k, v in zip(("process", "gain_chol", "cov_update", "gain_solve"), kms[:4] / max(kms[:4].sum(), 1e-12))},
-        "status_nonzero": bad, "finite": finite, "arms_agree": arms_agree, "gen_s": gen_s,
+        "status_nonzero": bad, "finite": finite, "arms_agree": arms_agree, "gen_s": gen_s, "oracle_rel": oracle_rel, "oracle_filters": spot,
         "mc_stats": {"rmse_pos": float(np.sqrt(acc[0] / max(acc[3], 1))), "rmse_vel": float(np.sqrt(acc[1] / max(acc[3], 1))), "count": float(acc[3])},
     }
     batch.close()
     return res
+
+
+def oracle_spot_check(st, filters, init_uv, meas, R, passed, n, steps):
+    """max over the given filters of max|delta|/max|ref| for (state, Sigma) between the GPU batch after `steps` steps and
+    oracle filters (oracle/ekf_oracle.hpp, FP64) driven with the same stream.  bench.py may execute oracle/ only as checker."""
+    from tests import oracle_lib as O
+    N = 22 + 3 * n
+    worst = 0.0
+    for f in filters:
+        o = O.OracleFilter(); o.add_features(init_uv[f])
+        for s in range(steps):
+            o.process(DT); o.update(meas[s, f], R[f], passed[f])
+        os_ = o.state()
+        g = np.concatenate([st["mu"][f], st["feat"][f, :n].ravel()]); r = np.concatenate([os_["mu"], os_["feat"].ravel()])
+        worst = max(worst, float(np.abs(g - r).max() / np.abs(r).max()), float(np.abs(st["P"][f, :N, :N] - os_["P"]).max() / np.abs(os_["P"]).max()))
+    return worst
 
 
 def bench_replenish(args, rank, world, local, prev, pts):
@@ -584,7 +605,8 @@ def main():
                                         "executed_frac": step_executed / peak if peak else None}},
             "kernel_ms": ekf["kernel_ms"], "kernel_share": ekf["kernel_share"],
             "fp64_peak_tflops": {"dmma": dmma_peak, "dfma": dfma_peak},
-            "checks": {"status_nonzero": ekf["status_nonzero"], "finite": ekf["finite"], "arms_agree": ekf["arms_agree"], "mc_stats": ekf["mc_stats"]},
+            "checks": {"status_nonzero": ekf["status_nonzero"], "finite": ekf["finite"], "arms_agree": ekf["arms_agree"],
+                       "oracle_rel": ekf["oracle_rel"], "oracle_filters": ekf["oracle_filters"], "oracle_tol": 1e-9, "mc_stats": ekf["mc_stats"]},
         }
         if not args.skip_cpu:
             line["cpu_baseline"] = cpu_baseline_ekf(256, 6)

@@ -30,11 +30,12 @@ def _qconj(q):
 
 
 def ekf_streams(first_filter: int, num_filters: int, n: int, steps: int, dt: float = 0.05, depth_sigma: float = 0.01,
-                vel_range: float = 0.05, omega_range: float = 0.05):
+                vel_range: float = 0.2, omega_range: float = 0.2):
     """Returns init_uv [F,n,2], meas [steps,F,n,2], truth [steps,F,22] (float64).
 
     Filter g = first_filter + i draws from Philox(key=g): depth z = 0.5 + N(0, depth_sigma),
-    x, y = U(-1.5, 1.5) * z, body velocity ~ U(-vel_range, vel_range)^3, omega likewise, a = 0.
+    x, y = U(-1.5, 1.5) * z, body velocity ~ U(-vel_range, vel_range)^3, omega likewise, a = 0
+    (defaults = SURVEY.md §8d config 3: U(-0.2, 0.2) m/s and rad/s, depth sigma 0.01).
     """
     F = num_filters
     X = np.zeros((F, n, 3)); vel = np.zeros((F, 3)); om = np.zeros((F, 3))

@@ -164,3 +164,131 @@ def klt_postprocess(next_pts, status, cols, rows, K9, kill_pad=11):
     npf = np.ascontiguousarray(next_pts, np.float32); stc = np.ascontiguousarray(status, np.uint8); K9 = np.ascontiguousarray(K9, np.float32)
     klt.klt_oracle_postprocess(C.c_int(n), P(npf), P(stc), C.c_int(cols), C.c_int(rows), P(K9), C.c_int(kill_pad), P(meas), P(cov), P(passed))
     return meas, cov, passed
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# oracle/_ref: the reference's own TightlyCoupledEKF, compiled from the unmodified sources under /root/reference against the
+# stand-in headers of oracle/_shim (oracle/Makefile target `ref`).  Built here when the reference tree is present; the GPU box
+# and any machine without /root/reference use the prebuilt files (oracle/_ref/ is git-ignored but travels with gpurun).
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+REFERENCE_ROOT = "/root/reference"
+
+
+def _load_ref():
+    paths = [os.path.join(REF_DIR, n) for n in ("libekf_ref_f32.so", "libekf_ref_f64.so")]
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "include", "ekf_vio")):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL)
+    if not all(os.path.exists(p) for p in paths):
+        return None
+    libs = []
+    for p in paths:
+        l = C.CDLL(p)
+        l.ekfref_create.restype = C.c_void_p; l.ekfref_create.argtypes = [C.c_double, C.c_double, C.c_double]
+        l.ekfref_clone.restype = C.c_void_p; l.ekfref_clone.argtypes = [C.c_void_p]
+        l.ekfref_destroy.argtypes = [C.c_void_p]
+        l.ekfref_check_sigma.restype = C.c_long; l.ekfref_error_count.restype = C.c_long
+        l.ekfref_feature_depth_variance.restype = C.c_double
+        libs.append(l)
+    return libs
+
+
+REF_LIBS = _load_ref()
+
+
+class RefFilter:
+    """One TightlyCoupledEKF of the reference itself (f64=False: float as written; f64=True: `float` mapped to `double`).
+    The reference's convolveFeature cache is a function static shared by all filters of a process (E2): drive one filter at
+    a time and call RefFilter.reset_static_cache() between independent runs."""
+
+    def __init__(self, f64=True, depth=0.5, depth_var=100.0, uv_var=1e-5, _handle=None):
+        assert REF_LIBS is not None, "oracle/_ref is not built and /root/reference is absent"
+        self.lib = REF_LIBS[1 if f64 else 0]
+        self.f64 = f64
+        self.h = C.c_void_p(_handle if _handle is not None else self.lib.ekfref_create(depth, depth_var, uv_var))
+
+    def __del__(self):
+        try:
+            self.lib.ekfref_destroy(self.h)
+        except Exception:
+            pass
+
+    @staticmethod
+    def reset_static_cache():
+        for l in REF_LIBS:
+            l.ekfref_reset_static_cache()
+
+    def clone(self):
+        return RefFilter(self.f64, _handle=self.lib.ekfref_clone(self.h))
+
+    @property
+    def n(self):
+        return self.lib.ekfref_num_features(self.h)
+
+    def add_features(self, uv):
+        uv = np.ascontiguousarray(uv, np.float64)
+        self.lib.ekfref_add_features(self.h, P(uv), C.c_int(len(uv)))
+
+    def process(self, dt):
+        self.lib.ekfref_process(self.h, C.c_double(dt))
+
+    def update(self, z, R, passed):
+        z = np.ascontiguousarray(z, np.float64); R = np.ascontiguousarray(R, np.float64); passed = np.ascontiguousarray(passed, np.uint8)
+        assert len(z) == self.n and len(passed) == self.n
+        self.lib.ekfref_update(self.h, P(z), P(R), P(passed))
+
+    def state(self):
+        n = self.n; N = 22 + 3 * n
+        out = dict(mu=np.zeros(22), feat=np.zeros((n, 3)), P=np.zeros((N, N)), flags=np.zeros(n, np.uint8), klt_last=np.zeros((n, 2)))
+        self.lib.ekfref_get_state(self.h, P(out["mu"]), P(out["feat"]), P(out["P"]), P(out["flags"]), P(out["klt_last"]))
+        return out
+
+    def set_mean(self, mu=None, feat=None):
+        mu = None if mu is None else np.ascontiguousarray(mu, np.float64); feat = None if feat is None else np.ascontiguousarray(feat, np.float64)
+        self.lib.ekfref_set_mean(self.h, P(mu), P(feat))
+
+    def set_sigma(self, Pm):
+        Pm = np.ascontiguousarray(Pm, np.float64)
+        self.lib.ekfref_set_sigma(self.h, P(Pm))
+
+    def linearize(self, dt):
+        N = 22 + 3 * self.n; F = np.zeros((N, N))
+        self.lib.ekfref_linearize(self.h, C.c_double(dt), P(F))
+        return F
+
+    def convolve_base(self, mu, dt):
+        mu = np.ascontiguousarray(mu, np.float64); out = np.zeros(22)
+        self.lib.ekfref_convolve_base(self.h, P(mu), C.c_double(dt), P(out))
+        return out
+
+    def convolve_feature(self, mu, f3, dt):
+        mu = np.ascontiguousarray(mu, np.float64); f3 = np.ascontiguousarray(f3, np.float64); out = np.zeros(3)
+        self.lib.ekfref_convolve_feature(self.h, P(mu), P(f3), C.c_double(dt), P(out))
+        return out
+
+    def process_noise(self, dt):
+        q = np.zeros(22 + 3 * self.n)
+        self.lib.ekfref_process_noise(self.h, C.c_double(dt), P(q))
+        return q
+
+    def measurement_map(self, measured):
+        measured = np.ascontiguousarray(measured, np.uint8)
+        H = np.zeros((2 * int(measured.sum()), 22 + 3 * self.n))
+        m = self.lib.ekfref_measurement_map(self.h, P(measured), P(H))
+        return H[:m]
+
+    def check_sigma(self):
+        """Number of ROS_FATAL lines TightlyCoupledEKF::checkSigma raises (pass criterion of the reference: none)."""
+        return int(self.lib.ekfref_check_sigma(self.h))
+
+    def feature_depth_variance(self, i):
+        return float(self.lib.ekfref_feature_depth_variance(self.h, C.c_int(i)))
+
+    def feature_homogenous_covariance(self, i):
+        c = np.zeros(4); self.lib.ekfref_feature_homogenous_covariance(self.h, C.c_int(i), P(c)); return c.reshape(2, 2)
+
+    def set_feature_homogenous_covariance(self, i, c):
+        c = np.ascontiguousarray(c, np.float64).reshape(4); self.lib.ekfref_set_feature_homogenous_covariance(self.h, C.c_int(i), P(c))
+
+    def pixel_maps(self, K):
+        K = np.ascontiguousarray(K, np.float64).reshape(9); a = np.zeros(2); b = np.zeros(2)
+        self.lib.ekfref_pixel_maps(self.h, P(K), P(a), P(b)); return a, b

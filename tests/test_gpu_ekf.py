@@ -437,3 +437,65 @@ def test_feature_removal_marginalises_and_filter_continues(cuda, n):
     z2 = np.zeros((2, n, 2)); z2[:, :n - 4] = orc2.state()["feat"][:, :2] + rng.normal(0, 1e-3, (n - 4, 2))
     orc2.update(z2[0, :n - 4], R2[0], np.ones(n - 4, np.uint8)); b.update(*torch_inputs(z2, R, p2))
     assert_close(gpu_state(b, 0), orc2.state(), what="after removal")
+
+
+@pytest.mark.parametrize("flags", [pytest.param(0, id="default"), pytest.param(4, id="literal-joseph")])
+def test_config3_stream_free_running_100_steps(cuda, flags):
+    """BASELINE.json configs[2] / SURVEY.md §8d config 3 — the stream bench.py times: n = 50, velocity and angular rate
+    ~ U(-0.2, 0.2), depth sigma 0.01, dt 0.05, R = 1e-5 I, every feature measured, 100 steps free-running.  16 filters of
+    the batch against 16 oracle filters, state and Sigma within 1e-9 after every step (the loop of
+    test/analyzeEKFSimulation.cpp:45-99)."""
+    from ekf_vio_b200 import workload
+    F, n, steps = 16, 50, 100
+    uv, meas, _ = workload.ekf_streams(0, F, n, steps)
+    R = np.tile(np.array([1e-5, 0, 0, 1e-5]), (F, n, 1)); passed = np.ones((F, n), np.uint8)
+    b = make_batch(F, n, flags)
+    b.add_features_h(np.full(F, n, np.int32), uv)
+    orcs = []
+    for f in range(F):
+        o = O.OracleFilter(); o.add_features(uv[f]); orcs.append(o)
+    import torch
+    dR = torch.from_numpy(R).cuda(); dp = torch.from_numpy(passed).cuda(); dm = torch.from_numpy(meas).cuda()
+    worst_mu = worst_P = 0.0
+    for s in range(steps):
+        b.process(0.05); b.update(dm[s], dR, dp)
+        st = b.get_state()
+        assert (st["status"] == 0).all()
+        for f, o in enumerate(orcs):
+            o.process(0.05); o.update(meas[s, f], R[f], passed[f])
+            os_ = o.state()
+            rm = rel(np.concatenate([st["mu"][f], st["feat"][f].ravel()]), np.concatenate([os_["mu"], os_["feat"].ravel()]))
+            rp = rel(st["P"][f, :22 + 3 * n, :22 + 3 * n], os_["P"])
+            worst_mu = max(worst_mu, rm); worst_P = max(worst_P, rp)
+            assert rm <= TOL and rp <= TOL, f"config 3 filter {f} step {s}: state {rm:.3e} P {rp:.3e}"
+    print(f"config 3 stream, {F} filters x {steps} steps: worst state {worst_mu:.3e}, worst P {worst_P:.3e}")
+    b.close()
+
+
+@pytest.mark.parametrize("flags", [pytest.param(0, id="default"), pytest.param(4, id="literal-joseph")])
+def test_config4_large_state_n300(cuda, flags):
+    """BASELINE.json configs[3] / SURVEY.md §8d config 4: n = 300 (N = 922, m = 600), the regime the reference exercises
+    at n = 503 (test/test_ekf.cpp:113-141).  Two filters on distinct streams, 3 free-running steps of process + update
+    (all measured), state and Sigma within 1e-9 of the oracle after every call."""
+    from ekf_vio_b200 import workload
+    F, n, steps = 2, 300, 3
+    uv, meas, _ = workload.ekf_streams(0, F, n, steps)
+    R = np.tile(np.array([1e-5, 0, 0, 1e-5]), (F, n, 1)); passed = np.ones((F, n), np.uint8)
+    b = make_batch(F, n, flags)
+    b.add_features_h(np.full(F, n, np.int32), uv)
+    orcs = []
+    for f in range(F):
+        o = O.OracleFilter(); o.add_features(uv[f]); orcs.append(o)
+    for s in range(steps):
+        b.process(0.05)
+        for o in orcs:
+            o.process(0.05)
+        for f, o in enumerate(orcs):
+            assert_close(gpu_state(b, f), o.state(), what=f"config 4 filter {f} process {s}")
+        b.update(*torch_inputs(meas[s], R, passed))
+        for f, o in enumerate(orcs):
+            o.update(meas[s, f], R[f], passed[f])
+            g = gpu_state(b, f)
+            assert_close(g, o.state(), what=f"config 4 filter {f} update {s}")
+            assert g["status"] == 0
+    b.close()
