@@ -129,9 +129,14 @@ def test_process_functions_match_the_reference_source():
             m = r2.state()["mu"]; m[7] = 1.0; r2.set_mean(mu=m); s = o2.state(); o2.set_state(mu=m, feat=s["feat"], Pm=s["P"], cache=s["cache"])
         Fr, Fo = r2.linearize(dt), o2.linearize(dt)
         assert rel(Fr, Fo) <= 1e-12, f"Jacobian dt={dt} after {setter}"
-    # the last call (dt = 0, omega_x = 3.1415 unchanged) is the stale-cache case: a fresh evaluation at dt = 0 leaves every feature
-    # where it is (3x3 diagonal blocks = identity); with the dq_inv cached for dt = 0.1 the features are still rotated by 0.31 rad
-    assert np.abs(Fr[22:25, 22:25] - np.eye(3)).max() > 1e-2
+    # E2 made visible: dt = 0.1 and then dt = 0.2 with the same omega — columns 7-9 are evaluated before the omega columns
+    # refresh the cache, so their feature rows carry the rotation cached for dt = 0.1; a filter that has never seen dt = 0.1 differs
+    Fr, Fo = r2.linearize(0.2), o2.linearize(0.2)
+    assert rel(Fr, Fo) <= 1e-12
+    fresh = O.OracleFilter(depth=0.1, depth_var=0.0, uv_var=0.0); fresh.add_features(feats)
+    s = fresh.state(); fresh.set_state(mu=r2.state()["mu"], feat=s["feat"], Pm=s["P"], cache=s["cache"])
+    Ff = fresh.linearize(0.2)
+    assert np.abs(Fr[22:, 7:10] - Ff[22:, 7:10]).max() > 1e-3 and rel(Fr[:22], Ff[:22]) <= 1e-12
 
 
 def test_update_variants_match_the_reference_source():
