@@ -83,6 +83,7 @@ SIGNATURES = {
     "ekfvio_batch_linearize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "ekfvio_batch_check_sigma": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "ekfvio_batch_get_state": (c_int, [c_void_p] + [c_void_p] * 8),
+    "ekfvio_batch_get_state_range": (c_int, [c_void_p, c_int, c_int] + [c_void_p] * 9),
     "ekfvio_batch_set_state": (c_int, [c_void_p] + [c_void_p] * 7),
     "ekfvio_batch_add_features_h": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ekfvio_batch_update_h": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -235,6 +236,18 @@ class EkfBatch:
         }
         _check(lib.ekfvio_batch_get_state(self._h, _ptr(out["mu"]), _ptr(out["feat"]), _ptr(out["P"]), _ptr(out["nfeat"]),
                                           _ptr(out["cache"]), _ptr(out["flags"]), _ptr(out["klt_last"]), _ptr(out["status"])))
+        return out
+
+    def get_state_range(self, first: int, count: int, want_P: bool = True) -> dict:
+        """State of filters [first, first + count) plus `route`, the update path each took in the last update."""
+        F, nm, Nm = count, max(self.nmax, 1), self.Nmax
+        out = {
+            "mu": np.zeros((F, 22)), "feat": np.zeros((F, nm, 3)), "P": np.zeros((F, Nm, Nm)) if want_P else None,
+            "nfeat": np.zeros(F, np.int32), "cache": np.zeros((F, 7)), "flags": np.zeros((F, nm), np.uint8),
+            "klt_last": np.zeros((F, nm, 2)), "status": np.zeros(F, np.int32), "route": np.zeros(F, np.int32),
+        }
+        _check(lib.ekfvio_batch_get_state_range(self._h, first, count, _ptr(out["mu"]), _ptr(out["feat"]), _ptr(out["P"]), _ptr(out["nfeat"]),
+                                                _ptr(out["cache"]), _ptr(out["flags"]), _ptr(out["klt_last"]), _ptr(out["status"]), _ptr(out["route"])))
         return out
 
     def set_state(self, mu=None, feat=None, P=None, nfeat=None, cache=None, flags=None, klt_last=None):

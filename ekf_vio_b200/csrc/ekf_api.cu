@@ -1,6 +1,7 @@
 // C-ABI layer for the batched EKF (include/ekfvio_c.h).  Owns device memory, picks the kernel
 // path, counts launches.  No CPU fallback: every entry point fails if CUDA does.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -27,13 +28,14 @@ int fail_msg(const std::string& msg) { g_last_error = msg; return 1; }
 static EkfPtrs ptrs(const ekfvio_batch* b) {
     EkfPtrs p;
     p.mu = b->d_mu; p.feat = b->d_feat; p.nfeat = b->d_nfeat; p.cache = b->d_cache; p.dflags = b->d_flags;
-    p.klt_last = b->d_klt_last; p.status = b->d_status; p.idx = b->d_idx; p.y = b->d_y; p.m = b->d_m; p.K = b->d_K; p.W = b->d_W; p.L = b->d_L; p.asym = b->d_asym;
+    p.klt_last = b->d_klt_last; p.status = b->d_status; p.idx = b->d_idx; p.y = b->d_y; p.m = b->d_m; p.K = b->d_K; p.W = b->d_W; p.L = b->d_L; p.asym = b->d_asym; p.route = b->d_route;
     p.F = b->F; p.nmax = b->nmax; p.Nmax = b->Nmax; p.ldP = b->ldP; p.ldK = b->ldK; p.mmax = b->mmax;
     p.flags = b->prm.flags;
     p.sigma_lower = b->upper_stale ? 1 : 0;
     p.depth = b->prm.default_point_depth; p.depth_var = b->prm.default_point_depth_variance;
     p.uv_var = b->prm.default_point_homogenous_variance;
     p.gain_smem_doubles = gain_general_smem_doubles(b->mmax);
+    p.illcond = b->illcond;
     return p;
 }
 
@@ -71,7 +73,7 @@ int ekfvio_batch_destroy(ekfvio_batch* b) {
     cudaSetDevice(b->device);
     cudaFree(b->d_mu); cudaFree(b->d_feat); cudaFree(b->d_P[0]); cudaFree(b->d_P[1]); cudaFree(b->d_nfeat); cudaFree(b->d_cache);
     cudaFree(b->d_flags); cudaFree(b->d_klt_last); cudaFree(b->d_status); cudaFree(b->d_dt); cudaFree(b->d_K); cudaFree(b->d_W);
-    cudaFree(b->d_S); cudaFree(b->d_L); cudaFree(b->d_asym); cudaFree(b->d_LS); cudaFree(b->d_LL); cudaFree(b->d_LT); cudaFree(b->d_y); cudaFree(b->d_idx); cudaFree(b->d_m); cudaFree(b->d_fjac);
+    cudaFree(b->d_S); cudaFree(b->d_L); cudaFree(b->d_asym); cudaFree(b->d_route); cudaFree(b->d_LS); cudaFree(b->d_LL); cudaFree(b->d_LT); cudaFree(b->d_y); cudaFree(b->d_idx); cudaFree(b->d_m); cudaFree(b->d_fjac);
     cudaFree(b->dd_z); cudaFree(b->dd_R); cudaFree(b->dd_pass);
     cudaFreeHost(b->h_z); cudaFreeHost(b->h_R); cudaFreeHost(b->h_pass); cudaFreeHost(b->h_out);
     if (b->copy_st) cudaStreamDestroy(b->copy_st);
@@ -98,6 +100,8 @@ int ekfvio_batch_create(ekfvio_batch** out, int device, int num_filters, int max
     b->ldP = (b->Nmax + (b->large ? 1 : 0) + 7) / 8 * 8;          // (large path: one spare panel row carries y through the forward substitution)
     b->ldK = b->large ? (b->mmax + 63) / 64 * 64 : (b->mmax + 15) / 16 * 16;    // K / W panels are chunk-major in 16-column chunks (kw_at)
     if (params) b->prm = *params; else ekfvio_default_params(&b->prm);
+    b->illcond = ILLCOND_RATIO;
+    if (const char* e = getenv("EKFVIO_ILLCOND")) { const double v = atof(e); if (v > 1.0) b->illcond = v; }
     size_t F = b->F, nm = b->nmax > 0 ? b->nmax : 1;
     size_t Pbytes = F * b->ldP * b->ldP * sizeof(double), Kbytes = F * b->ldP * b->ldK * sizeof(double);
 #define ALLOC(ptr, bytes) do { cudaError_t e2 = cudaMalloc((void**)&(ptr), (bytes)); if (e2 != cudaSuccess) { ekfvio_batch_destroy(b); return ekfvio::fail("cudaMalloc " #ptr, e2); } cudaMemset((ptr), 0, (bytes)); } while (0)
@@ -117,6 +121,7 @@ int ekfvio_batch_create(ekfvio_batch** out, int device, int num_filters, int max
     ALLOC(b->d_idx, F * b->mmax * sizeof(int));
     ALLOC(b->d_m, F * sizeof(int));
     ALLOC(b->d_asym, F * sizeof(int));
+    ALLOC(b->d_route, F * sizeof(int));
     if (b->Nmax <= 176 && b->mmax <= 104) ALLOC(b->d_L, F * gain_tiled_scratch_doubles(b->mmax) * sizeof(double));
     if (b->large) {
         ALLOC(b->d_LS, F * large_scratch_doubles_S(b->mmax) * sizeof(double));
@@ -232,7 +237,13 @@ int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, c
         b->cur ^= 1;
         return 0;
     }
-    if (!(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | 0x100u)) && gain_tiled_supported(pp)) {
+    const bool gain_tiled = !(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | 0x100u)) && gain_tiled_supported(pp);
+    const bool need_S_scratch = gain_general_smem_doubles(b->mmax) == 0;
+    if (!b->d_S && need_S_scratch) {
+        size_t bytes = (size_t)b->F * ((size_t)b->mmax * b->mmax + b->mmax) * sizeof(double);
+        CU(cudaMalloc((void**)&b->d_S, bytes));
+    }
+    if (gain_tiled) {
         b->timer.begin(1, st);
         CU(launch_gain_tiled(0, pp, b->d_P[b->cur], d_z, d_R, d_pass, st));
         b->timer.end(st);
@@ -241,10 +252,6 @@ int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, c
         b->timer.end(st);
         b->launches += (b->prm.flags & EKFVIO_FLAG_LITERAL_JOSEPH) ? 1 : 2;   // forward-only kernel + full solve (each skips the other's filters)
     } else {
-        if (!b->d_S && gain_general_smem_doubles(b->mmax) == 0) {
-            size_t bytes = (size_t)b->F * ((size_t)b->mmax * b->mmax + b->mmax) * sizeof(double);
-            CU(cudaMalloc((void**)&b->d_S, bytes));
-        }
         b->timer.begin(1, st);
         CU(launch_gain_general(pp, b->d_P[b->cur], d_z, d_R, d_pass, b->d_S, st));
         b->timer.end(st);
@@ -255,9 +262,9 @@ int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, c
     else { CU(cudaEventRecord(b->ev_state, st)); CU(cudaEventRecord(b->ev_inputs_free, st)); b->state_ev_valid = b->inputs_ev_valid = true; }
     b->timer.begin(2, st);
     {
-        const bool tiled = !(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | 0x200u)) && joseph_tiled_supported(pp);
+        const bool tiled = gain_tiled && !(b->prm.flags & 0x200u) && joseph_tiled_supported(pp);
         const bool sym = tiled && !(b->prm.flags & 0x400u) && joseph_sym_supported(pp);
-        if (sym) {   // symmetric filters: lower-triangle kernel; the (rare) asymmetric ones: full kernel
+        if (sym) {   // ROUTE_SYM: lower-triangle kernel; ROUTE_TILED (few): full kernel
             CU(launch_joseph_sym(pp, b->d_P[b->cur], b->d_P[b->cur ^ 1], st));
             CU(launch_joseph_tiled(pp, b->d_P[b->cur], b->d_P[b->cur ^ 1], 1, st));
             b->launches += 1;
@@ -313,30 +320,38 @@ int ekfvio_batch_get_view(ekfvio_batch* b, ekfvio_batch_view* v) {
     return 0;
 }
 
-int ekfvio_batch_get_state(ekfvio_batch* b, double* h_mu, double* h_feat, double* h_P, int* h_nfeat, double* h_cache, uint8_t* h_flags,
-                           double* h_klt_last, int* h_status) {
+int ekfvio_batch_get_state_range(ekfvio_batch* b, int first, int count, double* h_mu, double* h_feat, double* h_P, int* h_nfeat, double* h_cache,
+                                 uint8_t* h_flags, double* h_klt_last, int* h_status, int* h_route) {
+    if (!b || first < 0 || count < 0 || first + count > b->F) return fail_msg("get_state_range: filter range outside the batch");
     CU(cudaSetDevice(b->device));
     if (h_P && ensure_full_sigma(b, b->last_stream)) return 1;
     CU(cudaDeviceSynchronize());
-    size_t F = b->F, nm = b->nmax;
-    if (h_mu) CU(cudaMemcpy(h_mu, b->d_mu, F * BASE * sizeof(double), cudaMemcpyDeviceToHost));
-    if (h_feat && nm) CU(cudaMemcpy(h_feat, b->d_feat, F * nm * 3 * sizeof(double), cudaMemcpyDeviceToHost));
-    if (h_nfeat) CU(cudaMemcpy(h_nfeat, b->d_nfeat, F * sizeof(int), cudaMemcpyDeviceToHost));
-    if (h_cache) CU(cudaMemcpy(h_cache, b->d_cache, F * 7 * sizeof(double), cudaMemcpyDeviceToHost));
-    if (h_flags && nm) CU(cudaMemcpy(h_flags, b->d_flags, F * nm, cudaMemcpyDeviceToHost));
-    if (h_klt_last && nm) CU(cudaMemcpy(h_klt_last, b->d_klt_last, F * nm * 2 * sizeof(double), cudaMemcpyDeviceToHost));
-    if (h_status) CU(cudaMemcpy(h_status, b->d_status, F * sizeof(int), cudaMemcpyDeviceToHost));
+    if (count == 0) return 0;
+    size_t F = count, o = first, nm = b->nmax;
+    if (h_mu) CU(cudaMemcpy(h_mu, b->d_mu + o * BASE, F * BASE * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_feat && nm) CU(cudaMemcpy(h_feat, b->d_feat + o * nm * 3, F * nm * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_nfeat) CU(cudaMemcpy(h_nfeat, b->d_nfeat + o, F * sizeof(int), cudaMemcpyDeviceToHost));
+    if (h_cache) CU(cudaMemcpy(h_cache, b->d_cache + o * 7, F * 7 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_flags && nm) CU(cudaMemcpy(h_flags, b->d_flags + o * nm, F * nm, cudaMemcpyDeviceToHost));
+    if (h_klt_last && nm) CU(cudaMemcpy(h_klt_last, b->d_klt_last + o * nm * 2, F * nm * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (h_status) CU(cudaMemcpy(h_status, b->d_status + o, F * sizeof(int), cudaMemcpyDeviceToHost));
+    if (h_route) CU(cudaMemcpy(h_route, b->d_route + o, F * sizeof(int), cudaMemcpyDeviceToHost));
     if (h_P) {
         double* tmp = nullptr;
         size_t bytes = F * (size_t)b->Nmax * b->Nmax * sizeof(double);
         CU(cudaMalloc((void**)&tmp, bytes));
-        cudaError_t e = launch_pack_P(b->d_P[b->cur], tmp, b->ldP, b->Nmax, b->F, 1, nullptr);
+        cudaError_t e = launch_pack_P(b->d_P[b->cur] + o * b->ldP * b->ldP, tmp, b->ldP, b->Nmax, count, 1, nullptr);
         b->launches += 1;
         if (e == cudaSuccess) e = cudaMemcpy(h_P, tmp, bytes, cudaMemcpyDeviceToHost);
         cudaFree(tmp);
         if (e != cudaSuccess) return ekfvio::fail("get_state P", e);
     }
     return 0;
+}
+
+int ekfvio_batch_get_state(ekfvio_batch* b, double* h_mu, double* h_feat, double* h_P, int* h_nfeat, double* h_cache, uint8_t* h_flags,
+                           double* h_klt_last, int* h_status) {
+    return ekfvio_batch_get_state_range(b, 0, b ? b->F : 0, h_mu, h_feat, h_P, h_nfeat, h_cache, h_flags, h_klt_last, h_status, nullptr);
 }
 
 int ekfvio_batch_set_state(ekfvio_batch* b, const double* h_mu, const double* h_feat, const double* h_P, const int* h_nfeat,

@@ -133,6 +133,7 @@ struct ekfvio_batch {
     int device = 0;
     int F = 0, nmax = 0, Nmax = 0, ldP = 0, mmax = 0, ldK = 0;
     ekfvio_params prm{};
+    double illcond = 0.0;          // see ekf_kernels.h ILLCOND_RATIO
     // state
     double* d_mu = nullptr;        // [F][22]
     double* d_feat = nullptr;      // [F][nmax][3]
@@ -157,6 +158,7 @@ struct ekfvio_batch {
     int* d_idx = nullptr;          // [F][mmax]
     int* d_m = nullptr;            // [F]
     int* d_asym = nullptr;         // [F] sticky: Sigma or an R block of this filter is not symmetric
+    int* d_route = nullptr;        // [F] update path of the current update (ekf_kernels.h ROUTE_*)
     double* d_fjac = nullptr;      // [F][(22*22 + nmax*27 + nmax*9)] A | B | D
     // pinned staging + device input buffers for the *_h entry points
     double* h_z = nullptr; double* h_R = nullptr; uint8_t* h_pass = nullptr;

@@ -480,11 +480,10 @@ __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const do
 // updateWithFeaturePositions, part 1 (TightlyCoupledEKF.cpp:475-580, 600-620): measurement map,
 // residual, S = H Sigma H' + R, LDL^T of the upper triangle of S, K, W = Sigma H' - K S, state
 // update.  The covariance update itself is ekf_joseph_general.
-__global__ void __launch_bounds__(PT) ekf_gain_general(EkfPtrs p, const double* __restrict__ Pin, const double* __restrict__ z,
-                                                       const double* __restrict__ Rin, const uint8_t* __restrict__ pass,
-                                                       double* __restrict__ Sg) {
+__device__ void gain_general_filter(const EkfPtrs& p, const double* __restrict__ Pin, const double* __restrict__ z,
+                                    const double* __restrict__ Rin, const uint8_t* __restrict__ pass, double* __restrict__ Sg, int f) {
     extern __shared__ double sm[];
-    const int f = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     const int n = p.nfeat[f], N = BASE + 3 * n;
     const int ld = p.ldP, ldK = p.ldK, nmax = p.nmax, mmax = p.mmax;
     const double* Pi = Pin + (size_t)f * ld * ld;
@@ -612,11 +611,22 @@ __global__ void __launch_bounds__(PT) ekf_gain_general(EkfPtrs p, const double* 
     }
 }
 
+// One CTA per filter, or — as the fallback behind the tiled kernels (only_route >= 0) — a small persistent grid that walks over
+// the batch and serves the filters the Cholesky kernel routed here (normally none: the launch is a few flag reads per CTA).
+__global__ void __launch_bounds__(PT) ekf_gain_general(EkfPtrs p, const double* __restrict__ Pin, const double* __restrict__ z,
+                                                       const double* __restrict__ Rin, const uint8_t* __restrict__ pass,
+                                                       double* __restrict__ Sg, int only_route) {
+    for (int f = blockIdx.x; f < p.F; f += gridDim.x) {
+        if (only_route >= 0 && p.route[f] != only_route) continue;
+        gain_general_filter(p, Pin, z, Rin, pass, Sg, f);
+        __syncthreads();
+    }
+}
+
 // Joseph update (:586-596, :625) in selection form:
 //   Sigma' = (I-KH) Sigma (I-KH)' + K R K' = Sigma - K Sigma(idx,:) - W K',  W = Sigma(:,idx) - K S
 // 32x32 output tile per CTA, 256 threads (2x2 each), k-chunks of 16 staged in shared memory.
-__global__ void __launch_bounds__(256) ekf_joseph_general(EkfPtrs p, const double* __restrict__ Pin, double* __restrict__ Pout) {
-    const int f = blockIdx.z;
+__device__ void joseph_general_tile(const EkfPtrs& p, const double* __restrict__ Pin, double* __restrict__ Pout, int f) {
     const int n = p.nfeat[f], N = BASE + 3 * n, m = p.m[f];
     const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
     if (i0 >= N || j0 >= N) return;
@@ -665,6 +675,14 @@ __global__ void __launch_bounds__(256) ekf_joseph_general(EkfPtrs p, const doubl
         }
 }
 
+__global__ void __launch_bounds__(256) ekf_joseph_general(EkfPtrs p, const double* __restrict__ Pin, double* __restrict__ Pout, int only_route) {
+    for (int f = blockIdx.z; f < p.F; f += gridDim.z) {     // gridDim.z == F, or a small persistent grid for the fallback launch
+        if (only_route >= 0 && p.route[f] != only_route) continue;
+        joseph_general_tile(p, Pin, Pout, f);
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 __global__ void ekf_reset_kernel(EkfPtrs p, double* P0) {  // initializeBaseState (:23-56)
     const int f = blockIdx.x, tid = threadIdx.x;
@@ -678,7 +696,7 @@ __global__ void ekf_reset_kernel(EkfPtrs p, double* P0) {  // initializeBaseStat
     }
     if (tid < BASE) p.mu[(size_t)f * BASE + tid] = (tid == 3) ? 1.0 : 0.0;
     if (tid == 0) {
-        p.nfeat[f] = 0; p.status[f] = 0; p.m[f] = 0; p.asym[f] = 0;
+        p.nfeat[f] = 0; p.status[f] = 0; p.m[f] = 0; p.asym[f] = 0; p.route[f] = 0;
         double* c = p.cache + (size_t)f * 7;
         c[0] = c[1] = c[2] = 0.0; c[3] = 1.0; c[4] = c[5] = c[6] = 0.0;
     }
@@ -902,7 +920,7 @@ size_t gain_general_smem_doubles(int mmax) {
 }
 
 cudaError_t launch_gain_general(const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, double* Sg,
-                                cudaStream_t st) {
+                                cudaStream_t st, int only_route) {
     size_t sm = p.gain_smem_doubles * sizeof(double);
     static size_t configured_on[64] = {0};
     size_t& configured = configured_on[current_device_slot()];
@@ -911,14 +929,15 @@ cudaError_t launch_gain_general(const EkfPtrs& p, const double* Pin, const doubl
         if (e != cudaSuccess) return e;
         configured = sm;
     }
-    ekf_gain_general<<<p.F, PT, sm, st>>>(p, Pin, z, R, pass, Sg);
+    const int grid = only_route >= 0 ? (p.F < 148 ? p.F : 148) : p.F;
+    ekf_gain_general<<<grid, PT, sm, st>>>(p, Pin, z, R, pass, Sg, only_route);
     return cudaGetLastError();
 }
 
-cudaError_t launch_joseph_general(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st) {
+cudaError_t launch_joseph_general(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st, int only_route) {
     int tiles = (p.Nmax + 31) / 32;
-    dim3 grid(tiles, tiles, p.F);
-    ekf_joseph_general<<<grid, 256, 0, st>>>(p, Pin, Pout);
+    dim3 grid(tiles, tiles, only_route >= 0 ? (p.F < 16 ? p.F : 16) : p.F);
+    ekf_joseph_general<<<grid, 256, 0, st>>>(p, Pin, Pout, only_route);
     return cudaGetLastError();
 }
 

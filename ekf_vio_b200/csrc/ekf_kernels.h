@@ -12,14 +12,33 @@ namespace ekfvio {
 // (Host-side state, like the reference not meant for concurrent use from several threads.)
 inline int current_device_slot() { int dev = 0; return (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) ? dev : 0; }
 
+// Per-filter, per-update routing decided by ekf_chol_tiled:
+//   ROUTE_SYM         Sigma and R symmetric, S positive definite and well conditioned: Sigma - Z Z'
+//                     (ekf_fwd_tiled + ekf_joseph_sym in its one-phase form)
+//   ROUTE_JOSEPH_SYM  Sigma and R symmetric, but the reduced form is not safe — a pivot ratio of S beyond ILLCOND_RATIO, where
+//                     Sigma - Z Z' would lose the small posterior variances to cancellation against a huge prior, or an S that
+//                     is not positive definite, which the signed factor S = L J L' carries through as the reference's unpivoted
+//                     LDL^T does (TightlyCoupledEKF.cpp:577-580) — or EKFVIO_FLAG_LITERAL_JOSEPH asks for it: the Joseph form
+//                     term by term (ekf_solve_tiled + ekf_joseph_sym in its two-phase form; lower triangle + mirror, so Sigma
+//                     stays exactly symmetric)
+//   ROUTE_JOSEPH_FULL asymmetric R or Sigma: the Joseph form with no symmetry assumption (ekf_solve_tiled + ekf_joseph_tiled)
+// (EKFVIO_FLAG_FORCE_GENERAL_PATH bypasses all of this: the general kernels, LDL^T exactly as the oracle's.)
+constexpr int ROUTE_SYM = 0, ROUTE_JOSEPH_SYM = 1, ROUTE_JOSEPH_FULL = 2;
+// max pivot / min pivot of the factor of S.  Healthy updates sit at 1e5 (first update: cond(S) ~ 9e5).  Measured on the config-3
+// streams against the extended-precision oracle (tools/step_error_probe.py, profiles/r02_illcond_sweep.log): up to 1e9 every
+// reduced update stays within the FP64 oracle's own rounding error of the step; at 1e11 the first ones do not.
+constexpr double ILLCOND_RATIO = 1e9;
+
 // Plain device-pointer bundle passed by value to every EKF kernel.
 struct EkfPtrs {
     double* mu; double* feat; int* nfeat; double* cache; uint8_t* dflags; double* klt_last; int* status;
     int* idx; double* y; int* m; double* K; double* W; double* L; int* asym;
+    int* route;        // per update: ROUTE_SYM / ROUTE_JOSEPH_SYM / ROUTE_JOSEPH_FULL
     int F, nmax, Nmax, ldP, ldK, mmax;
     uint32_t flags;
     int sigma_lower;   // the input Sigma of symmetric filters is valid only up to the diagonal block of each feature row (after a lower-mode process)
     double depth, depth_var, uv_var;
+    double illcond;    // pivot-ratio threshold of the reduced update (ILLCOND_RATIO; EKFVIO_ILLCOND in the environment overrides it for experiments)
     size_t gain_smem_doubles;
 };
 
@@ -29,9 +48,10 @@ cudaError_t launch_process_general(const EkfPtrs& p, const double* Pin, double* 
                                    long long* launches, int lower);
 bool process_lower_capable(const EkfPtrs& p);
 cudaError_t launch_mirror_lower(const EkfPtrs& p, double* P0, cudaStream_t st);
+// only_route < 0: every filter; otherwise only the filters the Cholesky kernel routed there (p.route[f] == only_route)
 cudaError_t launch_gain_general(const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, double* Sg,
-                                cudaStream_t st);
-cudaError_t launch_joseph_general(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st);
+                                cudaStream_t st, int only_route = -1);
+cudaError_t launch_joseph_general(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st, int only_route = -1);
 size_t gain_general_smem_doubles(int mmax);
 cudaError_t launch_reset(const EkfPtrs& p, double* P0, cudaStream_t st);
 cudaError_t launch_add_features(const EkfPtrs& p, double* P0, const int* ks, const double* uv, int kmax, cudaStream_t st);

@@ -147,7 +147,7 @@ __device__ __forceinline__ void joseph_tiled_filter(const EkfPtrs& p, const doub
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const double* __restrict__ Pin, double* __restrict__ Pout, int only_asym) {
     for (int f = blockIdx.x; f < p.F; f += gridDim.x) {
-        if (only_asym && p.asym[f] == 0) continue;        // symmetric filters went to ekf_joseph_sym
+        if (only_asym && p.route[f] != ROUTE_JOSEPH_FULL) continue;   // the symmetric routes went to ekf_joseph_sym
         joseph_tiled_filter<NW>(p, Pin, Pout, f);
         __syncthreads();                                  // shared memory is reused by the next filter
     }
@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
         if (tid == 0) {  // K is N x 0: only the quaternion renormalisation of :605-609 acts
             double qn = sqrt(mu_g[3] * mu_g[3] + mu_g[4] * mu_g[4] + mu_g[5] * mu_g[5] + mu_g[6] * mu_g[6]);
             mu_g[3] /= qn; mu_g[4] /= qn; mu_g[5] /= qn; mu_g[6] /= qn;
+            p.route[f] = (p.asym[f] || (p.flags & 0x400u)) ? ROUTE_JOSEPH_FULL : ROUTE_SYM;      // the covariance kernels only copy Sigma (m = 0)
         }
         return;
     }
@@ -279,12 +280,51 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
     }
     __syncthreads();
 
-    chol_tiles<NWC>(Ls, Li, nb, &s_bad);
-    if (tid == 0 && s_bad) atomicOr(&p.status[f], 1);
+    // S = L J L', J = diag(+-1): the reference's unpivoted LDL^T (SimplicialLDLT, TightlyCoupledEKF.cpp:577-580) carries on with an S
+    // that is not positive definite, and so does this factorisation.
+    __shared__ double s_sgn[NB * 8];
+    __shared__ int s_neg, s_route;
+    if (tid == 0) s_neg = 0;
+    for (int a = tid; a < NB * 8; a += 128) s_sgn[a] = 1.0;
     __syncthreads();
+    chol_tiles<NWC>(Ls, Li, nb, &s_bad, s_sgn, &s_neg);
+    // Routing of this filter's update (ekf_kernels.h ROUTE_*).  Sigma - Z Z' is only taken where it is as accurate as the Joseph
+    // form: S positive definite with a pivot ratio below ILLCOND_RATIO.  Beyond that it would cancel the small posterior variances
+    // against a huge prior, so such filters get the Joseph form term by term on the tiled kernels (no symmetry assumed), which
+    // also handle the signed factor.  status bit3 records "S was not positive definite" (informational: the reference does not
+    // notice), bit0 a zero pivot (the reference's Eigen::NumericalIssue, :579).
+    if (warp == 0) {
+        double dmax = 0.0, dmin = 1.79e308;
+        for (int a = lane; a < m; a += 32) {
+            const double d = Ls[tile_of(a >> 3, a >> 3) + tsw(a & 7, a & 7)];
+            dmax = fmax(dmax, d); dmin = fmin(dmin, d);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o)); dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o)); }
+        if (lane == 0) {
+            int route = ROUTE_SYM;
+            if (p.flags & EKFVIO_FLAG_LITERAL_JOSEPH) route = ROUTE_JOSEPH_SYM;
+            if (!(dmax * dmax <= p.illcond * dmin * dmin)) route = ROUTE_JOSEPH_SYM;          // (also catches NaN)
+            if (s_neg) { route = ROUTE_JOSEPH_SYM; atomicOr(&p.status[f], 8); }
+            if (!sym_now || (p.flags & 0x400u)) route = ROUTE_JOSEPH_FULL;                        // (0x400: diagnostic, never the symmetric kernel)
+            if (s_bad) atomicOr(&p.status[f], 1);
+            s_route = route; p.route[f] = route;
+        }
+    }
+    __syncthreads();
+    const int route = s_route;
+    if (low && route != ROUTE_SYM) {
+        // lower mode, and this filter leaves the symmetric fast path for this update: the kernels it goes to read all of Sigma,
+        // of which the last process() wrote the feature rows only up to their diagonal blocks — complete it
+        double* Pw = const_cast<double*>(Pi);
+        const int N = BASE + 3 * n;
+        for (int r = BASE + warp; r < N; r += 4) {
+            for (int c = r + 1 + lane; c < N; c += 32) Pw[(size_t)r * ld + c] = Pw[(size_t)c * ld + r];
+        }
+    }
     // Symmetric filters (ekf_fwd_tiled): v = inv(L) y replaces y, so that K y = Z v needs no K.  Block forward
     // substitution by one warp: t = y_jb - sum_k L(jb,k) v_k, v_jb = inv(L_jb,jb) t (explicit inverse tiles).
-    if (warp == 0 && p.asym[f] == 0 && !(p.flags & EKFVIO_FLAG_LITERAL_JOSEPH)) {
+    if (warp == 0 && route == ROUTE_SYM) {
         __shared__ double s_vv[NB * 8], s_t[8];
         const int r = lane >> 2, q = lane & 3;
         for (int jb = 0; jb < nb; ++jb) {
@@ -308,10 +348,11 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
         for (int a = lane; a < m; a += 32) y_g[a] = s_vv[a];
     }
     // factor and inverse tiles to global scratch (same swizzled layout)
-    double* Lg = p.L + (size_t)f * (NT + NB) * 64;
+    double* Lg = p.L + (size_t)f * ((NT + NB) * 64 + NB * 8);
     const int used = nb * (nb + 1) / 2 * 64;
     for (int e = tid * 2; e < used; e += 256) *reinterpret_cast<double2*>(Lg + e) = *reinterpret_cast<const double2*>(Ls + e);
     for (int e = tid * 2; e < nb * 64; e += 256) *reinterpret_cast<double2*>(Lg + NT * 64 + e) = *reinterpret_cast<const double2*>(Li + e);
+    for (int a = tid; a < NB * 8; a += 128) Lg[(NT + NB) * 64 + a] = s_sgn[a];
 }
 
 // Kernel 2 of 2: K = Sigma(:,idx) inv(L)' inv(L), sparseView, mu += K y, W = Sigma(:,idx) - K S,
@@ -327,6 +368,7 @@ __device__ __forceinline__ void solve_tiled_filter(const EkfPtrs& p, const doubl
     double* s_y = Ss + NB * NB * 64;       // NB*8
     int* s_idx = reinterpret_cast<int*>(s_y + NB * 8);   // NB*8
     __shared__ short s_inv[NW * 16];
+    __shared__ double s_sgn[NB * 8];                     // J of S = L J L' (all +1 unless S is not positive definite)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m = p.m[f];
@@ -346,14 +388,14 @@ __device__ __forceinline__ void solve_tiled_filter(const EkfPtrs& p, const doubl
     const int r = lane >> 2, q = lane & 3;
 
     {   // L and inverse tiles: straight copy from scratch
-        const double* Lg = p.L + (size_t)f * (NT + NB) * 64;
+        const double* Lg = p.L + (size_t)f * ((NT + NB) * 64 + NB * 8);
         const int used = nb * (nb + 1) / 2 * 64;
         for (int e = tid * 2; e < used; e += NW * 64) cp_async16(Ls + e, Lg + e);
         for (int e = tid * 2; e < nb * 64; e += NW * 64) cp_async16(Li + e, Lg + NT * 64 + e);
         cp_async_commit();
         const int* idx_g = p.idx + (size_t)f * p.mmax;
         const double* y_g = p.y + (size_t)f * p.mmax;
-        for (int a = tid; a < NB * 8; a += NW * 32) { s_idx[a] = a < m ? idx_g[a] : 0; s_y[a] = a < m ? y_g[a] : 0.0; }
+        for (int a = tid; a < NB * 8; a += NW * 32) { s_idx[a] = a < m ? idx_g[a] : 0; s_y[a] = a < m ? y_g[a] : 0.0; s_sgn[a] = Lg[(NT + NB) * 64 + a]; }
     }
     __syncthreads();
     // this warp's 16-row strip of Sigma(:,idx): the gathers are issued now, so that their latency
@@ -435,7 +477,16 @@ __device__ __forceinline__ void solve_tiled_filter(const EkfPtrs& p, const doubl
             }
         }
         CLK_MARK(5);
-        // backward: K L = Z
+        // K = Sigma(:,idx) inv(S) = (C inv(L)') J inv(L): the signs between the two substitutions
+#pragma unroll
+        for (int jb = 0; jb < NB; ++jb) {
+            if (jb < nb) {
+                const double j0 = s_sgn[jb * 8 + 2 * q], j1 = s_sgn[jb * 8 + 2 * q + 1];
+#pragma unroll
+                for (int rt = 0; rt < 2; ++rt) { k0[rt][jb] *= j0; k1[rt][jb] *= j1; }
+            }
+        }
+        // backward: K L = Z J
 #pragma unroll
         for (int jr = 0; jr < NB; ++jr) {
             const int jb = NB - 1 - jr;
@@ -549,7 +600,7 @@ __device__ __forceinline__ void solve_tiled_filter(const EkfPtrs& p, const doubl
 template <int NW, int NB>
 __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const double* __restrict__ Pin, const double* __restrict__ Rin) {
     for (int f = blockIdx.x; f < p.F; f += gridDim.x) {   // persistent: see ekf_joseph_tiled
-        if (p.asym[f] == 0 && !(p.flags & EKFVIO_FLAG_LITERAL_JOSEPH)) continue;   // symmetric filters: ekf_fwd_tiled
+        if (p.route[f] == ROUTE_SYM) continue;   // ekf_fwd_tiled
         solve_tiled_filter<NW, NB>(p, Pin, Rin, f);
         __syncthreads();
     }
@@ -571,7 +622,7 @@ __global__ void __launch_bounds__(NW * 32, 2) ekf_fwd_tiled(EkfPtrs p, const dou
 
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m = p.m[f];
-    if (m == 0 || p.asym[f] != 0) return;  // asymmetric filters: ekf_solve_tiled
+    if (m == 0 || p.route[f] != ROUTE_SYM) return;  // the others: ekf_solve_tiled
     const int n = p.nfeat[f], N = BASE + 3 * n;
     const int ld = p.ldP, ldK = p.ldK, nmax = p.nmax;
     const double* Pi = Pin + (size_t)f * ld * ld;
@@ -581,7 +632,7 @@ __global__ void __launch_bounds__(NW * 32, 2) ekf_fwd_tiled(EkfPtrs p, const dou
     const int nb = (m + 7) >> 3;
     const int r = lane >> 2, q = lane & 3;
     {
-        const double* Lg = p.L + (size_t)f * (NT + NB) * 64;
+        const double* Lg = p.L + (size_t)f * ((NT + NB) * 64 + NB * 8);
         const int used = nb * (nb + 1) / 2 * 64;
         for (int e = tid * 2; e < used; e += NW * 64) cp_async16(Ls + e, Lg + e);
         for (int e = tid * 2; e < nb * 64; e += NW * 64) cp_async16(Li + e, Lg + NT * 64 + e);
@@ -738,13 +789,15 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
     // drains: while a filter's result is being stored, the first panels of the next one are in flight.
     // schur: the gain kernel left Z = Sigma(:,idx) inv(L)' in the K panel and Sigma' = Sigma - Z Z' is one phase;
     // otherwise (EKFVIO_FLAG_LITERAL_JOSEPH) the K and W panels go through the two phases of the Joseph form.
-    const bool schur = !(p.flags & EKFVIO_FLAG_LITERAL_JOSEPH);
-    struct Meta { int f, N, m, nch, nv; const double* Pi; const double* Kf; const double* Wf; };
+    // (per filter: ROUTE_SYM one phase with Z, ROUTE_JOSEPH_SYM two phases with K and W)
+    struct Meta { int f, N, m, nch, nv; bool schur; const double* Pi; const double* Kf; const double* Wf; };
     auto meta = [&](int f) {
-        Meta M; M.f = f;
-        if (f < p.F && p.asym[f] == 0) {
-            M.N = BASE + 3 * p.nfeat[f]; M.m = p.m[f];
+        Meta M; M.f = f; M.schur = true;
+        const int route = f < p.F ? p.route[f] : ROUTE_JOSEPH_FULL;
+        if (route != ROUTE_JOSEPH_FULL) {
+            M.N = BASE + 3 * p.nfeat[f]; M.m = p.m[f]; M.schur = route == ROUTE_SYM;
         } else { M.N = 0; M.m = 0; }                        // nothing to do (asymmetric filters: ekf_joseph_tiled)
+        const bool schur = M.schur;
         M.nch = (M.m + SKC - 1) / SKC; M.nv = schur ? M.nch : 2 * M.nch;
         M.Pi = Pin + (size_t)f * ld * ld; M.Kf = p.K + (size_t)f * ld * ldK; M.Wf = p.W + (size_t)f * ld * ldK;
         return M;
@@ -752,6 +805,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
     int gs = 0;                                            // stages issued so far -> buffer gs % SNST
     auto issue = [&](const Meta& M, int v, const int* sidx) {
         if (v < M.nv) {
+            const bool schur = M.schur;
             double* A = sms + (gs % SNST) * STAGE;
             double* B = A + A_DOUBLES;
             const int phase = schur ? 1 : (v >= M.nch), k0 = ((phase && !schur) ? v - M.nch : v) * SKC, m = M.m;
@@ -827,9 +881,9 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
             if (v + 2 < cur.nv) issue(cur, v + 2, s_idx[ib]);
             else { issue(nxt, issued_next, s_idx[ib ^ 1]); ++issued_next; }
             const double* A = sms + (gc % SNST) * STAGE;
-            const double* B = schur ? A : A + A_DOUBLES;
+            const double* B = cur.schur ? A : A + A_DOUBLES;
             ++gc;
-            const bool phase1 = schur || v >= cur.nch;
+            const bool phase1 = cur.schur || v >= cur.nch;
 #pragma unroll
             for (int kk = 0; kk < SKC / 4; ++kk) {
                 double fa0[IPW], fa1[IPW], fb0[IPW], fb1[IPW];
@@ -933,7 +987,7 @@ cudaError_t launch_joseph_sym(const EkfPtrs& p, const double* Pin, double* Pout,
 }
 
 bool gain_tiled_supported(const EkfPtrs& p) { return p.Nmax <= 176 && p.mmax <= 104 && p.L != nullptr; }
-size_t gain_tiled_scratch_doubles(int mmax) { int NB = mmax <= 64 ? 8 : 13; return (size_t)(NB * (NB + 1) / 2 + NB) * 64; }
+size_t gain_tiled_scratch_doubles(int mmax) { int NB = mmax <= 64 ? 8 : 13; return (size_t)(NB * (NB + 1) / 2 + NB) * 64 + NB * 8; }   // L tiles | inverse diagonal tiles | signs
 
 // which = 0: Cholesky kernel, 1: solve kernel (two launches so the API layer can time them apart)
 cudaError_t launch_gain_tiled(int which, const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, cudaStream_t st) {

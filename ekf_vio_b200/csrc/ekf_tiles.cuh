@@ -34,11 +34,16 @@ __device__ __forceinline__ void cfrag_to_afrag(double c0, double c1, int lane, d
 }
 
 
-// Blocked right-looking Cholesky of an (8*nb) x (8*nb) matrix held as swizzled lower-triangular
-// 8x8 tiles in shared memory (Ls), in place; Li receives the explicit inverses of the diagonal tiles.
-// Called by all NWC warps of the CTA.  *bad is set if a pivot is not positive.
+// Blocked right-looking factorisation of an (8*nb) x (8*nb) symmetric matrix held as swizzled lower-triangular 8x8 tiles in
+// shared memory (Ls), in place; Li receives the explicit inverses of the diagonal tiles.  Called by all NWC warps of the CTA.
+//
+// sgn == nullptr: Cholesky, A = L L'; *bad_flag is set if a pivot is not positive.
+// sgn != nullptr (shared memory, 8*nb floats-as-doubles): the SIGNED factorisation A = L J L', J = diag(sgn), sgn = +-1 — the
+// unpivoted LDL^T of the reference (SimplicialLDLT, TightlyCoupledEKF.cpp:577-580: L_ldlt = L |D|^-1/2 ... i.e. L = L_ldlt |D|^1/2,
+// J = sign(D)) in Cholesky clothing, so that an S that is not positive definite is carried on with exactly as the reference
+// does.  *bad_flag is then set only for a zero (or NaN) pivot, *neg_flag if any pivot was negative.
 template <int NWC>
-__device__ void chol_tiles(double* Ls, double* Li, int nb, int* bad_flag) {
+__device__ void chol_tiles(double* Ls, double* Li, int nb, int* bad_flag, double* sgn = nullptr, int* neg_flag = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = lane >> 2, q = lane & 3;
     for (int jb = 0; jb < nb; ++jb) {
@@ -48,20 +53,25 @@ __device__ void chol_tiles(double* Ls, double* Li, int nb, int* bad_flag) {
             double a[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) a[c] = T[tsw(rr, c)];
-            bool bad = false;
-            double rd[8];
+            bool bad = false, neg = false;
+            double rd[8], sg[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 double dcc = __shfl_sync(0xffffffffu, a[c], c);
-                if (!(dcc > 0.0)) bad = true;
+                double sc = 1.0;
+                if (sgn) {
+                    if (dcc < 0.0) { sc = -1.0; dcc = -dcc; neg = true; }
+                    if (!(dcc > 0.0)) bad = true;          // zero or NaN pivot
+                } else if (!(dcc > 0.0)) bad = true;
+                sg[c] = sc;
                 double piv = sqrt(dcc);
                 double rpiv = 1.0 / piv;       // one reciprocal per column instead of a division per row
                 rd[c] = rpiv;
-                if (rr == c) a[c] = piv; else if (rr > c) a[c] = a[c] * rpiv;
+                if (rr == c) a[c] = piv; else if (rr > c) a[c] = a[c] * (rpiv * sc);
 #pragma unroll
                 for (int c2 = c + 1; c2 < 8; ++c2) {
                     double l = __shfl_sync(0xffffffffu, a[c], c2);
-                    if (rr >= c2) a[c2] -= a[c] * l;
+                    if (rr >= c2) a[c2] -= a[c] * (l * sc);
                 }
             }
             // column j = rr of inv(L): forward substitution with rows fetched by shuffle
@@ -80,10 +90,18 @@ __device__ void chol_tiles(double* Ls, double* Li, int nb, int* bad_flag) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) I8[tsw(i, rr)] = (i >= rr) ? x[i] : 0.0;
                 if (bad && lane == 0) *bad_flag = 1;
+                if (sgn) {
+                    if (neg && lane == 0) *neg_flag = 1;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) if (rr == c) sgn[jb * 8 + c] = sg[c];
+                }
             }
         }
         __syncthreads();
-        {   // panel: L(ib,jb) = A(ib,jb) * inv(Ljj)'
+        // signs of this block column: J scales the columns of the panel and the k index of the trailing update
+        double s2q0 = 1.0, s2q1 = 1.0, sk0 = 1.0, sk1 = 1.0;
+        if (sgn) { s2q0 = sgn[jb * 8 + 2 * q]; s2q1 = sgn[jb * 8 + 2 * q + 1]; sk0 = sgn[jb * 8 + q]; sk1 = sgn[jb * 8 + 4 + q]; }
+        {   // panel: L(ib,jb) = A(ib,jb) * inv(Ljj)' * J_jb
             const double* I8 = Li + jb * 64;
             double b0 = I8[tsw(r, q)], b1 = I8[tsw(r, 4 + q)];
             for (int ib = jb + 1 + warp; ib < nb; ib += NWC) {
@@ -93,11 +111,11 @@ __device__ void chol_tiles(double* Ls, double* Li, int nb, int* bad_flag) {
                 dmma884(c0, c1, a0, b0);
                 dmma884(c0, c1, a1, b1);
                 __syncwarp();
-                *reinterpret_cast<double2*>(&T[tsw(r, 2 * q)]) = make_double2(c0, c1);
+                *reinterpret_cast<double2*>(&T[tsw(r, 2 * q)]) = make_double2(c0 * s2q0, c1 * s2q1);
             }
         }
         __syncthreads();
-        {   // trailing update: A(ib,kb) -= L(ib,jb) L(kb,jb)'  for ib >= kb > jb
+        {   // trailing update: A(ib,kb) -= L(ib,jb) J_jb L(kb,jb)'  for ib >= kb > jb
             const int t = nb - 1 - jb;
             for (int e = warp; e < t * (t + 1) / 2; e += NWC) {
                 int ii = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
@@ -109,8 +127,8 @@ __device__ void chol_tiles(double* Ls, double* Li, int nb, int* bad_flag) {
                 const double* TB = Ls + tile_of(kb, jb);
                 double* TC = Ls + tile_of(ib, kb);
                 double2 c = *reinterpret_cast<double2*>(&TC[tsw(r, 2 * q)]);
-                dmma884(c.x, c.y, -TA[tsw(r, q)], TB[tsw(r, q)]);
-                dmma884(c.x, c.y, -TA[tsw(r, 4 + q)], TB[tsw(r, 4 + q)]);
+                dmma884(c.x, c.y, -TA[tsw(r, q)] * sk0, TB[tsw(r, q)]);
+                dmma884(c.x, c.y, -TA[tsw(r, 4 + q)] * sk1, TB[tsw(r, 4 + q)]);
                 *reinterpret_cast<double2*>(&TC[tsw(r, 2 * q)]) = c;
             }
         }

@@ -25,8 +25,11 @@
  *                            private copy per filter                 (TightlyCoupledEKF.cpp:400-403)
  *   flags [F][nmax]          Feature::delete_flag                    (Feature.h:46)
  *   klt_last [F][nmax][2]    Feature::last_result_from_klt_tracker   (Feature.h:43)
- *   status[F]                bit0: zero pivot in the S factorisation (TightlyCoupledEKF.cpp:579)
+ *   status[F]                bit0: zero pivot in the S factorisation (TightlyCoupledEKF.cpp:579, Eigen::NumericalIssue)
  *                            bit1: non-finite state after an update
+ *                            bit2: addNewFeatures beyond the batch's capacity (nothing appended)
+ *                            bit3: informational — S was not positive definite in some update; as in the reference, whose
+ *                                  unpivoted LDL^T carries on with such an S, the update was evaluated by the LDL^T kernels
  */
 #ifndef EKFVIO_C_H_
 #define EKFVIO_C_H_
@@ -115,6 +118,10 @@ int ekfvio_batch_check_sigma(ekfvio_batch* b, int* d_neg_diag, double* d_max_asy
  * Layouts as in the header comment; P has leading dimension Nmax = 22 + 3*max_features. */
 int ekfvio_batch_get_state(ekfvio_batch* b, double* h_mu, double* h_feat, double* h_P, int* h_nfeat, double* h_cache,
                            uint8_t* h_flags, double* h_klt_last, int* h_status);
+/* The same for filters [first, first + count) only (outputs sized for `count` filters), plus the update path each filter took
+ * in the last update (h_route, may be NULL: 0 symmetric fast path, 1 tiled Joseph form, 2 general LDL^T kernels). */
+int ekfvio_batch_get_state_range(ekfvio_batch* b, int first, int count, double* h_mu, double* h_feat, double* h_P, int* h_nfeat,
+                                 double* h_cache, uint8_t* h_flags, double* h_klt_last, int* h_status, int* h_route);
 int ekfvio_batch_set_state(ekfvio_batch* b, const double* h_mu, const double* h_feat, const double* h_P, const int* h_nfeat,
                            const double* h_cache, const uint8_t* h_flags, const double* h_klt_last);
 

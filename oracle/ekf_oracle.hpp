@@ -83,7 +83,7 @@ public:
     std::vector<std::array<S, 2>> klt_last;     // Feature::last_result_from_klt_tracker
     std::vector<uint8_t> delete_flag;           // Feature::delete_flag
     std::vector<S> Sigma;                       // dense N x N, row-major
-    int status = 0;                             // bit0: LDLT hit a zero pivot (TightlyCoupledEKF.cpp:579)
+    int status = 0;                             // bit0: LDLT hit a zero pivot (TightlyCoupledEKF.cpp:579); bit3: a negative pivot was seen (diagnostic)
     // E2: the function-static cache of convolveFeature (TightlyCoupledEKF.cpp:400-403), made one
     // private cache per filter with the reference's initial values.
     S last_omega[3] = {S(0), S(0), S(0)};
@@ -364,6 +364,7 @@ public:
             S d = Sm[(size_t)c * m + c];
             for (int k = 0; k < c; ++k) d -= L[(size_t)c * m + k] * L[(size_t)c * m + k] * D[k];
             D[c] = d;
+            if (d < S(0)) status |= 8;                                 // diagnostic only: S is not positive definite (the reference carries on)
             if (d == S(0)) { ok = false; break; }
             for (int r = c + 1; r < m; ++r) {
                 S v = Sm[(size_t)c * m + r];                           // upper(S)(c,r) mirrored to (r,c)

@@ -187,4 +187,42 @@ double ekfo_batch_run(int F, int n, int steps, double dt, const double* init_uv,
     return sec;
 }
 
+// One step (process(dt) + update) of the restated algorithm evaluated in 80-bit extended precision (long double, eps 5.4e-20) from a
+// state given in doubles — the yardstick for the FP64 evaluations: |FP64 oracle - this| is the rounding error the reference's step
+// itself carries in FP64, which on ill-conditioned steps (cond(S) ~ 1e12) is far above 1e-9 (tests/test_gpu_ekf.py).
+void ekfo_step_extended(int n, const double* base_mu, const double* feat, const double* P, const double* cache7, double dt, const double* z,
+                        const double* R, const uint8_t* pass, double* out_mu, double* out_feat, double* out_P) {
+    Filter<long double> flt;
+    t_set(flt, base_mu, feat, n, P, cache7, nullptr, nullptr);
+    flt.process((long double)dt);
+    t_update(flt, z, R, pass);
+    t_get(flt, out_mu, out_feat, out_P, nullptr, nullptr, nullptr, nullptr);
+}
+
+// Diagnostic companion of ekfo_batch_run: per filter the final status word (bit0 zero pivot, bit3 a negative LDL^T pivot was seen),
+// the step at which bit3 was first set (-1: never), min diagonal and max |entry| of the final Sigma.
+void ekfo_batch_run_diag(int F, int n, int steps, double dt, const double* init_uv, const double* z, double r, int threads,
+                         int* out_status, int* out_first_neg, double* out_mindiag, double* out_maxabs) {
+    std::vector<double> R((size_t)n * 4, 0.0);
+    for (int i = 0; i < n; ++i) { R[4 * i] = r; R[4 * i + 3] = r; }
+    std::vector<uint8_t> pass((size_t)n, 1);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 0 ? threads : omp_get_max_threads())
+#endif
+    for (int i = 0; i < F; ++i) {
+        Filter<double> flt;
+        flt.addNewFeatures(init_uv + (size_t)i * n * 2, n);
+        int first = -1;
+        for (int s = 0; s < steps; ++s) {
+            flt.process(dt);
+            flt.updateWithFeaturePositions(z + ((size_t)s * F + i) * n * 2, R.data(), pass.data());
+            if (first < 0 && (flt.status & 8)) first = s;
+        }
+        const int N = BASE + 3 * n;
+        double md = 1e300, ma = 0;
+        for (int a = 0; a < N; ++a) { md = std::min(md, (double)flt.Sigma[(size_t)a * N + a]); for (int b = 0; b < N; ++b) ma = std::max(ma, std::fabs((double)flt.Sigma[(size_t)a * N + b])); }
+        out_status[i] = flt.status; out_first_neg[i] = first; out_mindiag[i] = md; out_maxabs[i] = ma;
+    }
+}
+
 }  // extern "C"

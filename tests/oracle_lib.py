@@ -292,3 +292,13 @@ class RefFilter:
     def pixel_maps(self, K):
         K = np.ascontiguousarray(K, np.float64).reshape(9); a = np.zeros(2); b = np.zeros(2)
         self.lib.ekfref_pixel_maps(self.h, P(K), P(a), P(b)); return a, b
+
+
+def step_extended(mu, feat, Pm, cache, dt, z, R, passed):
+    """process(dt) + update of the restated algorithm in 80-bit extended precision, from / to double arrays."""
+    n = len(feat); N = 22 + 3 * n
+    c = lambda a, t=np.float64: np.ascontiguousarray(a, t)
+    mu, feat, Pm, cache, z, R, passed = c(mu), c(feat), c(Pm), c(cache), c(z), c(R), c(passed, np.uint8)
+    om, of, oP = np.zeros(22), np.zeros((n, 3)), np.zeros((N, N))
+    ekf.ekfo_step_extended(C.c_int(n), P(mu), P(feat), P(Pm), P(cache), C.c_double(dt), P(z), P(R), P(passed), P(om), P(of), P(oP))
+    return dict(mu=om, feat=of, P=oP)

