@@ -61,14 +61,19 @@ def flops_per_filter_step_executed(n: int) -> float:
 
 def ekf_config(F: int, n: int, world: int) -> dict:
     """The workload both arms (ours and --impl reference) are measured on: BASELINE.json configs[2]."""
-    return {"workload": f"batched EKF: {F} filters/GPU x (22+3*{n})-dim state, process(dt)+update(all {n} measured) per step, dt={DT}",
+    return {"workload": f"batched EKF: {F} filters/GPU x (22+3*{n})-dim state, process(dt)+update(all {n} measured) per step, dt={DT}; SURVEY 8d config 3 streams "
+                        "(body velocity and angular rate ~ U(-0.2, 0.2), depth sigma 0.01, R = 1e-5 I)",
             "l2": "working set per step (two 1.0 GB Sigma buffers + 1.3 GB gain panels at 4096 filters) is larger than the 126 MB L2; no flush needed",
             "filters_total": F * world, "features": n,
-            "update_form": "library default: Joseph form of symmetric filters evaluated as Sigma - Z Z' (EKFVIO_FLAG_LITERAL_JOSEPH = term by term)"}
+            "update_form": "library default: per filter and update, the Joseph form of a symmetric filter is evaluated as Sigma - Z Z' where S is positive definite with a "
+                           "pivot ratio <= 1e9, term by term (signed factor S = L J L') otherwise; EKFVIO_FLAG_LITERAL_JOSEPH = always term by term"}
 
 
 KLT_BYTES_WITH_DERIVS = 2_140_800   # SURVEY.md §8d, 640x480 levels 0-3, read once + write levels 1-3 + int16x2 derivatives
 KLT_BYTES_NO_DERIVS = 508_800
+# dram__bytes_read.sum + dram__bytes_write.sum per image pair of the two pyramid kernels from the round's ncu --set full capture
+# (profiles/r02_ncu_klt_summary.txt); None until a capture of the current kernels exists
+KLT_NCU_TRAFFIC_PER_PAIR = None
 
 
 class ClockSampler:
@@ -152,7 +157,7 @@ def sum_over_ranks(x: float, world: int, device: str = "cuda") -> float:
 
 
 # ------------------------------------------------------------------------------------------------
-def bench_ekf(args, rank, world, local):
+def bench_ekf(args, rank, world, local, comm=None):
     import torch
     from ekf_vio_b200 import capi, workload
     F, n, K, W = args.filters, N_FEAT, args.steps, args.warmup
@@ -191,9 +196,8 @@ def bench_ekf(args, rank, world, local):
     e0.record()
     run(W, W + K)
     batch.accumulate_errors(d_truth, d_acc)
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(d_acc[:4], op=dist.ReduceOp.SUM)          # Monte-Carlo error statistics over NVLink
+    if comm is not None:
+        comm.allreduce(d_acc[:4])                                 # Monte-Carlo error statistics: ekfvio_stats_allreduce = one ncclAllReduce over NVLink
     e1.record()
     barrier(world)
     ms_total = max_over_ranks(e0.elapsed_time(e1), world)
@@ -285,6 +289,61 @@ def oracle_spot_check(before, after, filters, init_uv, meas, R, passed, n, steps
     return {"one_step": one, "oracle_own": own, "batch_true": true}
 
 
+def flops_update_executed(n: int) -> float:
+    """Reduced update as executed (symmetric counting): N m^2 + N^2 m + m^3/3."""
+    N, m = 22 + 3 * n, 2 * n
+    return 1.0 * N * m * m + 1.0 * N * N * m + m ** 3 / 3
+
+
+def bench_ekf_rate(F, n, K, W, rank, world, local, comm, oracle_check):
+    """Device-resident rate of one configuration (config 4: large states; config 5: the 65 536-filter sweep), same step as
+    bench_ekf: process(dt) + update(all n measured), streams keyed on the global filter index.  Optionally one step of filter 0
+    against the FP64 oracle, seeded with the batch's own state."""
+    import torch
+    from ekf_vio_b200 import capi, workload
+    init_uv, meas, truth = workload.ekf_streams(rank * F, F, n, K + W + 1, dt=DT)
+    R = np.tile(np.array([1e-5, 0, 0, 1e-5]), (F, n, 1)); passed = np.ones((F, n), np.uint8)
+    d_meas = torch.from_numpy(meas).cuda(); d_R = torch.from_numpy(R).cuda(); d_pass = torch.from_numpy(passed).cuda()
+    d_truth = torch.from_numpy(truth[K + W - 1]).cuda(); d_acc = torch.zeros(8, dtype=torch.float64, device="cuda")
+    batch = capi.EkfBatch(F, n, device=local)
+    batch.add_features_h(np.full(F, n, np.int32), init_uv)
+    for s in range(W):
+        batch.process(DT); batch.update(d_meas[s], d_R, d_pass)
+    barrier(world)
+    l0 = batch.launches
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(W, W + K):
+        batch.process(DT); batch.update(d_meas[s], d_R, d_pass)
+    batch.accumulate_errors(d_truth, d_acc)
+    if comm is not None:
+        comm.allreduce(d_acc[:4])
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    launches = batch.launches - l0
+    acc = d_acc.cpu().numpy()
+    st = batch.get_state(want_P=False)
+    res = {"filters_per_gpu": F, "filters_total": F * world, "features": n, "steps": K, "warmup": W, "value": F * world * K / (ms * 1e-3), "unit": "filter-steps/s",
+           "ms_per_step": ms / K, "gpu_launches": int(launches), "status_nonzero": int(((st["status"] & 3) != 0).sum()), "finite": bool(np.isfinite(st["mu"]).all()),
+           "mc_stats": {"rmse_pos": float(np.sqrt(acc[0] / max(acc[3], 1))), "rmse_vel": float(np.sqrt(acc[1] / max(acc[3], 1))), "count": float(acc[3])}}
+    if oracle_check:
+        from tests import oracle_lib as O
+        N = 22 + 3 * n
+        b0 = batch.get_state_range(0, 1)
+        batch.process(DT); batch.update(d_meas[K + W], d_R, d_pass)
+        a0 = batch.get_state_range(0, 1)
+        o = O.OracleFilter(); o.add_features(init_uv[0])
+        o.set_state(mu=b0["mu"][0], feat=b0["feat"][0, :n], Pm=b0["P"][0, :N, :N], cache=b0["cache"][0])
+        o.process(DT); o.update(meas[K + W, 0], R[0], passed[0])
+        s1 = o.state()
+        rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+        res["oracle_rel"] = max(rel(np.concatenate([a0["mu"][0], a0["feat"][0, :n].ravel()]), np.concatenate([s1["mu"], s1["feat"].ravel()])), rel(a0["P"][0, :N, :N], s1["P"]))
+        res["oracle_tol"] = 1e-9
+    batch.close()
+    return res
+
+
 def bench_replenish(args, rank, world, local, prev, pts):
     """SURVEY.md §8(f)1 — EKFVIO::replenishFeatures for a batch of frames: cv::FAST(50, nms) + check image + greedy
     scan with 60 features already in the state and 40 wanted (NUM_FEATURES 100).  Frames resident in HBM; e2e from host."""
@@ -360,17 +419,18 @@ def bench_vio_loop(args, rank, world, local):
 
 
 def bench_klt(args, rank, world, local):
+    """KLT features tracked/s at 640x480.  Headline leg: SURVEY.md §8d's synthetic rate workload — config 2's base image warped by
+    seeded random affine maps (|t| <= 24 px, |shear| <= 0.05), points = its first 200 FAST(50, nms) corners.  Second leg: config 2
+    itself (test -> moved / test -> shear), whose tracked counts must be cv2's (190 / 194)."""
     import torch
     from ekf_vio_b200 import capi, workload
     B, npts, K, W = args.klt_pairs, 200, args.steps, args.warmup
-    G = min(B, 32)                      # distinct synthetic pairs; the batch cycles through them (separate buffers)
-    prev, nxt, pts, flow = workload.klt_pairs(rank * G, G, 640, 480, npts)
+    G = min(B, 32)                      # distinct pairs per rank; the batch cycles through them (separate buffers: nothing is shared in L2)
     reps = (B + G - 1) // G
-    prev, nxt, pts, flow = (np.ascontiguousarray(np.concatenate([a] * reps)[:B]) for a in (prev, nxt, pts, flow))
+    tile = lambda a: np.ascontiguousarray(np.concatenate([a] * reps)[:B])
+    prev, nxt, pts, flow = (tile(a) for a in workload.klt_pairs_8d(rank * G, G))
     trk = capi.KltTracker(640, 480, B, npts, device=local)
-    d_prev = torch.from_numpy(prev).cuda(); d_next = torch.from_numpy(nxt).cuda()
-    d_pts = torch.from_numpy(pts).cuda()
-    d_out = torch.zeros_like(d_pts); d_status = torch.zeros(B, npts, dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros(B, npts, 2, dtype=torch.float32, device="cuda"); d_status = torch.zeros(B, npts, dtype=torch.uint8, device="cuda")
     d_err = torch.zeros(B, npts, dtype=torch.float32, device="cuda")
     d_npts = torch.full((B,), npts, dtype=torch.int32, device="cuda")
     K9 = np.zeros((B, 9), np.float32); K9[:, 0] = 400.0; K9[:, 4] = 400.0; K9[:, 8] = 1.0
@@ -378,76 +438,109 @@ def bench_klt(args, rank, world, local):
     d_meas = torch.zeros(B, npts, 2, dtype=torch.float32, device="cuda"); d_cov = torch.zeros(B, npts, 4, dtype=torch.float32, device="cuda")
     d_passed = torch.zeros(B, npts, dtype=torch.uint8, device="cuda")
 
-    def step():
-        trk.build_pyramid_pair(0, d_prev, 1, d_next, False)       # both pyramids, as cv::calcOpticalFlowPyrLK rebuilds them per call
-        d_out.copy_(d_pts)                                        # initial flow = previous positions
-        trk.track(0, 1, d_pts, d_out, d_status, d_err, d_npts)
-        trk.postprocess(d_out, d_status, d_npts, d_K9, d_meas, d_cov, d_passed)
+    def device_leg(prev_h, next_h, pts_h, steps, warm):
+        d_prev = torch.from_numpy(prev_h).cuda(); d_next = torch.from_numpy(next_h).cuda(); d_pts = torch.from_numpy(pts_h).cuda()
 
-    for _ in range(W):
-        step()
-    barrier(world)
-    trk.enable_timing(True)
-    l0 = trk.launches
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        step()
-    e1.record()
-    barrier(world)
-    ms_total = max_over_ranks(e0.elapsed_time(e1), world)
-    launches = trk.launches - l0
-    kms, kcnt = trk.timing()
-    trk.enable_timing(False)
+        def step():
+            trk.build_pyramid_pair(0, d_prev, 1, d_next, False)       # both pyramids, as cv::calcOpticalFlowPyrLK rebuilds them per call
+            d_out.copy_(d_pts)                                        # initial flow = previous positions (OPTFLOW_USE_INITIAL_FLOW)
+            trk.track(0, 1, d_pts, d_out, d_status, d_err, d_npts)
+            trk.postprocess(d_out, d_status, d_npts, d_K9, d_meas, d_cov, d_passed)
+
+        for _ in range(warm):
+            step()
+        barrier(world)
+        trk.enable_timing(True)
+        l0 = trk.launches
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        barrier(world)
+        ms_total = max_over_ranks(e0.elapsed_time(e1), world)
+        launches = trk.launches - l0
+        kms, kcnt = trk.timing()
+        trk.enable_timing(False)
+        return ms_total, launches, kms, kcnt, d_pts
+
+    ms_total, launches, kms, kcnt, d_pts = device_leg(prev, nxt, pts, K, W)
     tracked = float(d_passed.sum().item())
     attempted = float(B * npts)
     tracked_all = sum_over_ranks(tracked, world); attempted_all = sum_over_ranks(attempted, world)
-    # sanity: the known synthetic flow is recovered
-    good = d_status.bool()
-    fl = (d_out - d_pts)[good].mean(0).cpu().numpy() if bool(good.any()) else np.zeros(2)
+    good = d_passed.bool()
+    fl = (d_out - d_pts)[good].view(-1, 2)
+    # sanity: the recovered flow of a pair is its affine map's (translation + shear * (y - 240) in x)
+    exp = torch.from_numpy(flow).cuda()[:, None, :].expand(B, npts, 2)[good].view(-1, 2)
+    flow_err_y = float((fl[:, 1] - exp[:, 1]).abs().median().item()) if fl.numel() else None
 
     # e2e: host images + points in (page-locked host memory), host results out
-    prev = torch.from_numpy(prev).pin_memory().numpy(); nxt = torch.from_numpy(nxt).pin_memory().numpy()
+    prev_p = torch.from_numpy(prev).pin_memory().numpy(); nxt_p = torch.from_numpy(nxt).pin_memory().numpy()
     nn = pts.copy()
     npts_h = np.full(B, npts, np.int32)
     for _ in range(max(1, W // 2)):
-        nn[:] = pts; trk.track_pair_h(prev, nxt, pts, nn, npts_h)
+        nn[:] = pts; trk.track_pair_h(prev_p, nxt_p, pts, nn, npts_h)
     barrier(world)
     t0 = time.perf_counter()
     for _ in range(K):
         nn[:] = pts
-        st_h, _ = trk.track_pair_h(prev, nxt, pts, nn, npts_h)
+        st_h, _ = trk.track_pair_h(prev_p, nxt_p, pts, nn, npts_h)
     barrier(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
     in_pad = ~((nn[..., 0] < 11) | (nn[..., 1] < 11) | (640 - nn[..., 0] < 11) | (480 - nn[..., 1] < 11))
     tracked_e2e = sum_over_ranks(float(((st_h == 1) & in_pad).sum()), world)
+    e2e = {"value": tracked_e2e * K / e2e_s, "unit": "features/s", "h2d_bytes_per_step": int(prev.nbytes + nxt.nbytes + 2 * pts.nbytes + npts_h.nbytes),
+           "d2h_bytes_per_step": int(nn.nbytes + st_h.nbytes + 4 * st_h.size),
+           "note": "ekfvio_klt_track_pair_h: both frames of every pair uploaded per call, as cv::calcOpticalFlowPyrLK takes them"}
+    # a tracker in a sequence only needs the new frame: the previous frame's pyramid (with derivatives) is already on the device
+    if hasattr(trk, "track_next_h"):
+        trk.track_pair_h(prev_p, nxt_p, pts, nn, npts_h)                  # establishes "previous"
+        seq = [nxt_p, prev_p]
+        for i in range(2):
+            nn[:] = pts; trk.track_next_h(seq[i % 2], pts, nn, npts_h)
+        barrier(world)
+        t0 = time.perf_counter()
+        tr = 0.0
+        for i in range(K):
+            nn[:] = pts
+            st_n, _ = trk.track_next_h(seq[i % 2], pts, nn, npts_h)
+        barrier(world)
+        seq_s = max_over_ranks(time.perf_counter() - t0, world)
+        in_pad = ~((nn[..., 0] < 11) | (nn[..., 1] < 11) | (640 - nn[..., 0] < 11) | (480 - nn[..., 1] < 11))
+        e2e["sequence"] = {"value": sum_over_ranks(float(((st_n == 1) & in_pad).sum()), world) * K / seq_s, "unit": "features/s",
+                           "h2d_bytes_per_step": int(nxt.nbytes + 2 * pts.nbytes + npts_h.nbytes),
+                           "note": "ekfvio_klt_track_next_h: only the new frame travels; the previous pyramid stays on the device (KLTTracker in EKFVIO::addFrame)"}
 
-    # roofline of the dominant streaming kernel: level 0 (reads 640x480 once, writes derivatives + level 1)
+    # roofline of the pyramid + Scharr construction (all levels of both images of a pair)
     peaks = load_peaks()
-    lvl0_calls = max(kcnt[0], 1)
-    # one level-0 launch per step covers both images of every pair: the previous frame (read, write
-    # derivatives + level 1) and the next frame (read, write level 1)
-    bytes_l0 = B * ((640 * 480 + 640 * 480 * 4 + 320 * 240) + (640 * 480 + 320 * 240))
-    ms_l0 = kms[0] / lvl0_calls
     pyr_ms = float(kms[:4].sum() / K)
     pyr_bytes = B * (KLT_BYTES_WITH_DERIVS + KLT_BYTES_NO_DERIVS)
+    bytes_l0 = B * ((640 * 480 + 640 * 480 * 4 + 320 * 240) + (640 * 480 + 320 * 240))
+    ms_l0 = kms[0] / max(kcnt[0], 1)
     res = {
         "metric": "KLT features tracked/s at 640x480", "value": tracked_all * K / (ms_total * 1e-3), "unit": "features/s",
         "attempted_per_s": attempted_all * K / (ms_total * 1e-3), "ms_per_step": ms_total / K,
-        "config": {"workload": f"{B} image pairs/GPU 640x480, 200 points each, both pyramids rebuilt per step (as cv::calcOpticalFlowPyrLK does), win 21, 4 levels; inputs larger than L2"},
-        "tracked_fraction": tracked / attempted, "mean_flow_err_px": float(np.abs(fl - flow.mean(0)).max()),
-        "e2e": {"value": tracked_e2e * K / e2e_s, "unit": "features/s", "h2d_bytes_per_step": int(prev.nbytes + nxt.nbytes + 2 * pts.nbytes + npts_h.nbytes),
-                "d2h_bytes_per_step": int(nn.nbytes + st_h.nbytes + 4 * st_h.size)},
+        "config": {"workload": f"{B} image pairs/GPU 640x480 (SURVEY 8d: config 2's base image under seeded affine maps, |t| <= 24 px, |shear| <= 0.05; {G} distinct pairs/GPU), "
+                               "its first 200 FAST(50, nms) corners per pair, both pyramids rebuilt per step (as cv::calcOpticalFlowPyrLK does), win 21, 4 levels; inputs larger than L2"},
+        "tracked_fraction": tracked / attempted, "tracked": tracked_all, "attempted": attempted_all, "median_flow_err_px": flow_err_y,
+        "e2e": e2e,
         "gpu_launches": int(launches),
-        "kernel_ms": {"pyr_level0": ms_l0, "pyramids_per_step": pyr_ms, "track": kms[4] / max(kcnt[4], 1)},
-        "roofline": {"bound": "hbm", "kernel": "klt_level_kernel (pyramid + Scharr, all levels of both images)",
+        "kernel_ms": {"pyr_level0": ms_l0, "pyr_levels_1_3": float(kms[1:4].sum() / max(kcnt[1], 1)), "pyramids_per_step": pyr_ms, "track": kms[4] / max(kcnt[4], 1)},
+        "roofline": {"bound": "hbm", "kernel": "klt_level0_tma_kernel + klt_levels_fused_kernel (pyramid + Scharr, all levels of both images; TMA-staged)",
                      "achieved": pyr_bytes / (pyr_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": pyr_bytes / (pyr_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                     # level-0 launch of 64 pairs in profiles/r01_ncu_traffic.txt: 39.3 MB read + 80.5 MB written (the rest of the
-                     # 127.8 MB algorithmic bytes is still in L2 when the kernel ends), scaled per pair
-                     "traffic": (39.33e6 + 80.51e6) / 64 * B, "peak_source": peaks["source"],
-                     "level0_achieved": bytes_l0 / (ms_l0 * 1e-3) / 1e9},
+                     "bytes_per_launch_pair": pyr_bytes, "traffic": KLT_NCU_TRAFFIC_PER_PAIR * B if KLT_NCU_TRAFFIC_PER_PAIR else None,
+                     "peak_source": peaks["source"], "level0_achieved": bytes_l0 / (ms_l0 * 1e-3) / 1e9},
     }
+    # ---- config 2 itself: test -> moved / test -> shear, 200 FAST corners (BASELINE.json configs[1]) ----
+    p2, n2, pts2, expect = workload.klt_pairs_config2(B)
+    ms2, _, _, _, _ = device_leg(p2, n2, pts2, max(3, K // 4), 2)
+    st2 = d_status.cpu().numpy()
+    per_pair = st2.sum(1)
+    res["config2"] = {"workload": f"{B} pairs/GPU: images/640_480_test.png -> moved / shear variants (alternating), first 200 FAST(50, nms) corners",
+                      "value": sum_over_ranks(float(d_passed.sum().item()), world) * max(3, K // 4) / (ms2 * 1e-3), "unit": "features/s",
+                      "ms_per_step": ms2 / max(3, K // 4), "status_tracked_per_pair": [int(per_pair[0]), int(per_pair[1])], "cv2_tracked_per_pair": [int(expect[0]), int(expect[1])],
+                      "status_counts_match_cv2": bool((per_pair == expect).all()), "passed_kill_pad_fraction": float(d_passed.float().mean().item())}
     trk.close()
     res["replenish"] = bench_replenish(args, rank, world, local, prev, pts)
     res["vio_loop"] = bench_vio_loop(args, rank, world, local)
@@ -492,7 +585,7 @@ def cpu_baseline_klt(pairs: int = 8, reps: int = 3):
         import cv2
     except ImportError:
         return {"value": None, "unit": "features/s", "cores": 0, "kind": "reference", "sample": "cv2 not importable on this box"}
-    prev, nxt, pts, _ = workload.klt_pairs(0, pairs, 640, 480, 200)
+    prev, nxt, pts, _ = workload.klt_pairs_8d(0, pairs)
     cores = os.cpu_count() or 1
     cv2.setNumThreads(cores)
     crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
@@ -571,6 +664,7 @@ def main():
     ap.add_argument("--klt-pairs", type=int, default=256, help="image pairs per GPU for the KLT leg")
     ap.add_argument("--skip-klt", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-large", action="store_true", help="skip the config-4 (n=300) and config-5 (65 536 filters, N>1) legs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -585,8 +679,24 @@ def main():
     from ekf_vio_b200 import capi
 
     dmma_peak, dfma_peak = capi.measure_fp64_peak(local)
-    ekf = bench_ekf(args, rank, world, local)
+    comm = None
+    if world > 1:
+        # the library's own collective (ekfvio_stats_allreduce, NCCL): torch.distributed only carries the 128-byte id to the ranks
+        import torch.distributed as dist
+
+        def exchange(raw):
+            t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                t.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+            dist.broadcast(t, 0)
+            return bytes(t.cpu().numpy().tobytes())
+        comm = capi.StatsComm(local, world, rank, exchange)
+    ekf = bench_ekf(args, rank, world, local, comm)
     klt = None if args.skip_klt else bench_klt(args, rank, world, local)
+    # config 4 (BASELINE.json configs[3]): 64 filters/GPU x (22 + 3*300) states, the blocked multi-CTA DMMA path
+    cfg4 = None if args.skip_large else bench_ekf_rate(64, 300, min(args.steps, 12), 3, rank, world, local, comm, oracle_check=(rank == 0 and not args.skip_cpu))
+    # config 5 (BASELINE.json configs[4]): 65 536 filters in total, sharded over the ranks (only when there are ranks to shard over)
+    cfg5 = bench_ekf_rate(65536 // world, N_FEAT, min(args.steps, 10), 3, rank, world, local, comm, oracle_check=False) if world > 1 and not args.skip_large else None
 
     if rank == 0:
         n = N_FEAT
@@ -631,6 +741,22 @@ def main():
                        "batch_true_error": ekf["oracle"]["batch_true"] if ekf["oracle"] else None,
                        "oracle_filters": ekf["oracle_filters"], "mc_stats": ekf["mc_stats"]},
         }
+        if comm is not None:
+            line["collective"] = {"api": "ekfvio_stats_allreduce (ncclAllReduce, FP64 sum, 4 doubles per report)", "nranks": comm.size()}
+        if cfg4:
+            f4 = flops_per_filter_step(300)
+            fx4 = 486 * 300 * 300 + 5.7e3 * 300 + 4.3e4 + (1.75e3 * 300 + 5.3e3) + flops_update_executed(300)
+            v4 = cfg4["value"] / world
+            cfg4["workload"] = "BASELINE.json configs[3]: 64 filters/GPU x (22+3*300)-dim state (N = 922, m = 600), process + update per step, blocked multi-CTA DMMA path"
+            cfg4["roofline"] = {"bound": "tensor", "pipe": "fp64 (DMMA.8x8x4)", "peak": peak, "unit": "TFLOP/s",
+                                "survey_flops_per_filter_step": f4, "achieved": v4 * f4 / 1e12, "frac": v4 * f4 / 1e12 / peak if peak else None,
+                                "executed_flops_per_filter_step": fx4, "executed_achieved": v4 * fx4 / 1e12, "executed_frac": v4 * fx4 / 1e12 / peak if peak else None}
+            line["config4"] = cfg4
+        if cfg5:
+            v5 = cfg5["value"] / world
+            cfg5["workload"] = "BASELINE.json configs[4]: 65 536 filters in total (n = 50) sharded over the ranks, error statistics reduced by ekfvio_stats_allreduce"
+            cfg5["whole_step_frac_survey_flops"] = v5 * fstep / 1e12 / peak if peak else None
+            line["config5"] = cfg5
         if not args.skip_cpu:
             line["cpu_baseline"] = cpu_baseline_ekf(256, 6)
         if klt:
@@ -638,6 +764,8 @@ def main():
                 klt["cpu_baseline"] = cpu_baseline_klt()
             line["klt"] = klt
         print(json.dumps(line), file=result_out, flush=True)
+    if comm is not None:
+        comm.close()
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

@@ -82,6 +82,11 @@ SIGNATURES = {
     "ekfvio_batch_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ekfvio_batch_linearize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "ekfvio_batch_check_sigma": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ekfvio_comm_unique_id": (c_int, [c_void_p]),
+    "ekfvio_comm_create": (c_int, [C.POINTER(c_void_p), c_int, c_int, c_int, c_void_p]),
+    "ekfvio_comm_destroy": (c_int, [c_void_p]),
+    "ekfvio_comm_size": (c_int, [c_void_p]),
+    "ekfvio_stats_allreduce": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "ekfvio_batch_get_state": (c_int, [c_void_p] + [c_void_p] * 8),
     "ekfvio_batch_get_state_range": (c_int, [c_void_p, c_int, c_int] + [c_void_p] * 9),
     "ekfvio_batch_set_state": (c_int, [c_void_p] + [c_void_p] * 7),
@@ -102,6 +107,7 @@ SIGNATURES = {
     "ekfvio_klt_track": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ekfvio_klt_postprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ekfvio_klt_track_pair_h": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ekfvio_klt_track_next_h": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ekfvio_klt_read_level": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, C.POINTER(c_int), C.POINTER(c_int)]),
     "ekfvio_klt_launch_count": (C.c_longlong, [c_void_p]),
     "ekfvio_fast_create": (c_int, [C.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int]),
@@ -276,6 +282,32 @@ class EkfBatch:
         return ms, cnt
 
 
+class StatsComm:
+    """The NCCL communicator behind ekfvio_stats_allreduce.  `exchange(id_bytes_or_None) -> bytes` hands rank 0's 128-byte id to
+    every rank (bench.py uses a torch.distributed broadcast for that; any transport will do)."""
+
+    def __init__(self, device: int, nranks: int, rank: int, exchange):
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            _check(lib.ekfvio_comm_unique_id(ident))
+        raw = exchange(bytes(ident) if rank == 0 else None)
+        buf = (C.c_ubyte * 128).from_buffer_copy(raw)
+        self._h = c_void_p()
+        _check(lib.ekfvio_comm_create(C.byref(self._h), device, nranks, rank, buf))
+
+    def size(self) -> int:
+        return int(lib.ekfvio_comm_size(self._h))
+
+    def allreduce(self, buf):
+        """In-place FP64 sum of a device tensor over all ranks, on the current stream."""
+        _check(lib.ekfvio_stats_allreduce(self._h, _ptr(buf), int(buf.numel()), _stream()))
+
+    def close(self):
+        if self._h:
+            lib.ekfvio_comm_destroy(self._h)
+            self._h = c_void_p()
+
+
 def measure_fp64_peak(device: int = 0):
     """(DMMA TFLOP/s, DFMA TFLOP/s) measured on this GPU by register-resident loops."""
     a, b = c_double(), c_double()
@@ -340,6 +372,16 @@ class KltTracker:
         npts = np.ascontiguousarray(npts, np.int32)
         _check(lib.ekfvio_klt_track_pair_h(self._h, _ptr(prev), _ptr(nxt), int(prev.shape[2]), batch, _ptr(prev_pts), _ptr(next_pts),
                                            _ptr(status), _ptr(err), _ptr(npts), _stream()))
+        return status, err
+
+    def track_next_h(self, nxt: np.ndarray, prev_pts: np.ndarray, next_pts: np.ndarray, npts: np.ndarray):
+        """Sequence form of track_pair_h: only the new frame is uploaded; the previous one is the last call's `nxt`."""
+        batch = nxt.shape[0]
+        status = np.zeros((batch, self.max_points), np.uint8)
+        err = np.zeros((batch, self.max_points), np.float32)
+        npts = np.ascontiguousarray(npts, np.int32)
+        _check(lib.ekfvio_klt_track_next_h(self._h, _ptr(nxt), int(nxt.shape[2]), batch, _ptr(prev_pts), _ptr(next_pts), _ptr(status), _ptr(err),
+                                           _ptr(npts), _stream()))
         return status, err
 
     def read_level(self, slot: int, img: int, level: int, want_deriv: bool):

@@ -1,4 +1,5 @@
 // C-ABI layer for the batched pyramidal KLT tracker (include/ekfvio_c.h, klt section).
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -18,6 +19,40 @@ using ekfvio::fail_msg;
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return ekfvio::fail(#x, e_); } while (0)
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- TMA descriptors -------------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver entry point; it is looked up at run time so that the library links against the
+// runtime only.  An image batch is a 3-D tensor of 32-bit words: (pitch / 4, height, images), strides (pitch, image stride).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+        else cudaGetLastError();
+    }
+    return fn;
+}
+static bool tma_eligible(const void* base, int pitch, size_t img_stride) {
+    return encode_tiled_fn() && (((size_t)base) & 15) == 0 && (pitch & 15) == 0 && (img_stride & 15) == 0 && pitch >= 16;
+}
+static bool make_tensor_map(CUtensorMap* out, const void* base, int pitch, int h, int nimg, size_t img_stride, int box_words, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || box_words > 256 || box_rows > 256 || box_words < 1 || box_rows < 1) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)(pitch / 4), (cuuint64_t)h, (cuuint64_t)(nimg > 0 ? nimg : 1)};
+    const cuuint64_t gstride[2] = {(cuuint64_t)pitch, (cuuint64_t)img_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)box_words, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+static int staged_rows(int h) { return (h + 7) / 8 * 8 + 4; }      // klt_levels_fused_kernel: a thread's 8-row block may overhang the image
+constexpr int kHaloX = 16;                                          // klt_kernels.cu HX: boxes start on 16-byte boundaries
+constexpr int kTileWords = (256 + 2 * kHaloX) / 4, kTileRows = 64 + 4;   // klt_level0_tma_kernel's staged tile (klt_kernels.cu ATW / ATH)
 
 extern "C" {
 
@@ -39,6 +74,7 @@ int ekfvio_klt_destroy(ekfvio_klt* k) {
     if (k->copy_st) cudaStreamDestroy(k->copy_st);
     for (int i = 0; i < 4; ++i) if (k->ev_chunk[i]) cudaEventDestroy(k->ev_chunk[i]);
     delete[] k->slot_has_derivs; delete[] k->slot_batch;
+    delete[] k->tmap_l0; delete[] k->tmap_l1;
     delete k;
     return 0;
 }
@@ -93,6 +129,32 @@ int ekfvio_klt_create(ekfvio_klt** out, int device, int width, int height, int m
     if (e != cudaSuccess) { ekfvio_klt_destroy(k); return ekfvio::fail("ekfvio_klt_create alloc", e); }
     size_t smem = track_smem_bytes(win);
     (void)smem;
+    // TMA descriptors of the slots' own level-0 / level-1 images, and the plan for the fused levels 1..3
+    k->tmap_l0 = new unsigned long long[num_slots][16]();
+    k->tmap_l1 = new unsigned long long[num_slots][16]();
+    static_assert(sizeof(CUtensorMap) == 16 * sizeof(unsigned long long), "CUtensorMap is 128 bytes");
+    k->tma_ok = encode_tiled_fn() != nullptr;
+    if (getenv("EKFVIO_KLT_NO_TMA") == nullptr) {
+        for (int s = 0; s < num_slots && k->tma_ok; ++s) {
+            uint8_t* base = k->d_slots + (size_t)s * k->slot_bytes;
+            k->tma_ok = make_tensor_map(reinterpret_cast<CUtensorMap*>(k->tmap_l0[s]), base + P.lv[0].img_off, P.lv[0].pitch, P.lv[0].h, max_batch,
+                                        P.lv[0].img_stride, kTileWords, kTileRows);
+        }
+        if (k->tma_ok && P.levels >= 2 && P.levels <= 4) {
+            const Level& L1 = P.lv[1];
+            // staged levels in shared memory: level 1 | level 2, level 3 over the (then dead) level 1
+            size_t off = 0;
+            for (int l = 1; l < P.levels && l <= 2; ++l) off += align_up((size_t)(P.lv[l].pitch + 2 * kHaloX) * staged_rows(P.lv[l].h), 128);
+            bool ok = (L1.pitch + 2 * kHaloX) / 4 <= 256 && staged_rows(L1.h) <= 256 && off <= 200 * 1024;
+            if (P.levels == 4 && (size_t)(P.lv[3].pitch + 2 * kHaloX) * staged_rows(P.lv[3].h) > (size_t)(L1.pitch + 2 * kHaloX) * staged_rows(L1.h)) ok = false;
+            for (int s = 0; s < num_slots && ok; ++s) {
+                uint8_t* base = k->d_slots + (size_t)s * k->slot_bytes;
+                ok = make_tensor_map(reinterpret_cast<CUtensorMap*>(k->tmap_l1[s]), base + L1.img_off, L1.pitch, L1.h, max_batch, L1.img_stride,
+                                     (L1.pitch + 2 * kHaloX) / 4, staged_rows(L1.h));
+            }
+            if (ok) { k->fused_levels = P.levels - 1; k->fused_smem = off + 128; }      // (+128: the kernel aligns its base)
+        }
+    } else k->tma_ok = false;
     *out = k;
     return 0;
 }
@@ -120,6 +182,28 @@ static int build_slots(ekfvio_klt* k, int nslots, const int* slots, const uint8_
     const Pyr& P = k->pyr;
     for (int l = 0; l < P.levels; ++l) {
         const Level& L = P.lv[l];
+        if (l == 1 && k->fused_levels > 0) {
+            // levels 1 .. fused_levels of every image in one launch: level 1 arrives by TMA and stays in shared memory
+            FusedJob fj[2] = {FusedJob{nullptr, 0, 0, 0}, FusedJob{nullptr, 0, 0, 0}};
+            CUtensorMap maps[2];
+            for (int s = 0; s < 2; ++s) {
+                const int sl = s < nslots ? slots[s] : slots[0];
+                memcpy(&maps[s], k->tmap_l1[sl], sizeof(CUtensorMap));
+                if (s < nslots) fj[s] = FusedJob{k->d_slots + (size_t)slots[s] * k->slot_bytes, with_derivs[s] ? 1 : 0, batch, first};
+            }
+            FusedLevel fl[3];
+            size_t off = 0;
+            for (int i = 0; i < k->fused_levels; ++i) {
+                const Level& Li = P.lv[1 + i];
+                fl[i] = FusedLevel{Li.w, Li.h, Li.pitch, Li.dpitch, Li.pitch + 2 * kHaloX, staged_rows(Li.h), i == 2 ? 0 : (int)off, Li.img_off, Li.der_off, Li.img_stride, Li.der_stride};
+                off += align_up((size_t)(Li.pitch + 2 * kHaloX) * staged_rows(Li.h), 128);
+            }
+            k->timer.begin(1, st);
+            CU(launch_levels_fused(maps[0], maps[1], fj[0], fj[1], fl, k->fused_levels, k->fused_smem, st));
+            k->timer.end(st);
+            k->launches += 1;
+            break;
+        }
         LevelJob jobs[2];
         bool any = false;
         for (int s = 0; s < 2; ++s) {
@@ -140,7 +224,31 @@ static int build_slots(ekfvio_klt* k, int nslots, const int* slots, const uint8_
         int npitch = 0; size_t nstride = 0;
         if (l + 1 < P.levels) { npitch = P.lv[l + 1].pitch; nstride = P.lv[l + 1].img_stride; }
         k->timer.begin(l < 3 ? l : 3, st);
-        CU(launch_level(jobs[0], jobs[1], L.w, L.h, L.pitch, L.img_stride, L.dpitch, L.der_stride / sizeof(short2), npitch, nstride, st));
+        bool done = false;
+        if (l == 0 && k->tma_ok) {
+            // level 0 staged by TMA: the source is either the caller's image batch (a descriptor is encoded for this call) or the
+            // slot's own level 0 (descriptors made at create time).  Sources TMA cannot address (unaligned base / pitch) take the
+            // cp.async kernel below.
+            CUtensorMap maps[2];
+            TmaJob tj[2] = {TmaJob{nullptr, nullptr, nullptr, 0, 0}, TmaJob{nullptr, nullptr, nullptr, 0, 0}};
+            bool ok = true;
+            for (int s = 0; s < 2 && ok; ++s) {
+                const int sl = s < nslots ? slots[s] : slots[0];
+                if (s < nslots && imgs[s]) {
+                    const uint8_t* src = imgs[s] + (size_t)first * pitch * k->height;
+                    ok = tma_eligible(src, pitch, (size_t)pitch * k->height) && make_tensor_map(&maps[s], src, pitch, k->height, batch, (size_t)pitch * k->height, kTileWords, kTileRows);
+                    if (ok) tj[s] = TmaJob{jobs[s].copy_dst, jobs[s].deriv, jobs[s].down, batch, 0};
+                } else {
+                    memcpy(&maps[s], k->tmap_l0[sl], sizeof(CUtensorMap));
+                    if (s < nslots) tj[s] = TmaJob{nullptr, jobs[s].deriv, jobs[s].down, batch, first};
+                }
+            }
+            if (ok) {
+                CU(launch_level0_tma(maps[0], maps[1], tj[0], tj[1], L.w, L.h, L.pitch, L.img_stride, L.dpitch, L.der_stride / sizeof(short2), npitch, nstride, st));
+                done = true;
+            }
+        }
+        if (!done) CU(launch_level(jobs[0], jobs[1], L.w, L.h, L.pitch, L.img_stride, L.dpitch, L.der_stride / sizeof(short2), npitch, nstride, st));
         k->timer.end(st);
         k->launches += 1;
     }
@@ -260,6 +368,81 @@ int ekfvio_klt_track_pair_h(ekfvio_klt* k, const uint8_t* h_prev, const uint8_t*
     memcpy(h_next_pts, ho, npt * 2 * sizeof(float));
     if (h_err) memcpy(h_err, ho + npt * 2, npt * sizeof(float));
     memcpy(h_status, ho + npt * 3, npt);
+    k->seq_prev = 1;                            // slot 1 now holds the latest frame (its derivatives are built on demand)
+    return 0;
+}
+
+// The tracker inside a sequence (KLTTracker as EKFVIO::addFrame drives it, EKFVIO.cpp:201-217): the previous frame's pyramid is
+// already on the device from the last call, so only the new frame is uploaded; it is built with derivatives because it is the
+// "previous" frame of the next call.  Same chunked upload / build / track overlap as ekfvio_klt_track_pair_h.
+int ekfvio_klt_track_next_h(ekfvio_klt* k, const uint8_t* h_next, int pitch, int batch, const float* h_prev_pts, float* h_next_pts,
+                            uint8_t* h_status, float* h_err, const int* h_npts, void* stream) {
+    if (k->seq_prev < 0) return fail_msg("ekfvio_klt_track_next_h: no previous frame on the device (call ekfvio_klt_track_pair_h first)");
+    const int prev_slot = k->seq_prev, next_slot = prev_slot == 0 ? 1 : 0;
+    if (batch <= 0 || batch > k->max_batch || batch > k->slot_batch[prev_slot]) return fail_msg("ekfvio_klt_track_next_h: batch does not match the previous frame's");
+    CU(cudaSetDevice(k->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Level& L0 = k->pyr.lv[0];
+    uint8_t* sp = k->d_slots + (size_t)prev_slot * k->slot_bytes;
+    uint8_t* sn = k->d_slots + (size_t)next_slot * k->slot_bytes;
+    size_t npt = (size_t)batch * k->max_points;
+    float* hp = k->h_pts;
+    memcpy(hp, h_prev_pts, npt * 2 * sizeof(float));
+    memcpy(hp + npt * 2, h_next_pts, npt * 2 * sizeof(float));
+    int* hn = reinterpret_cast<int*>(hp + (size_t)k->max_batch * k->max_points * 6);
+    memcpy(hn, h_npts, batch * sizeof(int));
+    CU(cudaMemcpyAsync(k->d_prev_pts, hp, npt * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(k->d_next_pts, hp + npt * 2, npt * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(k->d_npts, hn, batch * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(k->d_status, 0, npt, st));
+    CU(cudaMemsetAsync(k->d_err, 0, npt * sizeof(float), st));
+    const uint8_t* none[1] = {nullptr};
+    const int wd[1] = {1};
+    if (!k->slot_has_derivs[prev_slot]) {       // the previous frame came in as the "next" of a pair call: add its derivatives
+        int rc = build_slots(k, 1, &prev_slot, none, 0, batch, wd, st);
+        if (rc) return rc;
+    }
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, h_next) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    if (!pinned) cudaGetLastError();
+    const int nchunks = batch >= 32 ? 4 : 1, per = (batch + nchunks - 1) / nchunks;
+    CU(cudaEventRecord(k->ev_chunk[0], st));
+    CU(cudaStreamWaitEvent(k->copy_st, k->ev_chunk[0], 0));
+    for (int c = 0, first = 0; first < batch; ++c, first += per) {
+        const int nb = batch - first < per ? batch - first : per;
+        const uint8_t* h = h_next + (size_t)first * k->height * pitch;
+        uint8_t* dst = sn + L0.img_off + (size_t)first * L0.img_stride;
+        if (pinned && L0.img_stride == (size_t)L0.pitch * k->height) {
+            CU(cudaMemcpy2DAsync(dst, L0.pitch, h, pitch, k->width, (size_t)k->height * nb, cudaMemcpyHostToDevice, k->copy_st));
+        } else if (pinned) {
+            for (int b = 0; b < nb; ++b)
+                CU(cudaMemcpy2DAsync(dst + (size_t)b * L0.img_stride, L0.pitch, h + (size_t)b * k->height * pitch, pitch, k->width, k->height,
+                                     cudaMemcpyHostToDevice, k->copy_st));
+        } else {
+            uint8_t* stage = k->h_img + (size_t)first * L0.img_stride;
+            for (int b = 0; b < nb; ++b)
+                for (int y = 0; y < k->height; ++y)
+                    memcpy(stage + (size_t)b * L0.img_stride + (size_t)y * L0.pitch, h + ((size_t)b * k->height + y) * pitch, (size_t)k->width);
+            CU(cudaMemcpyAsync(dst, stage, L0.img_stride * nb, cudaMemcpyHostToDevice, k->copy_st));
+        }
+        CU(cudaEventRecord(k->ev_chunk[c & 3], k->copy_st));
+        CU(cudaStreamWaitEvent(st, k->ev_chunk[c & 3], 0));
+        int rc = build_slots(k, 1, &next_slot, none, 0, nb, wd, st, first, batch);
+        if (rc) return rc;
+        k->timer.begin(4, st);
+        CU(launch_track(k->pyr, sp, sn, k->d_prev_pts, k->d_next_pts, k->d_status, k->d_err, k->d_npts, k->max_points, first, nb, k->prm, st));
+        k->timer.end(st);
+        k->launches += 1;
+    }
+    float* ho = hp + npt * 2;
+    CU(cudaMemcpyAsync(ho, k->d_next_pts, npt * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ho + npt * 2, k->d_err, npt * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ho + npt * 3, k->d_status, npt, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(h_next_pts, ho, npt * 2 * sizeof(float));
+    if (h_err) memcpy(h_err, ho + npt * 2, npt * sizeof(float));
+    memcpy(h_status, ho + npt * 3, npt);
+    k->seq_prev = next_slot;
     return 0;
 }
 

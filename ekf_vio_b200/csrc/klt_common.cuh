@@ -61,6 +61,14 @@ struct ekfvio_klt {
     float* h_pts = nullptr;           // pinned: max_batch*max_points*(2+2+1) floats + status bytes
     long long launches = 0;
     KernelTimer timer;
+    int seq_prev = -1;                // slot that holds the latest frame of a sequence (ekfvio_klt_track_pair_h / _track_next_h)
+    // TMA descriptors (CUtensorMap, 128 bytes each, kept as raw words so that this header needs no <cuda.h>): per slot the
+    // level-0 and level-1 images as 3-D tensors of 32-bit words (x/4, y, image); see klt_api.cu make_tensor_map
+    unsigned long long (*tmap_l0)[16] = nullptr;   // [num_slots]
+    unsigned long long (*tmap_l1)[16] = nullptr;   // [num_slots]
+    bool tma_ok = false;                           // driver entry point found and the slot levels are TMA-eligible
+    int fused_levels = 0;                          // levels 1 .. fused_levels are built by klt_levels_fused_kernel (0: per-level launches)
+    size_t fused_smem = 0;
     cudaStream_t copy_st = nullptr;   // uploads of the host-buffer entry point, chunk by chunk
     cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
 };

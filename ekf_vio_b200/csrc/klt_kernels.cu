@@ -6,6 +6,8 @@
 #include <float.h>
 #include <limits.h>
 
+#include <cuda.h>
+
 #include "klt_common.cuh"
 #include "klt_kernels.h"
 
@@ -217,6 +219,291 @@ __global__ void __launch_bounds__(LT, 16) klt_level_kernel(LevelJob j0, LevelJob
     }
 }
 
+// ================================================================================================================
+// TMA-staged pyramid construction (north_star: "TMA-staged image-pyramid construction").
+//
+// The images are described to the tensor memory accelerator as 3-D tensors of 32-bit words (x/4, y, image): one elected
+// thread issues cp.async.bulk.tensor for a whole tile incl. its halo and the bytes land in shared memory behind an
+// mbarrier — no per-thread address arithmetic, no cp.async bookkeeping in the other warps.  A box must start on a 16-byte
+// boundary of the innermost dimension (a start at -8 bytes raises an illegal-instruction fault on the B200, tools/tma_min.cu),
+// hence the 16-pixel halo to the left of every staged tile.  TMA fills out-of-image elements with zeros, OpenCV's pyramid wants BORDER_REFLECT_101: the few halo columns / rows of tiles that touch the image
+// border are patched in shared memory after the tile has landed (the mirrored pixels are inside the same tile).
+//
+//   klt_level0_tma_kernel   level 0 (any level with a TMA-eligible source): 256 x 64 pixel tiles, a warp owns an 8-row band of a
+//                           tile and its lanes 32 consecutive 8-pixel groups, so every shared-memory access of a warp is one
+//                           contiguous 128/256-byte segment (the cp.async kernel above had four row groups of a warp on the same
+//                           banks); two tiles in flight per CTA (double buffer, one mbarrier each).
+//   klt_levels_fused_kernel levels 1 .. 3 of one image per CTA: level 1 arrives by TMA as one box and stays in shared memory
+//                           together with the levels derived from it; derivatives and pyrDown results of all three levels
+//                           leave in one launch instead of three (the small levels were latency / launch bound).
+// Per-thread arithmetic (level_block) is the IDP4A formulation of klt_level_kernel, bit-identical to cv::pyrDown / cv::Scharr.
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 3-D tile (x in 32-bit words, y, image) -> shared memory; completion is signalled on `bar` with the byte count
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, unsigned long long* bar, int cx, int cy, int cz) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(cx), "r"(cy), "r"(cz)
+                 : "memory");
+}
+// generic-proxy accesses to a shared-memory buffer (reads of the previous tile, border patches) are ordered before the
+// async-proxy write of the next TMA into it
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// One thread: 8 columns x RPT rows of a level from a staged tile whose halo is materialised (REFLECT_101 already applied).
+// t0 points at the staged pixel (x - 8, yb - 2).  Optional outputs: pass-through copy, interleaved Scharr derivatives, pyrDown
+// rows of the next level to global memory and / or to a shared-memory image (`down_s`, pixel (0,0) of the next level).
+template <int RPTT>
+__device__ __forceinline__ void level_block(const uint8_t* __restrict__ t0, int tpitch, int x, int yb, int w, int h, uint8_t* __restrict__ copy_img,
+                                            int cpitch, short2* __restrict__ deriv, int dpitch, uint8_t* __restrict__ down, int npitch,
+                                            uint8_t* __restrict__ down_s, int nspitch) {
+    const bool full = x + 7 < w;
+    const int dw = (w + 1) / 2, dh = (h + 1) / 2;
+    const int gx = x / 2, gy = yb / 2;
+    const bool want_down = down || down_s;
+    unsigned win[3][8];                        // Scharr windows (x-1, x, x+1, x+2) of the last three rows
+    unsigned acc[RPTT / 2][4];                 // pyrDown sums of output rows gy .. gy + RPT/2 - 1
+#pragma unroll
+    for (int o = 0; o < RPTT / 2; ++o)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[o][k] = 0u;
+#pragma unroll
+    for (int i = 0; i < RPTT + 3; ++i) {       // staged row i  <->  image row yb - 2 + i
+        const uint8_t* tr = t0 + i * tpitch;
+        const unsigned w0 = *reinterpret_cast<const unsigned*>(tr + 4);     // pixels x-4 .. x-1
+        const uint2 w12 = *reinterpret_cast<const uint2*>(tr + 8);          // pixels x .. x+7
+        const unsigned w3 = *reinterpret_cast<const unsigned*>(tr + 16);    // pixels x+8 .. x+11
+        const unsigned w1 = w12.x, w2 = w12.y;
+        if (copy_img && i >= 2 && i < RPTT + 2) {
+            const int y = yb + i - 2;
+            if (y < h) *reinterpret_cast<uint2*>(copy_img + (size_t)y * cpitch + x) = w12;
+        }
+        if (want_down) {
+            unsigned hz[4];
+            hz[0] = dp4a_uu(w1, 0x00010406u, dp4a_uu(w0, 0x04010000u, 0u));
+            hz[1] = dp4a_uu(w2, 0x00000001u, dp4a_uu(w1, 0x04060401u, 0u));
+            hz[2] = dp4a_uu(w2, 0x00010406u, dp4a_uu(w1, 0x04010000u, 0u));
+            hz[3] = dp4a_uu(w3, 0x00000001u, dp4a_uu(w2, 0x04060401u, 0u));
+#pragma unroll
+            for (int o = 0; o < RPTT / 2; ++o) {
+                const int d = i - (2 * o + 2);
+                const unsigned wv = (d == 0) ? 6u : (d == 1 || d == -1) ? 4u : (d == 2 || d == -2) ? 1u : 0u;
+                if (wv) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc[o][k] += wv * hz[k];
+                }
+                if (d == 2 && gy + o < dh) {   // row complete: round, pack, store
+                    const unsigned r0 = (acc[o][0] + 128u) >> 8, r1 = (acc[o][1] + 128u) >> 8, r2 = (acc[o][2] + 128u) >> 8, r3 = (acc[o][3] + 128u) >> 8;
+                    const unsigned packed = r0 | (r1 << 8) | (r2 << 16) | (r3 << 24);
+                    if (down) {
+                        uint8_t* nd = down + (size_t)(gy + o) * npitch + gx;
+                        if (gx + 3 < dw) *reinterpret_cast<unsigned*>(nd) = packed;
+                        else {
+                            nd[0] = (uint8_t)r0;
+                            if (gx + 1 < dw) nd[1] = (uint8_t)r1;
+                            if (gx + 2 < dw) nd[2] = (uint8_t)r2;
+                        }
+                    }
+                    if (down_s) *reinterpret_cast<unsigned*>(down_s + (gy + o) * nspitch + gx) = packed;   // (columns >= dw are patched afterwards)
+                }
+            }
+        }
+        if (deriv && i >= 1) {
+            unsigned* W = win[i % 3];
+            W[0] = __funnelshift_r(w0, w1, 24);
+            W[1] = w1;
+            W[2] = __funnelshift_r(w1, w2, 8);
+            W[3] = __funnelshift_r(w1, w2, 16);
+            W[4] = __funnelshift_r(w1, w2, 24);
+            W[5] = w2;
+            W[6] = __funnelshift_r(w2, w3, 8);
+            W[7] = __funnelshift_r(w2, w3, 16);
+            if (i >= 3) {
+                const int y = yb + i - 3;
+                if (y < h) {
+                    const unsigned* A = win[(i - 2) % 3];
+                    const unsigned* C = win[(i - 1) % 3];
+                    unsigned o[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        int ix = dp4a_us(A[j], 0x000300FD, 0);
+                        ix = dp4a_us(C[j], 0x000A00F6, ix);
+                        ix = dp4a_us(W[j], 0x000300FD, ix);
+                        int iy = dp4a_us(A[j], 0x00FDF6FD, 0);
+                        iy = dp4a_us(W[j], 0x00030A03, iy);
+                        o[j] = __byte_perm((unsigned)ix, (unsigned)iy, 0x5410);
+                    }
+                    short2* out = deriv + (size_t)y * dpitch + x;
+                    if (full) {
+                        reinterpret_cast<uint4*>(out)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                        reinterpret_cast<uint4*>(out)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) if (x + j < w) reinterpret_cast<unsigned*>(out)[j] = o[j];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// REFLECT_101 halo of a staged image region: `img` points at staged pixel (X0, Y0) of a level of size w x h, the region holds
+// rows [Y0, Y0 + rows) and columns [X0, X0 + cols).  Columns x = -2, -1, w, w + 1 of the in-image rows first, then whole rows
+// y = -2, -1, h, h + 1 (callers synchronise between the two and afterwards).
+__device__ __forceinline__ void patch_cols(uint8_t* img, int pitch, int X0, int Y0, int cols, int rows, int w, int h, int tid, int nthreads) {
+    const bool left = X0 < 0, right = X0 + cols > w;
+    if (!left && !right) return;
+    for (int r = tid; r < rows; r += nthreads) {
+        const int y = Y0 + r;
+        if (y < 0 || y >= h) continue;
+        uint8_t* row = img + r * pitch - X0;                 // row[x] = pixel (x, y)
+        if (left) { row[-1] = row[1]; row[-2] = row[2]; }
+        if (right) { row[w] = row[w - 2]; if (X0 + cols > w + 1) row[w + 1] = row[w - 3]; }
+    }
+}
+__device__ __forceinline__ void patch_rows(uint8_t* img, int pitch, int X0, int Y0, int cols, int rows, int w, int h, int tid, int nthreads) {
+    (void)X0; (void)w;
+    const int words = cols >> 2;
+    for (int k = 0; k < 4; ++k) {
+        const int y = k < 2 ? k - 2 : h + (k - 2);           // -2, -1, h, h + 1
+        const int r = y - Y0;
+        if (r < 0 || r >= rows) continue;
+        const int ys = y < 0 ? -y : 2 * (h - 1) - y, rs = ys - Y0;
+        if (rs < 0 || rs >= rows) continue;
+        const unsigned* src = reinterpret_cast<const unsigned*>(img + rs * pitch);
+        unsigned* dst = reinterpret_cast<unsigned*>(img + r * pitch);
+        for (int c = tid; c < words; c += nthreads) dst[c] = src[c];
+    }
+}
+
+constexpr int ATW = 256, ATH = 64;                 // tile of klt_level0_tma_kernel (pixels)
+constexpr int HX = 16;                             // halo columns staged left and right of a tile (TMA box start: 16-byte aligned)
+constexpr int ASW = ATW + 2 * HX, ASH = ATH + 4;   // staged: x0-16 .. x0+ATW+15, y0-2 .. y0+ATH+1
+constexpr int ANT = 256;                           // threads: 8 warps = 8 row bands of RPT rows, 32 lanes = 32 column groups of 8 pixels
+
+__global__ void __launch_bounds__(ANT, 3) klt_level0_tma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                                                                TmaJob j0, TmaJob j1, int w, int h, int cpitch, size_t cstride, int dpitch,
+                                                                size_t dstride, int npitch, size_t nstride, int tiles_per_cta) {
+    constexpr int TILE_STRIDE = (ASH * ASW + 127) / 128 * 128;   // TMA destinations are 128-byte aligned
+    __shared__ __align__(128) uint8_t tiles[2][TILE_STRIDE];
+    __shared__ __align__(8) unsigned long long bars[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * ATW;
+    int b = blockIdx.z;
+    const bool second = b >= j0.batch;
+    if (second) b -= j0.batch;
+    const TmaJob& J = second ? j1 : j0;
+    if (!J.copy_dst && !J.deriv && !J.down) return;
+    const int ty_begin = blockIdx.y * tiles_per_cta;
+    const int ty_end = min(ty_begin + tiles_per_cta, (h + ATH - 1) / ATH);
+    if (ty_begin >= ty_end) return;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    constexpr unsigned TILE_BYTES = ASH * ASW;
+    auto issue = [&](int ty, int buf) {            // one elected thread
+        mbar_expect_tx(&bars[buf], TILE_BYTES);
+        // (the descriptor must be addressed in parameter space: no pointer selected at run time, which would make a local copy)
+        if (second) tma_load_3d(tiles[buf], &map1, &bars[buf], (x0 - HX) / 4, ty * ATH - 2, J.first + b);
+        else tma_load_3d(tiles[buf], &map0, &bars[buf], (x0 - HX) / 4, ty * ATH - 2, J.first + b);
+    };
+    if (tid == 0) issue(ty_begin, 0);
+    uint8_t* copy_img = J.copy_dst ? J.copy_dst + (size_t)b * cstride : nullptr;
+    short2* deriv = J.deriv ? J.deriv + (size_t)b * dstride : nullptr;
+    uint8_t* down = J.down ? J.down + (size_t)b * nstride : nullptr;
+    for (int ty = ty_begin; ty < ty_end; ++ty) {
+        const int it = ty - ty_begin, buf = it & 1;
+        if (tid == 0 && ty + 1 < ty_end) issue(ty + 1, buf ^ 1);      // (that buffer was released by the __syncthreads ending the previous iteration)
+        mbar_wait(&bars[buf], (it >> 1) & 1);
+        uint8_t* tile = tiles[buf];
+        const int y0 = ty * ATH;
+        const bool border = x0 == 0 || x0 + ATW + HX > w || y0 == 0 || y0 + ATH + 2 > h;
+        if (border) {                              // uniform per CTA
+            patch_cols(tile, ASW, x0 - HX, y0 - 2, ASW, ASH, w, h, tid, ANT);
+            __syncthreads();
+            patch_rows(tile, ASW, x0 - HX, y0 - 2, ASW, ASH, w, h, tid, ANT);
+            __syncthreads();
+        }
+        const int x = x0 + lane * 8, yb = y0 + warp * RPT;
+        if (x < w && yb < h)
+            level_block<RPT>(tile + (warp * RPT) * ASW + lane * 8 + (HX - 8), ASW, x, yb, w, h, copy_img, cpitch, deriv, dpitch, down, npitch, nullptr, 0);
+        fence_proxy_async();
+        __syncthreads();                           // everyone is done with this buffer: it may be refilled by the TMA issued next iteration
+    }
+}
+
+// Levels 1 .. nl of one image per CTA (nl <= 3).  Shared memory: the levels with a halo of HX columns left / right and 2 rows
+// above / below (pitch = level pitch + 2 HX, rows = roundup(h, 8) + 4: a thread's 8-row block may overhang the image); level 3 reuses
+// the space of level 1, which is dead by then.
+constexpr int FNT = 256;
+
+__global__ void __launch_bounds__(FNT, 2) klt_levels_fused_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+                                                                  FusedJob j0, FusedJob j1, FusedLevel l1, FusedLevel l2, FusedLevel l3, int nl) {
+    extern __shared__ __align__(128) uint8_t fsm_raw[];
+    __shared__ __align__(8) unsigned long long bar;
+    uint8_t* fsm = fsm_raw + ((128u - (smem_u32(fsm_raw) & 127u)) & 127u);      // TMA destinations are 128-byte aligned
+    const int tid = threadIdx.x;
+    int b = blockIdx.x;
+    const bool second = b >= j0.batch;
+    if (second) b -= j0.batch;
+    const FusedJob& J = second ? j1 : j0;
+    const int img = J.first + b;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&bar, (unsigned)(l1.spitch * l1.srows));
+        if (second) tma_load_3d(fsm + l1.soff, &map1, &bar, -HX / 4, -2, img);      // the whole level incl. halo: one box
+        else tma_load_3d(fsm + l1.soff, &map0, &bar, -HX / 4, -2, img);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+#pragma unroll
+    for (int li = 0; li < 3; ++li) {
+        if (li >= nl) break;
+        const FusedLevel& L = li == 0 ? l1 : (li == 1 ? l2 : l3);
+        uint8_t* simg = fsm + L.soff;                                    // staged pixel (-HX, -2)
+        patch_cols(simg, L.spitch, -HX, -2, L.spitch, L.srows, L.w, L.h, tid, FNT);
+        __syncthreads();
+        patch_rows(simg, L.spitch, -HX, -2, L.spitch, L.srows, L.w, L.h, tid, FNT);
+        __syncthreads();
+        const bool last = li + 1 >= nl;
+        short2* deriv = J.want_deriv ? reinterpret_cast<short2*>(J.slot + L.der_off + (size_t)img * L.der_stride) : nullptr;
+        uint8_t* down = nullptr; uint8_t* down_s = nullptr; int npitch = 0, nspitch = 0;
+        if (!last) {
+            const FusedLevel& Nx = li == 0 ? l2 : l3;
+            down = J.slot + Nx.img_off + (size_t)img * Nx.img_stride; npitch = Nx.pitch;
+            down_s = fsm + Nx.soff + 2 * Nx.spitch + HX; nspitch = Nx.spitch;
+        }
+        if (deriv || !last) {
+            const int bx = (L.w + 7) / 8, by = (L.h + RPT - 1) / RPT;
+            for (int e = tid; e < bx * by; e += FNT) {
+                const int cx = e % bx, cy = e / bx;
+                const int x = cx * 8, yb = cy * RPT;
+                level_block<RPT>(simg + yb * L.spitch + x + (HX - 8), L.spitch, x, yb, L.w, L.h, nullptr, 0, deriv, L.dpitch, down, npitch, down_s, nspitch);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // exact warp-wide sum of 32-bit partials in 64 bits: two REDUX.SUM on the 16-bit halves
 __device__ __forceinline__ long long warp_sum_ll(int v) {
     const int lo = v & 0xffff, hi = v >> 16;       // v == hi * 65536 + lo
@@ -235,11 +522,15 @@ constexpr int WARPS = 4;      // features per CTA
 constexpr int SEG = 7;        // pixels per row segment: 8 tile bytes give 7 horizontal tap pairs
 
 __host__ __device__ inline int track_segs_per_row(int win) { return (win + SEG - 1) / SEG; }
-// bytes per staged u8 tile row: the last segment reads three aligned words from its start; odd word count
+// bytes per staged u8 tile row: the last segment reads three aligned words from its start.  The word count is == 4 (mod 8): a
+// warp's 32 segment reads span 11 rows x a 4-bank window each, and with a row pitch of 4 banks (mod 32) eight consecutive rows
+// land on distinct banks — two wavefronts per load, the minimum for 11 rows (an odd pitch gave up to three: 44 % of the
+// kernel's shared-memory wavefronts were bank conflicts, profiles/r01_ncu_full_summary.txt)
 __host__ __device__ inline int track_tile_stride(int win) {
     int words = ((SEG * (track_segs_per_row(win) - 1)) >> 2) + 3;
     if (words * 4 < win + 1) words = (win + 4) / 4;
-    return (words | 1) * 4;
+    while ((words & 7) != 4) ++words;
+    return words * 4;
 }
 __host__ __device__ inline size_t track_warp_bytes(int win) {
     size_t nseg = (size_t)win * track_segs_per_row(win), t = ((size_t)win + 1) * (win + 1);
@@ -534,6 +825,34 @@ cudaError_t launch_level(const LevelJob& j0, const LevelJob& j1, int w, int h, i
     const int per = (ty + chunks - 1) / chunks;
     dim3 grid(tx, (ty + per - 1) / per, imgs);
     klt_level_kernel<<<grid, LT, 0, st>>>(j0, j1, w, h, cpitch, cstride, dpitch, dstride, npitch, nstride, per);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_level0_tma(const CUtensorMap& m0, const CUtensorMap& m1, const TmaJob& j0, const TmaJob& j1, int w, int h, int cpitch, size_t cstride,
+                              int dpitch, size_t dstride, int npitch, size_t nstride, cudaStream_t st) {
+    const int tx = (w + ATW - 1) / ATW, ty = (h + ATH - 1) / ATH, imgs = j0.batch + j1.batch;
+    const long long want = 148LL * 6;              // two waves of three resident CTAs per SM; beyond that, CTAs walk down several tiles
+    int chunks = (int)((want + (long long)tx * imgs - 1) / ((long long)tx * imgs));
+    chunks = chunks < 1 ? 1 : (chunks > ty ? ty : chunks);
+    const int per = (ty + chunks - 1) / chunks;
+    dim3 grid(tx, (ty + per - 1) / per, imgs);
+    klt_level0_tma_kernel<<<grid, ANT, 0, st>>>(m0, m1, j0, j1, w, h, cpitch, cstride, dpitch, dstride, npitch, nstride, per);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_levels_fused(const CUtensorMap& m0, const CUtensorMap& m1, const FusedJob& j0, const FusedJob& j1, const FusedLevel* lv, int nl,
+                                size_t smem, cudaStream_t st) {
+    static size_t configured_on[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& configured = configured_on[(dev >= 0 && dev < 64) ? dev : 0];
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(klt_levels_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    FusedLevel z{};
+    klt_levels_fused_kernel<<<j0.batch + j1.batch, FNT, smem, st>>>(m0, m1, j0, j1, lv[0], nl > 1 ? lv[1] : z, nl > 2 ? lv[2] : z, nl);
     return cudaGetLastError();
 }
 

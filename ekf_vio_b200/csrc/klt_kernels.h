@@ -1,10 +1,23 @@
 // Internal interface between klt_api.cu and klt_kernels.cu.
 #pragma once
+#include <cuda.h>
+
 #include "klt_common.cuh"
 
 namespace kltdev {
 cudaError_t launch_level(const LevelJob& j0, const LevelJob& j1, int w, int h, int cpitch, size_t cstride, int dpitch, size_t dstride,
                          int npitch, size_t nstride, cudaStream_t st);
+// TMA-staged pyramid kernels (klt_kernels.cu): level 0 in 256 x 64 tiles, levels 1..3 of an image fused in one CTA
+struct TmaJob {
+    uint8_t* copy_dst; short2* deriv; uint8_t* down;
+    int batch, first;                              // images [first, first + batch) of the tensor map's third dimension
+};
+struct FusedLevel { int w, h, pitch, dpitch, spitch, srows, soff; size_t img_off, der_off, img_stride, der_stride; };   // spitch / srows / soff: staged copy in shared memory
+struct FusedJob { uint8_t* slot; int want_deriv; int batch, first; };
+cudaError_t launch_level0_tma(const CUtensorMap& m0, const CUtensorMap& m1, const TmaJob& j0, const TmaJob& j1, int w, int h, int cpitch, size_t cstride,
+                              int dpitch, size_t dstride, int npitch, size_t nstride, cudaStream_t st);
+cudaError_t launch_levels_fused(const CUtensorMap& m0, const CUtensorMap& m1, const FusedJob& j0, const FusedJob& j1, const FusedLevel* lv, int nl,
+                                size_t smem, cudaStream_t st);
 size_t track_smem_bytes(int win);
 cudaError_t launch_track(const Pyr& pyr, const uint8_t* prev_slot, const uint8_t* next_slot, const float* prev_pts, float* next_pts,
                          uint8_t* status, float* err, const int* npts, int max_points, int first_image, int batch, const ekfvio_klt_params& prm,

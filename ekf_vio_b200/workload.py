@@ -1,4 +1,4 @@
-"""Synthetic workloads for bench.py and the size-independent tests (numpy only, no oracle, no cv2).
+"""Synthetic workloads for bench.py and the size-independent tests (numpy; cv2 only to warp images where it is installed).
 
 EKF streams follow the reference's own simulation harness (test/analyzeEKFSimulation.cpp:10-125):
 landmarks at depth ~0.5 m in front of the camera, a constant body-frame velocity / angular rate
@@ -118,6 +118,69 @@ def klt_pairs(first_seq: int, num_pairs: int, w: int = 640, h: int = 480, npts: 
         pts[i, :, 1] = rng.uniform(40, h - 40, npts)
         flow[i] = (tx, ty)
     return prev, nxt, pts, flow
+
+
+_GOLDEN = None
+
+
+def config2_fixture():
+    """BASELINE.json configs[1]: gray = cvtColor(imread(images/640_480_test.png)), its moved / shear
+    variants and the first 200 FAST(50, nms) corners, from the committed fixture tests/golden/klt_config2.npz (made by
+    tests/golden/make_klt_golden.py from the reference's images; /root/reference is not needed at run time)."""
+    global _GOLDEN
+    if _GOLDEN is None:
+        import os
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "klt_config2.npz")
+        d = np.load(path)
+        _GOLDEN = {k: d[k] for k in ("gray0", "gray_moved", "gray_shear", "pts200", "moved_200_status", "shear_200_status")}
+    return _GOLDEN
+
+
+def _warp_affine_reflect101(img: np.ndarray, M: np.ndarray) -> np.ndarray:
+    """dst = warpAffine(img, M, INTER_LINEAR, BORDER_REFLECT_101): cv2 where it is installed (the GPU box has it), else numpy."""
+    try:
+        import cv2
+        return cv2.warpAffine(img, M.astype(np.float64), (img.shape[1], img.shape[0]), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+    except ImportError:
+        h, w = img.shape
+        A = np.vstack([M, [0, 0, 1]]); Ai = np.linalg.inv(A)
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+        xs = Ai[0, 0] * xx + Ai[0, 1] * yy + Ai[0, 2]; ys = Ai[1, 0] * xx + Ai[1, 1] * yy + Ai[1, 2]
+        x0 = np.floor(xs).astype(int); y0 = np.floor(ys).astype(int); a = xs - x0; b = ys - y0
+
+        def at(yi, xi):
+            xi = np.abs(xi); xi = np.where(xi >= w, 2 * (w - 1) - xi, xi); yi = np.abs(yi); yi = np.where(yi >= h, 2 * (h - 1) - yi, yi)
+            return img[np.clip(yi, 0, h - 1), np.clip(xi, 0, w - 1)].astype(np.float64)
+        v = (1 - a) * (1 - b) * at(y0, x0) + a * (1 - b) * at(y0, x0 + 1) + (1 - a) * b * at(y0 + 1, x0) + a * b * at(y0 + 1, x0 + 1)
+        return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+
+
+def klt_pairs_8d(first_seq: int, num_pairs: int, max_shift: float = 24.0, max_shear: float = 0.05):
+    """SURVEY.md §8d "additional synthetic sequences for rate": the base image of config 2 translated / sheared by a seeded random
+    affine map (|t| <= 24 px, |shear| <= 0.05, seed = sequence index) with warpAffine(INTER_LINEAR, BORDER_REFLECT_101); points =
+    the first 200 FAST(50, nms) corners of the base image.  Returns prev [B,480,640] u8, next, pts [B,200,2] f32, flow [B,2]."""
+    g = config2_fixture()
+    base, pts0 = g["gray0"], g["pts200"]
+    prev = np.repeat(base[None], num_pairs, 0).copy(); nxt = np.zeros_like(prev)
+    pts = np.repeat(pts0[None], num_pairs, 0).astype(np.float32).copy(); flow = np.zeros((num_pairs, 2), np.float32)
+    for i in range(num_pairs):
+        rng = np.random.Generator(np.random.Philox(key=3_000_017 + first_seq + i))
+        tx, ty = rng.uniform(-max_shift, max_shift, 2); sh = rng.uniform(-max_shear, max_shear)
+        M = np.array([[1.0, sh, tx - sh * 240.0], [0.0, 1.0, ty]])
+        nxt[i] = _warp_affine_reflect101(base, M)
+        flow[i] = (tx, ty)
+    return prev, nxt, pts, flow
+
+
+def klt_pairs_config2(num_pairs: int):
+    """Config 2 itself, tiled to a batch: pair 2k = test -> moved, pair 2k+1 = test -> shear, the 200 FAST corners each.  Returns
+    prev, next, pts and the tracked counts cv2 4.13 obtains per pair (190 / 194, status of the golden fixture)."""
+    g = config2_fixture()
+    prev = np.repeat(g["gray0"][None], num_pairs, 0).copy()
+    nxt = np.stack([g["gray_moved"] if i % 2 == 0 else g["gray_shear"] for i in range(num_pairs)])
+    pts = np.repeat(g["pts200"][None], num_pairs, 0).astype(np.float32).copy()
+    expect = np.array([int(g["moved_200_status"].sum()) if i % 2 == 0 else int(g["shear_200_status"].sum()) for i in range(num_pairs)])
+    return prev, nxt, pts, expect
 
 
 def vio_sequences(first_seq: int, num_seq: int, num_frames: int, w: int = 640, h: int = 480, speed: float = 3.0):

@@ -231,6 +231,12 @@ int ekfvio_klt_postprocess(ekfvio_klt* k, const float* d_next_pts, const uint8_t
  * results back; synchronous.  The KLTTracker facade's findNewFeaturePositions is this call. */
 int ekfvio_klt_track_pair_h(ekfvio_klt* k, const uint8_t* h_prev, const uint8_t* h_next, int pitch, int batch, const float* h_prev_pts,
                             float* h_next_pts, uint8_t* h_status, float* h_err, const int* h_npts, void* stream);
+/* The same inside a sequence: the previous frame's pyramid is still on the device from the last ekfvio_klt_track_pair_h /
+ * _track_next_h call, so only the new frame is uploaded (half the host->device traffic) and built — with derivatives, since it is
+ * the previous frame of the next call.  This is KLTTracker::findNewFeaturePositions as EKFVIO::addFrame drives it frame after
+ * frame (EKFVIO.cpp:201-217).  Arguments as ekfvio_klt_track_pair_h without h_prev. */
+int ekfvio_klt_track_next_h(ekfvio_klt* k, const uint8_t* h_next, int pitch, int batch, const float* h_prev_pts, float* h_next_pts,
+                            uint8_t* h_status, float* h_err, const int* h_npts, void* stream);
 
 /* Reads back level `level` of image `img` in slot `slot` (tests): h_img[h_l][w_l] and, if not
  * NULL and the slot has derivatives, h_deriv[h_l][w_l][2] int16.  Synchronous. */
@@ -321,6 +327,20 @@ int ekfvio_frame_resize(const uint8_t* d_src, int src_pitch, int src_width, int 
 /* The same with host buffers (upload, resize, download; synchronous) — what the Frame facade's resizing constructor calls. */
 int ekfvio_frame_resize_h(const uint8_t* h_src, int src_pitch, int src_width, int src_height, int batch, int inv_scale, uint8_t* h_dst,
                           int dst_pitch);
+
+/* ---- Monte-Carlo statistics over the GPUs of a box (the only collective) ------------------------------------
+ * Independent filter / sequence shards never exchange data; the error accumulators that ekfvio_batch_accumulate_errors fills
+ * (the reference has no counterpart: analyzeEKFSimulation.cpp:86-99 inspects one filter by eye) are summed across ranks with
+ * one ncclAllReduce(ncclDouble, ncclSum) over NVLink.  One process per GPU: rank 0 obtains an id, the host application hands
+ * its 128 bytes to the other ranks by any means (bench.py: torch.distributed), every rank creates its communicator. */
+#define EKFVIO_COMM_ID_BYTES 128
+typedef struct ekfvio_comm ekfvio_comm;
+int ekfvio_comm_unique_id(unsigned char* id128);
+int ekfvio_comm_create(ekfvio_comm** out, int device, int nranks, int rank, const unsigned char* id128);
+int ekfvio_comm_destroy(ekfvio_comm* c);
+int ekfvio_comm_size(const ekfvio_comm* c);   /* ranks the communicator really spans (ncclCommCount) */
+/* In-place sum of d_buf[0..n) (device, FP64) over all ranks, enqueued on `stream`. */
+int ekfvio_stats_allreduce(ekfvio_comm* c, double* d_buf, int n, void* stream);
 
 #ifdef __cplusplus
 }

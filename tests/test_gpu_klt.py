@@ -210,3 +210,39 @@ def test_cv2_live_if_available(cuda, gold):
     np.testing.assert_array_equal(st[0], rs[:, 0])
     ok = (rs[:, 0] == 1) & in_killpad(rn[:, 0], 640, 480)
     assert np.abs(nx[0][ok] - rn[:, 0][ok]).max() <= 0.01
+
+
+def test_track_next_h_equals_track_pair_h_along_a_sequence(cuda):
+    """ekfvio_klt_track_next_h (only the new frame uploaded, previous pyramid reused) must give bit-identical positions and status
+    to ekfvio_klt_track_pair_h on the same consecutive frames (KLTTracker as EKFVIO::addFrame drives it, EKFVIO.cpp:201-217)."""
+    from ekf_vio_b200 import capi, workload
+    T, B, npts = 5, 3, 64
+    frames = workload.vio_sequences(0, B, T, 320, 240, speed=2.5)           # [T, B, h, w]
+    rng = np.random.default_rng(3)
+    pts = np.stack([rng.uniform(30, [290, 210], (npts, 2)) for _ in range(B)]).astype(np.float32)
+    n = np.array([npts, npts - 7, 20], np.int32)
+    a = capi.KltTracker(320, 240, B, npts); b = capi.KltTracker(320, 240, B, npts)
+    for t in range(1, T):
+        na = pts.copy(); nb = pts.copy()
+        sa, ea = a.track_pair_h(frames[t - 1], frames[t], pts, na, n)
+        if t == 1:
+            sb, eb = b.track_pair_h(frames[0], frames[1], pts, nb, n)
+        else:
+            sb, eb = b.track_next_h(frames[t], pts, nb, n)
+        for i in range(B):
+            np.testing.assert_array_equal(sa[i, :n[i]], sb[i, :n[i]], err_msg=f"frame {t} image {i} status")
+            np.testing.assert_array_equal(na[i, :n[i]], nb[i, :n[i]], err_msg=f"frame {t} image {i} positions")
+            np.testing.assert_array_equal(ea[i, :n[i]], eb[i, :n[i]])
+    a.close(); b.close()
+
+
+def test_stats_allreduce_single_rank(cuda):
+    """ekfvio_stats_allreduce on a one-rank communicator is the identity (the multi-rank path runs in bench.py --gpus N)."""
+    import torch
+    from ekf_vio_b200 import capi
+    comm = capi.StatsComm(0, 1, 0, lambda raw: raw)
+    assert comm.size() == 1
+    x = torch.arange(8, dtype=torch.float64, device="cuda")
+    comm.allreduce(x); torch.cuda.synchronize()
+    np.testing.assert_array_equal(x.cpu().numpy(), np.arange(8.0))
+    comm.close()
