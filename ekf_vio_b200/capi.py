@@ -76,6 +76,8 @@ SIGNATURES = {
     "ekfvio_batch_reset": (c_int, [c_void_p, c_void_p]),
     "ekfvio_batch_add_features": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ekfvio_batch_graph_replayed": (c_int, [c_void_p, c_int]),
+    "ekfvio_batch_graph_state": (c_int, [c_void_p]),
+    "ekfvio_batch_graph_state_restore": (c_int, [c_void_p, c_int]),
     "ekfvio_batch_remove_features": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ekfvio_batch_process": (c_int, [c_void_p, c_void_p, c_void_p]),
     "ekfvio_batch_process_dt": (c_int, [c_void_p, c_double, c_void_p]),
@@ -104,6 +106,7 @@ SIGNATURES = {
     "ekfvio_klt_num_levels": (c_int, [c_void_p]),
     "ekfvio_klt_build_pyramid": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ekfvio_klt_build_pyramid_pair": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "ekfvio_klt_build_pyramid_pair_ref": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ekfvio_klt_track": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ekfvio_klt_postprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ekfvio_klt_track_pair_h": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -350,6 +353,12 @@ class KltTracker:
     def build_pyramid(self, slot: int, imgs, with_derivs: bool):
         """imgs: uint8 cuda tensor [batch, H, pitch]."""
         _check(lib.ekfvio_klt_build_pyramid(self._h, slot, _ptr(imgs), int(imgs.shape[2]), int(imgs.shape[0]), int(with_derivs), _stream()))
+
+    def build_pyramid_pair_ref(self, prev_slot: int, prev_imgs, next_slot: int, next_imgs, next_with_derivs: bool = False):
+        """build_pyramid_pair without the copy of level 0: the image tensors must stay alive and unchanged until tracking is done."""
+        batch = prev_imgs.shape[0]
+        _check(lib.ekfvio_klt_build_pyramid_pair_ref(self._h, prev_slot, _ptr(prev_imgs), next_slot, _ptr(next_imgs), int(prev_imgs.shape[2]),
+                                                     batch, int(next_with_derivs), _stream()))
 
     def build_pyramid_pair(self, prev_slot: int, prev_imgs, next_slot: int, next_imgs, next_with_derivs: bool = False):
         """Both pyramids of a frame pair, sharing each level's launch. imgs: uint8 cuda [batch, H, pitch]."""

@@ -184,6 +184,14 @@ int ekfvio_batch_graph_replayed(ekfvio_batch* b, int sigma_buffer_flips) {
     return 0;
 }
 
+int ekfvio_batch_graph_state(const ekfvio_batch* b) { return b ? ((b->cur & 1) | (b->upper_stale ? 2 : 0)) : -1; }
+int ekfvio_batch_graph_state_restore(ekfvio_batch* b, int token) {
+    if (!b || token < 0 || token > 3) return fail_msg("ekfvio_batch_graph_state_restore: bad token");
+    b->cur = token & 1; b->upper_stale = (token & 2) != 0;
+    b->state_ev_valid = b->inputs_ev_valid = false;
+    return 0;
+}
+
 int ekfvio_batch_remove_features(ekfvio_batch* b, const uint8_t* d_remove, void* stream) {
     CU(cudaSetDevice(b->device));
     if (b->nmax == 0) return 0;

@@ -73,7 +73,7 @@ int ekfvio_klt_destroy(ekfvio_klt* k) {
     cudaFreeHost(k->h_img); cudaFreeHost(k->h_pts);
     if (k->copy_st) cudaStreamDestroy(k->copy_st);
     for (int i = 0; i < 4; ++i) if (k->ev_chunk[i]) cudaEventDestroy(k->ev_chunk[i]);
-    delete[] k->slot_has_derivs; delete[] k->slot_batch;
+    delete[] k->slot_has_derivs; delete[] k->slot_batch; delete[] k->slot_ext;
     delete[] k->tmap_l0; delete[] k->tmap_l1;
     delete k;
     return 0;
@@ -115,6 +115,7 @@ int ekfvio_klt_create(ekfvio_klt** out, int device, int width, int height, int m
     k->slot_bytes = align_up(off, 256);
     k->slot_has_derivs = new bool[num_slots]();
     k->slot_batch = new int[num_slots]();
+    k->slot_ext = new ExtLevel0[num_slots]();
     size_t npt = (size_t)max_batch * max_points;
     cudaError_t e = cudaMalloc((void**)&k->d_slots, k->slot_bytes * num_slots);
     if (e == cudaSuccess) e = cudaMalloc((void**)&k->d_prev_pts, npt * 2 * sizeof(float));
@@ -178,7 +179,7 @@ long long ekfvio_klt_launch_count(const ekfvio_klt* k) { return k ? k->launches 
 
 // Builds one or two slots level by level; both slots share each level's launch.
 static int build_slots(ekfvio_klt* k, int nslots, const int* slots, const uint8_t* const* imgs, int pitch, int batch, const int* with_derivs,
-                       cudaStream_t st, int first = 0, int total = -1) {   // images [first, first + batch) of a batch of `total`
+                       cudaStream_t st, int first = 0, int total = -1, bool by_ref = false) {   // images [first, first + batch) of a batch of `total`
     const Pyr& P = k->pyr;
     for (int l = 0; l < P.levels; ++l) {
         const Level& L = P.lv[l];
@@ -214,7 +215,7 @@ static int build_slots(ekfvio_klt* k, int nslots, const int* slots, const uint8_
             J.batch = batch;
             if (l == 0 && imgs[s]) {
                 J.src = imgs[s] + (size_t)first * pitch * k->height; J.spitch = pitch; J.sstride = (size_t)pitch * k->height;
-                J.copy_dst = base + L.img_off + (size_t)first * L.img_stride;
+                if (!by_ref) J.copy_dst = base + L.img_off + (size_t)first * L.img_stride;     // (by reference: level 0 stays where the caller has it)
             } else { J.src = base + L.img_off + (size_t)first * L.img_stride; J.spitch = L.pitch; J.sstride = L.img_stride; }
             if (with_derivs[s]) J.deriv = reinterpret_cast<short2*>(base + L.der_off + (size_t)first * L.der_stride);
             if (l + 1 < P.levels) J.down = base + P.lv[l + 1].img_off + (size_t)first * P.lv[l + 1].img_stride;
@@ -252,7 +253,10 @@ static int build_slots(ekfvio_klt* k, int nslots, const int* slots, const uint8_
         k->timer.end(st);
         k->launches += 1;
     }
-    for (int s = 0; s < nslots; ++s) { k->slot_has_derivs[slots[s]] = with_derivs[s] != 0; k->slot_batch[slots[s]] = total < 0 ? batch : total; }
+    for (int s = 0; s < nslots; ++s) {
+        k->slot_has_derivs[slots[s]] = with_derivs[s] != 0; k->slot_batch[slots[s]] = total < 0 ? batch : total;
+        k->slot_ext[slots[s]] = (by_ref && imgs[s]) ? ExtLevel0{imgs[s], pitch, (size_t)pitch * k->height} : ExtLevel0{nullptr, 0, 0};
+    }
     return 0;
 }
 
@@ -274,6 +278,18 @@ int ekfvio_klt_build_pyramid_pair(ekfvio_klt* k, int prev_slot, const uint8_t* d
     return build_slots(k, 2, slots, imgs, pitch, batch, wd, (cudaStream_t)stream);
 }
 
+int ekfvio_klt_build_pyramid_pair_ref(ekfvio_klt* k, int prev_slot, const uint8_t* d_prev, int next_slot, const uint8_t* d_next, int pitch, int batch,
+                                      int next_with_derivs, void* stream) {
+    if (prev_slot < 0 || prev_slot >= k->num_slots || next_slot < 0 || next_slot >= k->num_slots || prev_slot == next_slot || batch <= 0 ||
+        batch > k->max_batch || !d_prev || !d_next || pitch < k->width)
+        return fail_msg("ekfvio_klt_build_pyramid_pair_ref: bad slots, batch or images");
+    CU(cudaSetDevice(k->device));
+    const int slots[2] = {prev_slot, next_slot};
+    const uint8_t* imgs[2] = {d_prev, d_next};
+    const int wd[2] = {1, next_with_derivs};
+    return build_slots(k, 2, slots, imgs, pitch, batch, wd, (cudaStream_t)stream, 0, -1, true);
+}
+
 int ekfvio_klt_track(ekfvio_klt* k, int prev_slot, int next_slot, const float* d_prev_pts, float* d_next_pts, uint8_t* d_status, float* d_err,
                      const int* d_npts, int batch, void* stream) {
     if (prev_slot < 0 || prev_slot >= k->num_slots || next_slot < 0 || next_slot >= k->num_slots) return fail_msg("ekfvio_klt_track: bad slot");
@@ -282,7 +298,7 @@ int ekfvio_klt_track(ekfvio_klt* k, int prev_slot, int next_slot, const float* d
     CU(cudaSetDevice(k->device));
     k->timer.begin(4, (cudaStream_t)stream);
     CU(launch_track(k->pyr, k->d_slots + (size_t)prev_slot * k->slot_bytes, k->d_slots + (size_t)next_slot * k->slot_bytes, d_prev_pts, d_next_pts,
-                    d_status, d_err, d_npts, k->max_points, 0, batch, k->prm, (cudaStream_t)stream));
+                    d_status, d_err, d_npts, k->max_points, 0, batch, k->prm, (cudaStream_t)stream, k->slot_ext[prev_slot], k->slot_ext[next_slot]));
     k->timer.end((cudaStream_t)stream);
     k->launches += 1;
     return 0;
@@ -454,7 +470,11 @@ int ekfvio_klt_read_level(ekfvio_klt* k, int slot, int img, int level, uint8_t* 
     if (h_out) *h_out = L.h;
     CU(cudaDeviceSynchronize());
     uint8_t* base = k->d_slots + (size_t)slot * k->slot_bytes;
-    if (h_img) CU(cudaMemcpy2D(h_img, L.w, base + L.img_off + (size_t)img * L.img_stride, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    if (h_img) {
+        const ExtLevel0& E = k->slot_ext[slot];
+        if (level == 0 && E.img) CU(cudaMemcpy2D(h_img, L.w, E.img + (size_t)img * E.stride, E.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+        else CU(cudaMemcpy2D(h_img, L.w, base + L.img_off + (size_t)img * L.img_stride, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    }
     if (h_deriv) {
         if (!k->slot_has_derivs[slot]) return fail_msg("ekfvio_klt_read_level: slot has no derivatives");
         CU(cudaMemcpy2D(h_deriv, (size_t)L.w * 4, base + L.der_off + (size_t)img * L.der_stride, (size_t)L.dpitch * 4, (size_t)L.w * 4, L.h, cudaMemcpyDeviceToHost));

@@ -29,6 +29,10 @@ struct LevelJob {
     int batch;
 };
 
+// Level 0 of a slot may live in the caller's image batch instead of the slot (ekfvio_klt_build_pyramid_pair_ref): img == nullptr
+// means "in the slot".
+struct ExtLevel0 { const uint8_t* img; int pitch; size_t stride; };
+
 struct Pyr {
     int levels;  // number of levels (effective max level + 1)
     Level lv[KLT_MAX_LEVELS];
@@ -54,6 +58,7 @@ struct ekfvio_klt {
     size_t slot_bytes = 0;
     uint8_t* d_slots = nullptr;       // num_slots * slot_bytes
     bool* slot_has_derivs = nullptr;  // host
+    kltdev::ExtLevel0* slot_ext = nullptr;   // host, [num_slots]: level 0 by reference (see ExtLevel0)
     int* slot_batch = nullptr;        // host
     // staging for the *_h entry point
     float* d_prev_pts = nullptr; float* d_next_pts = nullptr; uint8_t* d_status = nullptr; float* d_err = nullptr; int* d_npts = nullptr;

@@ -4,6 +4,7 @@
 // integer pyrDown/Scharr, Q14 bilinear weights, int16 patches, exact integer window sums,
 // FP32 2x2 solve.  Compiled with --fmad=false so FP32 expressions round as OpenCV's do.
 #include <float.h>
+#include <stdlib.h>
 #include <limits.h>
 
 #include <cuda.h>
@@ -526,15 +527,16 @@ __host__ __device__ inline int track_segs_per_row(int win) { return (win + SEG -
 // warp's 32 segment reads span 11 rows x a 4-bank window each, and with a row pitch of 4 banks (mod 32) eight consecutive rows
 // land on distinct banks — two wavefronts per load, the minimum for 11 rows (an odd pitch gave up to three: 44 % of the
 // kernel's shared-memory wavefronts were bank conflicts, profiles/r01_ncu_full_summary.txt)
-__host__ __device__ inline int track_tile_stride(int win) {
+__host__ __device__ inline int track_tile_stride(int win, int mode = 1) {
     int words = ((SEG * (track_segs_per_row(win) - 1)) >> 2) + 3;
     if (words * 4 < win + 1) words = (win + 4) / 4;
+    if (mode == 0) return (words | 1) * 4;         // (round 1's odd pitch, kept for A/B measurements: EKFVIO_KLT_TRACK_STRIDE=0)
     while ((words & 7) != 4) ++words;
     return words * 4;
 }
-__host__ __device__ inline size_t track_warp_bytes(int win) {
+__host__ __device__ inline size_t track_warp_bytes(int win, int mode = 1) {
     size_t nseg = (size_t)win * track_segs_per_row(win), t = ((size_t)win + 1) * (win + 1);
-    size_t bytes = nseg * 8 * 4 /*Cp*/ + nseg * 8 * 4 /*dI*/ + t * 4 /*Dt*/ + ((size_t)win + 1) * track_tile_stride(win) /*Jt*/;
+    size_t bytes = nseg * 8 * 4 /*Cp*/ + nseg * 8 * 4 /*dI*/ + t * 4 /*Dt*/ + ((size_t)win + 1) * track_tile_stride(win, mode) /*Jt*/;
     return (bytes + 15) & ~(size_t)15;
 }
 
@@ -583,15 +585,15 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
                                                                const float* __restrict__ prev_pts, float* __restrict__ next_pts,
                                                                uint8_t* __restrict__ status, float* __restrict__ err, const int* __restrict__ npts,
                                                                int max_points, int win, int max_count, double epsilon, double min_eig,
-                                                               int use_initial_flow, int first_image) {
+                                                               int use_initial_flow, int first_image, int stride_mode, ExtLevel0 prev_ext, ExtLevel0 next_ext) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y + first_image;      // (a launch may cover a sub-range of the batch: chunked uploads)
     const int pt = blockIdx.x * WARPS + warp;
     if (pt >= npts[b]) return;
     const int jw1 = win + 1, tarea = jw1 * jw1;
-    const int SPR = track_segs_per_row(win), nseg = win * SPR, JS = track_tile_stride(win);
-    uint8_t* base = smem_raw + warp * track_warp_bytes(win);
+    const int SPR = track_segs_per_row(win), nseg = win * SPR, JS = track_tile_stride(win, stride_mode);
+    uint8_t* base = smem_raw + warp * track_warp_bytes(win, stride_mode);
     int* Cp = reinterpret_cast<int*>(base);
     unsigned* dI = reinterpret_cast<unsigned*>(Cp + nseg * 8);
     short2* Dt = reinterpret_cast<short2*>(dI + nseg * 8);
@@ -610,15 +612,15 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
     const int top = pyr.levels - 1;
 
     // stage a (win+1)^2 tile of an 8-bit image at (ox, oy) with REFLECT_101 borders
-    auto stage_u8 = [&](const uint8_t* img, const Level& L, int ox, int oy) {
+    auto stage_u8 = [&](const uint8_t* img, int ipitch, const Level& L, int ox, int oy) {
         if (lane < jw1) {
             const bool inside = ox >= 0 && oy >= 0 && ox + win < L.w && oy + win < L.h;
             if (inside) {
-                const uint8_t* p = img + (size_t)oy * L.pitch + ox + lane;
-                for (int y = 0; y < jw1; ++y) Jt[y * JS + lane] = p[(size_t)y * L.pitch];
+                const uint8_t* p = img + (size_t)oy * ipitch + ox + lane;
+                for (int y = 0; y < jw1; ++y) Jt[y * JS + lane] = p[(size_t)y * ipitch];
             } else {
                 const int cx = reflect101(ox + lane, L.w);
-                for (int y = 0; y < jw1; ++y) Jt[y * JS + lane] = img[(size_t)reflect101(oy + y, L.h) * L.pitch + cx];
+                for (int y = 0; y < jw1; ++y) Jt[y * JS + lane] = img[(size_t)reflect101(oy + y, L.h) * ipitch + cx];
             }
         }
         __syncwarp();
@@ -626,8 +628,11 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
 
     for (int level = top; level >= 0; --level) {
         const Level L = pyr.lv[level];
-        const uint8_t* I = prev_slot + L.img_off + (size_t)b * L.img_stride;
-        const uint8_t* J = next_slot + L.img_off + (size_t)b * L.img_stride;
+        // level 0 may be the caller's own image batch (ekfvio_klt_build_pyramid_pair_ref)
+        const bool iext = level == 0 && prev_ext.img, jext = level == 0 && next_ext.img;
+        const uint8_t* I = iext ? prev_ext.img + (size_t)b * prev_ext.stride : prev_slot + L.img_off + (size_t)b * L.img_stride;
+        const uint8_t* J = jext ? next_ext.img + (size_t)b * next_ext.stride : next_slot + L.img_off + (size_t)b * L.img_stride;
+        const int ipitch = iext ? prev_ext.pitch : L.pitch, jpitch = jext ? next_ext.pitch : L.pitch;
         const short2* dIm = reinterpret_cast<const short2*>(prev_slot + L.der_off + (size_t)b * L.der_stride);
         const float scale = (float)(1. / (1 << level));
         float px = prevx * scale, py = prevy * scale;
@@ -647,7 +652,7 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
         lk_weights(px - ipx, py - ipy, w00, w01, w10, w11);
         // stage the I tile (into Jt) and the derivative tile (zero outside the image)
         __syncwarp();
-        stage_u8(I, L, ipx, ipy);
+        stage_u8(I, ipitch, L, ipx, ipy);
         if (lane < jw1) {
             const int X = ipx + lane;
             const bool xin = (unsigned)X < (unsigned)L.w;
@@ -711,7 +716,7 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
             lk_weights(nx - inx, ny - iny, w00, w01, w10, w11);
             if (inx != sjx || iny != sjy) {       // the staged J tile is reused while the integer cell does not move
                 __syncwarp();
-                stage_u8(J, L, inx, iny);
+                stage_u8(J, jpitch, L, inx, iny);
                 sjx = inx; sjy = iny;
             }
             int sb1 = 0, sb2 = 0;                 // <= 35 slots x 8160 x 4080 fits 32 bits
@@ -755,7 +760,7 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
                 lk_weights(fx - inx, fy - iny, w00, w01, w10, w11);
                 if (inx != sjx || iny != sjy) {
                     __syncwarp();
-                    stage_u8(J, L, inx, iny);
+                    stage_u8(J, jpitch, L, inx, iny);
                 }
                 int es = 0;                       // <= 35 slots x 8160
                 {
@@ -856,18 +861,23 @@ cudaError_t launch_levels_fused(const CUtensorMap& m0, const CUtensorMap& m1, co
     return cudaGetLastError();
 }
 
-size_t track_smem_bytes(int win) { return track_warp_bytes(win) * WARPS; }
+static int track_stride_mode() {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("EKFVIO_KLT_TRACK_STRIDE"); mode = (e && e[0] == '0') ? 0 : 1; }
+    return mode;
+}
+size_t track_smem_bytes(int win) { return track_warp_bytes(win, track_stride_mode()) * WARPS; }
 
 cudaError_t launch_track(const Pyr& pyr, const uint8_t* prev_slot, const uint8_t* next_slot, const float* prev_pts, float* next_pts,
                          uint8_t* status, float* err, const int* npts, int max_points, int first_image, int batch, const ekfvio_klt_params& prm,
-                         cudaStream_t st) {
+                         cudaStream_t st, ExtLevel0 prev_ext, ExtLevel0 next_ext) {
     int mc = prm.max_iterations < 0 ? 0 : (prm.max_iterations > 100 ? 100 : prm.max_iterations);
     double eps = prm.epsilon < 0 ? 0 : (prm.epsilon > 10 ? 10 : prm.epsilon);
     eps *= eps;
     dim3 grid((max_points + WARPS - 1) / WARPS, batch);
     klt_track_kernel<<<grid, WARPS * 32, track_smem_bytes(prm.window_size), st>>>(pyr, prev_slot, next_slot, prev_pts, next_pts, status, err, npts,
                                                                                  max_points, prm.window_size, mc, eps, prm.min_eigen,
-                                                                                 prm.use_initial_flow, first_image);
+                                                                                 prm.use_initial_flow, first_image, track_stride_mode(), prev_ext, next_ext);
     return cudaGetLastError();
 }
 

@@ -21,7 +21,7 @@ cudaError_t launch_levels_fused(const CUtensorMap& m0, const CUtensorMap& m1, co
 size_t track_smem_bytes(int win);
 cudaError_t launch_track(const Pyr& pyr, const uint8_t* prev_slot, const uint8_t* next_slot, const float* prev_pts, float* next_pts,
                          uint8_t* status, float* err, const int* npts, int max_points, int first_image, int batch, const ekfvio_klt_params& prm,
-                         cudaStream_t st);
+                         cudaStream_t st, ExtLevel0 prev_ext = ExtLevel0{nullptr, 0, 0}, ExtLevel0 next_ext = ExtLevel0{nullptr, 0, 0});
 cudaError_t launch_postprocess(const float* next_pts, const uint8_t* status, const int* npts, const float* K9, int max_points, int batch,
                                int cols, int rows, int kill_pad, float* measured, float* cov, uint8_t* passed, cudaStream_t st);
 }  // namespace kltdev

@@ -22,6 +22,9 @@ struct KernelTimer {
     }
     void begin(int id, cudaStream_t st) {
         if (!on) return;
+        // timing events must not become nodes of a caller's CUDA graph (ekfvio_vio_add_frame records these entry points)
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cur_id = -1; return; }
         cur_a = get(); cur_id = id;
         cudaEventRecord(cur_a, st);
     }

@@ -39,6 +39,7 @@ struct ekfvio_vio {
     uint8_t* d_frames_in = nullptr; float* d_K_in = nullptr; double* d_dt_in = nullptr;
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     long long graph_launches[2] = {0, 0};    // kernel launches one replay stands for
+    int graph_batch_state[2] = {-1, -1};     // ekfvio_batch_graph_state at capture: a graph is only replayed in that state
     int parity_seen[2] = {0, 0};
     cudaStream_t own_st = nullptr;           // capture is not allowed on the legacy default stream: graph frames of such callers run here
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -229,17 +230,26 @@ int ekfvio_vio_add_frame(ekfvio_vio* v, const uint8_t* d_frames, int pitch, cons
     CU(cudaMemcpyAsync(v->d_K_in, d_K9, (size_t)v->S * 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     CU(cudaMemcpyAsync(v->d_dt_in, d_dt, (size_t)v->S * sizeof(double), cudaMemcpyDeviceToDevice, st));
     bool captured_now = false;                                   // (the capture pass already did the host-side bookkeeping)
+    // The graph has the batch's Sigma ping-pong buffer baked in: if somebody stepped the batch behind the loop's back
+    // (ekfvio_vio_filters() hands it out), the recording is stale — drop it and record again from the present state.
+    if (v->graph[parity] && v->graph_batch_state[parity] != ekfvio_batch_graph_state(v->ekf)) {
+        cudaGraphExecDestroy(v->graph[parity]);
+        v->graph[parity] = nullptr;
+    }
     if (!v->graph[parity]) {
         captured_now = true;
         const long long before = ekfvio_vio_launch_count(v);
         const int frames = v->frames, slot = v->cur_slot;
+        const int batch_state = ekfvio_batch_graph_state(v->ekf);
         CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         const int rc = enqueue_frame(v, v->d_frames_in, v->width, v->d_K_in, v->d_dt_in, stream);
         cudaGraph_t g = nullptr;
         cudaError_t e = cudaStreamEndCapture(st, &g);
         v->frames = frames; v->cur_slot = slot;              // the recorded frame has not run yet
+        if (rc || e != cudaSuccess) ekfvio_batch_graph_state_restore(v->ekf, batch_state);   // nothing of the recording ran: undo the batch's bookkeeping too
         if (rc) { if (g) cudaGraphDestroy(g); return rc; }
         if (e != cudaSuccess) return ekfvio::fail("cudaStreamEndCapture", e);
+        v->graph_batch_state[parity] = batch_state;
         v->graph_launches[parity] = ekfvio_vio_launch_count(v) - before;
         v->launches -= v->graph_launches[parity];            // counted again by the launch below
         e = cudaGraphInstantiate(&v->graph[parity], g, 0);

@@ -87,6 +87,11 @@ int ekfvio_batch_add_features(ekfvio_batch* b, const int* d_k, const double* d_u
  * kernels but none of the host-side bookkeeping of the calls it stands for.  Tell the batch how many Sigma buffer flips the
  * replayed sequence contains (process, update and remove_features flip once each); its copy-stream events are invalidated. */
 int ekfvio_batch_graph_replayed(ekfvio_batch* b, int sigma_buffer_flips);
+/* A captured graph has the batch's Sigma ping-pong buffer baked into its kernel arguments: it may only be replayed while the batch
+ * is in the state it was captured in.  ekfvio_batch_graph_state returns that state as an opaque token (compare tokens for equality
+ * before a replay; re-capture on mismatch); _restore puts back a token taken before a capture that failed half way. */
+int ekfvio_batch_graph_state(const ekfvio_batch* b);
+int ekfvio_batch_graph_state_restore(ekfvio_batch* b, int token);
 
 /* Feature removal.  The reference only flags lost features (TightlyCoupledEKF.cpp:524-528, Feature::delete_flag)
  * and never deletes them; this marginalises features out of the state: mean entries and rows/columns of Sigma are deleted, the
@@ -211,6 +216,11 @@ int ekfvio_klt_build_pyramid(ekfvio_klt* k, int slot, const uint8_t* d_imgs, int
  * in the slot". */
 int ekfvio_klt_build_pyramid_pair(ekfvio_klt* k, int prev_slot, const uint8_t* d_prev, int next_slot, const uint8_t* d_next, int pitch,
                                   int batch, int next_with_derivs, void* stream);
+/* The same without the pass-through copy of level 0: the slots reference the caller's image batches, which must stay alive and
+ * unmodified until the last ekfvio_klt_track on these slots (cv::calcOpticalFlowPyrLK's own contract: the images belong to the
+ * caller for the duration of the call, KLTTracker.cpp:61-64).  Saves 2 x width x height bytes of HBM writes per pair. */
+int ekfvio_klt_build_pyramid_pair_ref(ekfvio_klt* k, int prev_slot, const uint8_t* d_prev, int next_slot, const uint8_t* d_next, int pitch,
+                                      int batch, int next_with_derivs, void* stream);
 
 /* LKTrackerInvoker over all levels (cv::calcOpticalFlowPyrLK, KLTTracker.cpp:61-64) between
  * pyramid slots prev_slot (needs derivatives) and next_slot.  d_prev_pts[batch][max_points][2]

@@ -494,15 +494,15 @@ def test_config3_stream_100_steps(cuda, flags):
             e_true = max(rel(g_full, x_full), rel(g_P, ex["P"]))                  # batch vs the extended-precision result
             gate = max(TOL, 100 * e_orc)
             assert e <= gate, f"config 3 filter {f} step {s} (route {after['route'][f]}): one-step error {e:.3e}, the FP64 oracle's own error {e_orc:.3e}"
-            if gate > TOL:
-                wide += 1; worst_ratio = max(worst_ratio, e_true / e_orc)
+            if e > TOL:
+                wide += 1; worst_ratio = max(worst_ratio, e / e_orc)
             else:
                 worst_tight = max(worst_tight, e); worst_true = max(worst_true, e_true)
         before = after
-    print(f"config 3 stream, {len(check)} of {F} filters x {steps} steps: worst one-step error vs the oracle {worst_tight:.3e} (vs extended precision {worst_true:.3e}) on the "
-          f"{len(check) * steps - wide} steps gated at 1e-9; {wide} ill-conditioned steps gated by the FP64 oracle's own error (worst batch error / oracle error "
-          f"{worst_ratio:.1f}); update routes reduced / Joseph symmetric / Joseph full {routes.tolist()}")
-    assert wide <= 0.25 * len(check) * steps          # (9 of the 12 checked filters are arbitrary, 3 are picked for their spikes)
+    print(f"config 3 stream, {len(check)} of {F} filters x {steps} steps: {len(check) * steps - wide} steps within 1e-9 of the oracle (worst {worst_tight:.3e}; vs extended "
+          f"precision {worst_true:.3e}); {wide} ill-conditioned steps beyond 1e-9, all within 100 x the FP64 oracle's own error of the step (worst ratio {worst_ratio:.1f}); "
+          f"update routes reduced / Joseph symmetric / Joseph full {routes.tolist()}")
+    assert wide <= 0.15 * len(check) * steps          # (9 of the 12 checked filters are arbitrary, 3 are picked for their spikes)
     b.close()
 
 

@@ -246,3 +246,29 @@ def test_stats_allreduce_single_rank(cuda):
     comm.allreduce(x); torch.cuda.synchronize()
     np.testing.assert_array_equal(x.cpu().numpy(), np.arange(8.0))
     comm.close()
+
+
+def test_pyramid_pair_by_reference_tracks_like_the_copying_build(cuda):
+    """ekfvio_klt_build_pyramid_pair_ref keeps level 0 in the caller's buffers (no pass-through copy): levels, derivatives, tracked
+    positions and status must be bit-identical to the copying build — aligned and unaligned pitch (TMA and cp.async staging)."""
+    import torch
+    from ekf_vio_b200 import capi, workload
+    for w, h, pitch in ((640, 480, 640), (320, 240, 328), (333, 197, 333)):
+        B, npts = 3, 48
+        prev, nxt, pts, _ = workload.klt_pairs(5, B, w, h, npts)
+        pp = np.zeros((B, h, pitch), np.uint8); nn_ = np.zeros_like(pp); pp[:, :, :w] = prev; nn_[:, :, :w] = nxt
+        dp, dn = torch.from_numpy(pp).cuda(), torch.from_numpy(nn_).cuda()
+        dpts = torch.from_numpy(pts).cuda(); n = torch.full((B,), npts, dtype=torch.int32, device="cuda")
+        res = []
+        for by_ref in (False, True):
+            t = capi.KltTracker(w, h, B, npts)
+            (t.build_pyramid_pair_ref if by_ref else t.build_pyramid_pair)(0, dp, 1, dn, False)
+            out = dpts.clone(); st = torch.zeros(B, npts, dtype=torch.uint8, device="cuda"); er = torch.zeros(B, npts, device="cuda")
+            t.track(0, 1, dpts, out, st, er, n); torch.cuda.synchronize()
+            lv = [t.read_level(0, 1, l, True) for l in range(t.num_levels)]
+            res.append((out.cpu().numpy(), st.cpu().numpy(), er.cpu().numpy(), lv))
+            t.close()
+        np.testing.assert_array_equal(res[0][0], res[1][0]); np.testing.assert_array_equal(res[0][1], res[1][1]); np.testing.assert_array_equal(res[0][2], res[1][2])
+        for a, b in zip(res[0][3], res[1][3]):
+            np.testing.assert_array_equal(a[0], b[0]); np.testing.assert_array_equal(a[1], b[1])
+        assert res[0][1].sum() > 0.8 * B * npts
