@@ -76,6 +76,8 @@ SIGNATURES = {
     "ekfvio_batch_reset": (c_int, [c_void_p, c_void_p]),
     "ekfvio_batch_add_features": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ekfvio_batch_graph_replayed": (c_int, [c_void_p, c_int]),
+    "ekfvio_batch_convolve_base_h": (c_int, [c_void_p, c_int, c_void_p, c_double, c_void_p]),
+    "ekfvio_batch_convolve_feature_h": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_double, c_void_p]),
     "ekfvio_batch_graph_state": (c_int, [c_void_p]),
     "ekfvio_batch_graph_state_restore": (c_int, [c_void_p, c_int]),
     "ekfvio_batch_remove_features": (c_int, [c_void_p, c_void_p, c_void_p]),
@@ -245,6 +247,17 @@ class EkfBatch:
         }
         _check(lib.ekfvio_batch_get_state(self._h, _ptr(out["mu"]), _ptr(out["feat"]), _ptr(out["P"]), _ptr(out["nfeat"]),
                                           _ptr(out["cache"]), _ptr(out["flags"]), _ptr(out["klt_last"]), _ptr(out["status"])))
+        return out
+
+    def convolve_base_h(self, base22, dt: float, f: int = 0):
+        base22 = np.ascontiguousarray(base22, np.float64); out = np.zeros(22)
+        _check(lib.ekfvio_batch_convolve_base_h(self._h, f, _ptr(base22), float(dt), _ptr(out)))
+        return out
+
+    def convolve_feature_h(self, base22, feat3, dt: float, f: int = 0):
+        """One convolveFeature call against filter f's omega-keyed dq_inv cache (E2 semantics)."""
+        base22 = np.ascontiguousarray(base22, np.float64); feat3 = np.ascontiguousarray(feat3, np.float64); out = np.zeros(3)
+        _check(lib.ekfvio_batch_convolve_feature_h(self._h, f, _ptr(base22), _ptr(feat3), float(dt), _ptr(out)))
         return out
 
     def get_state_range(self, first: int, count: int, want_P: bool = True) -> dict:

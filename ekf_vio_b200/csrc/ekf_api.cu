@@ -80,6 +80,7 @@ int ekfvio_batch_destroy(ekfvio_batch* b) {
     if (b->ev_h2d) cudaEventDestroy(b->ev_h2d);
     if (b->ev_inputs_free) cudaEventDestroy(b->ev_inputs_free);
     if (b->ev_state) cudaEventDestroy(b->ev_state);
+    if (b->ev_entry) cudaEventDestroy(b->ev_entry);
     delete b;
     return 0;
 }
@@ -145,7 +146,8 @@ int ekfvio_batch_create(ekfvio_batch** out, int device, int num_filters, int max
     if (cudaStreamCreateWithFlags(&b->copy_st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_inputs_free, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&b->ev_state, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&b->ev_state, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b->ev_entry, cudaEventDisableTiming) != cudaSuccess) {
         ekfvio_batch_destroy(b);
         return fail_msg("stream / event creation failed");
     }
@@ -445,6 +447,8 @@ int ekfvio_batch_update_h(ekfvio_batch* b, const double* h_z, const double* h_R,
     void* dst[3] = {b->dd_z, b->dd_R, b->dd_pass};
     const size_t bytes[3] = {F * nm * 2 * sizeof(double), F * nm * 4 * sizeof(double), F * nm};
     if (b->inputs_ev_valid) CU(cudaStreamWaitEvent(b->copy_st, b->ev_inputs_free, 0));
+    // (not ordered behind earlier work on `stream`: that is what lets the upload overlap process(); the host buffers must hold
+    // their final contents when this function is called — see include/ekfvio_c.h)
     bool synced = false;
     for (int i = 0; i < 3; ++i) {
         cudaPointerAttributes attr;
@@ -459,6 +463,35 @@ int ekfvio_batch_update_h(ekfvio_batch* b, const double* h_z, const double* h_R,
     CU(cudaEventRecord(b->ev_h2d, b->copy_st));
     CU(cudaStreamWaitEvent(st, b->ev_h2d, 0));
     return ekfvio_batch_update(b, b->dd_z, b->dd_R, b->dd_pass, stream);
+}
+
+// convolveBaseState / convolveFeature as single evaluations (TightlyCoupledEKF.cpp:328-460).  Filter `f` of the batch supplies
+// and receives the dq_inv cache that convolveFeature keys on omega alone (E2); the filter's state is not touched.
+static int convolve_single(ekfvio_batch* b, int f, const double* h_base, const double* h_feat3, double dt, int which, double* h_out) {
+    if (!b || f < 0 || f >= b->F || !h_base || !h_out || (which == 1 && !h_feat3)) return fail_msg("ekfvio_batch_convolve: bad arguments");
+    CU(cudaSetDevice(b->device));
+    double io[57] = {0};
+    memcpy(io, h_base, BASE * sizeof(double));
+    if (which == 1) memcpy(io + 22, h_feat3, 3 * sizeof(double));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(io + 25, b->d_cache + (size_t)f * 7, 7 * sizeof(double), cudaMemcpyDeviceToHost));
+    double* d_io = nullptr;
+    CU(cudaMalloc((void**)&d_io, sizeof(io)));
+    cudaError_t e = cudaMemcpy(d_io, io, sizeof(io), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_convolve_single(d_io, dt, which, (b->prm.flags & EKFVIO_FLAG_FRESH_DQ_CACHE) ? 1 : 0, nullptr);
+    b->launches += 1;
+    if (e == cudaSuccess) e = cudaMemcpy(io, d_io, sizeof(io), cudaMemcpyDeviceToHost);
+    cudaFree(d_io);
+    if (e != cudaSuccess) return ekfvio::fail("ekfvio_batch_convolve", e);
+    if (which == 1) CU(cudaMemcpy(b->d_cache + (size_t)f * 7, io + 25, 7 * sizeof(double), cudaMemcpyHostToDevice));
+    memcpy(h_out, which == 0 ? io + 32 : io + 54, (which == 0 ? BASE : 3) * sizeof(double));
+    return 0;
+}
+int ekfvio_batch_convolve_base_h(ekfvio_batch* b, int f, const double* h_base22, double dt, double* h_out22) {
+    return convolve_single(b, f, h_base22, nullptr, dt, 0, h_out22);
+}
+int ekfvio_batch_convolve_feature_h(ekfvio_batch* b, int f, const double* h_base22, const double* h_feat3, double dt, double* h_out3) {
+    return convolve_single(b, f, h_base22, h_feat3, dt, 1, h_out3);
 }
 
 int ekfvio_batch_linearize_h(ekfvio_batch* b, double dt, double* h_F) {

@@ -169,7 +169,7 @@ struct ekfvio_batch {
     // host-buffer entry points: copies run on their own stream, ordered against the kernels by events, so
     // the upload of a step's measurements overlaps process() and the state download overlaps the covariance update
     cudaStream_t copy_st = nullptr;
-    cudaEvent_t ev_h2d = nullptr, ev_inputs_free = nullptr, ev_state = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_inputs_free = nullptr, ev_state = nullptr, ev_entry = nullptr;
     bool inputs_ev_valid = false, state_ev_valid = false;
     // lower mode: process() of a batch on the reduced tiled update path leaves the feature rows of symmetric filters
     // complete only up to their diagonal blocks; the update that follows restores the full matrix, any other reader

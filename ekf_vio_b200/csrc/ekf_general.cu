@@ -818,6 +818,23 @@ __global__ void ekf_mirror_lower_kernel(EkfPtrs p, double* __restrict__ P0) {
     }
 }
 
+// One call of TightlyCoupledEKF::convolveBaseState / convolveFeature (:328-395, :397-460) on the device, exactly as a caller of the
+// reference class gets it: convolveFeature consults the dq_inv cache keyed on omega ONLY (E2) — a hit reuses the rotation cached
+// for whatever dt it was computed with, a miss recomputes it for this dt and stores it.  io[0..21] base state, io[22..24] feature,
+// io[25..31] cache (in/out), io[32..56] results (22 base | 3 feature).  which: 0 base, 1 feature.
+__global__ void ekf_convolve_single_kernel(double* io, double dt, int which, int fresh) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (which == 0) { convolve_base(io, dt, io + 32); return; }
+    double* c = io + 25;
+    Q4 dqi;
+    if (!fresh && c[0] == io[10] && c[1] == io[11] && c[2] == io[12]) dqi = {c[3], c[4], c[5], c[6]};
+    else {
+        dqi = delta_quat(io[10], io[11], io[12], dt, -1.0);
+        c[0] = io[10]; c[1] = io[11]; c[2] = io[12]; c[3] = dqi.w; c[4] = dqi.x; c[5] = dqi.y; c[6] = dqi.z;
+    }
+    convolve_feature(dqi, V3{io[7], io[8], io[9]}, V3{io[13], io[14], io[15]}, dt, io[22], io[23], io[24], io + 54);
+}
+
 __global__ void ekf_fill_dt_kernel(double* dts, double dt, int F) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < F) dts[i] = dt;
@@ -938,6 +955,11 @@ cudaError_t launch_joseph_general(const EkfPtrs& p, const double* Pin, double* P
     int tiles = (p.Nmax + 31) / 32;
     dim3 grid(tiles, tiles, only_route >= 0 ? (p.F < 16 ? p.F : 16) : p.F);
     ekf_joseph_general<<<grid, 256, 0, st>>>(p, Pin, Pout, only_route);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_convolve_single(double* d_io, double dt, int which, int fresh, cudaStream_t st) {
+    ekf_convolve_single_kernel<<<1, 32, 0, st>>>(d_io, dt, which, fresh);
     return cudaGetLastError();
 }
 

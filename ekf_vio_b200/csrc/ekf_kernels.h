@@ -53,6 +53,7 @@ cudaError_t launch_gain_general(const EkfPtrs& p, const double* Pin, const doubl
                                 cudaStream_t st, int only_route = -1);
 cudaError_t launch_joseph_general(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st, int only_route = -1);
 size_t gain_general_smem_doubles(int mmax);
+cudaError_t launch_convolve_single(double* d_io, double dt, int which, int fresh, cudaStream_t st);
 cudaError_t launch_reset(const EkfPtrs& p, double* P0, cudaStream_t st);
 cudaError_t launch_add_features(const EkfPtrs& p, double* P0, const int* ks, const double* uv, int kmax, cudaStream_t st);
 cudaError_t launch_remove_features(const EkfPtrs& p, const double* Pin, double* Pout, const uint8_t* remove, cudaStream_t st);

@@ -249,20 +249,20 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
     // lower(a,b), a >= b  <-  upper(S)(b,a) = Sigma(idx[b], idx[a]) + R(b,a)  (SimplicialLDLT::compute(S')
     // reads upper(S), :578); identity tail.  Four independent gathers in flight per thread.
     {
-        const int total = nb * (nb + 1) / 2 * 64;
-        for (int e0 = tid; e0 < total; e0 += 128 * 4) {
+        // 128 threads = two tiles at a time, thread (tile half, rr, cc); the tile pair (ib, jb) of the lower-triangular list is
+        // advanced incrementally; four tiles (= four independent gathers) in flight per thread
+        const int ntiles = nb * (nb + 1) / 2;
+        const int rr = (tid >> 3) & 7, cc = tid & 7;
+        int ib = 0, jb = tid >> 6;
+        while (jb > ib) { jb -= ib + 1; ++ib; }
+        for (int t0 = tid >> 6; t0 < ntiles; t0 += 8) {
             double v[4]; int o[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                int e = e0 + u * 128;
+                const int t = t0 + 2 * u;
                 v[u] = 0.0; o[u] = -1;
-                if (e < total) {
-                    int t = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
-                    int ib = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
-                    while (ib * (ib + 1) / 2 > t) --ib;
-                    while ((ib + 1) * (ib + 2) / 2 <= t) ++ib;
-                    int jb = t - ib * (ib + 1) / 2;
-                    int a = ib * 8 + rr, b = jb * 8 + cc;
+                if (t < ntiles) {
+                    const int a = ib * 8 + rr, b = jb * 8 + cc;
                     o[u] = t * 64 + tsw(rr, cc);
                     if (a >= b) {
                         if (a < m) {
@@ -273,6 +273,8 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
                         }
                     }
                 }
+                jb += 2;
+                while (jb > ib) { jb -= ib + 1; ++ib; }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) if (o[u] >= 0) Ls[o[u]] = v[u];

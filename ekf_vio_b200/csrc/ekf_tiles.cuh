@@ -116,12 +116,12 @@ __device__ void chol_tiles(double* Ls, double* Li, int nb, int* bad_flag, double
         }
         __syncthreads();
         {   // trailing update: A(ib,kb) -= L(ib,jb) J_jb L(kb,jb)'  for ib >= kb > jb
+            // lower-triangular tile list (ii, kk2), kk2 <= ii < t, dealt round-robin to the warps; the pair is advanced
+            // incrementally (a square root per tile used to cost as much as the two DMMAs it addressed)
             const int t = nb - 1 - jb;
-            for (int e = warp; e < t * (t + 1) / 2; e += NWC) {
-                int ii = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
-                while (ii * (ii + 1) / 2 > e) --ii;
-                while ((ii + 1) * (ii + 2) / 2 <= e) ++ii;
-                int kk2 = e - ii * (ii + 1) / 2;
+            int ii = 0, kk2 = warp;
+            while (kk2 > ii) { kk2 -= ii + 1; ++ii; }
+            for (; ii < t; ) {
                 int ib = jb + 1 + ii, kb = jb + 1 + kk2;
                 const double* TA = Ls + tile_of(ib, jb);
                 const double* TB = Ls + tile_of(kb, jb);
@@ -130,6 +130,8 @@ __device__ void chol_tiles(double* Ls, double* Li, int nb, int* bad_flag, double
                 dmma884(c.x, c.y, -TA[tsw(r, q)] * sk0, TB[tsw(r, q)]);
                 dmma884(c.x, c.y, -TA[tsw(r, 4 + q)] * sk1, TB[tsw(r, 4 + q)]);
                 *reinterpret_cast<double2*>(&TC[tsw(r, 2 * q)]) = c;
+                kk2 += NWC;
+                while (kk2 > ii) { kk2 -= ii + 1; ++ii; }
             }
         }
         __syncthreads();

@@ -187,51 +187,52 @@ void TightlyCoupledEKF::updateWithFeaturePositions(std::vector<Eigen::Vector2f> 
 }
 
 Eigen::SparseMatrix<float> TightlyCoupledEKF::numericallyLinearizeProcess(Eigen::Matrix<float, BASE_STATE_SIZE, 1>& mu, std::list<Feature>& feats, float dt) {   // :176-325
-    // evaluated on the device for the state passed in (normally this->base_mu / this->features)
+    // evaluated on the device for the state passed in (normally this->base_mu / this->features).  The reference's function does
+    // not touch the filter: when a foreign state is passed in, the filter's own mean is put back afterwards (only the dq_inv
+    // cache moves, as the reference's function-static cache does).
     EKF_ASSERT(feats.size() == features.size());
-    for (int k = 0; k < BASE_STATE_SIZE; ++k) base_mu(k) = mu(k);
-    if (&feats != &features) { auto it = features.begin(); for (auto& e : feats) { it->setMu(e.getMu()); ++it; } }
+    const bool foreign = (&mu != &base_mu) || (&feats != &features);
+    Eigen::Matrix<float, BASE_STATE_SIZE, 1> saved_mu = base_mu;
+    std::vector<Eigen::Vector3f> saved_feat;
+    if (foreign) {
+        pushIfEdited();                                    // caller edits of the filter's own members first
+        for (auto& e : features) saved_feat.push_back(e.getMu());
+        for (int k = 0; k < BASE_STATE_SIZE; ++k) base_mu(k) = mu(k);
+        if (&feats != &features) { auto it = features.begin(); for (auto& e : feats) { it->setMu(e.getMu()); ++it; } }
+    }
     pushIfEdited();
     const int Nm = BASE_STATE_SIZE + 3 * capacity_, N = BASE_STATE_SIZE + 3 * (int)features.size();
     std::vector<double> F((size_t)Nm * Nm);
     EKF_CALL(ekfvio_batch_linearize_h(dev_, (double)dt, F.data()));
     Eigen::SparseMatrix<float> out(N, N);
     for (int r = 0; r < N; ++r) for (int c = 0; c < N; ++c) out(r, c) = (float)F[(size_t)r * Nm + c];
+    if (foreign) {
+        base_mu = saved_mu;
+        size_t i = 0;
+        for (auto& e : features) e.setMu(saved_feat[i++]);
+        pushIfEdited();
+    }
     pull();
     return out;
 }
 
-// convolveBaseState / convolveFeature (:328-460) are evaluated by the device process model on a scratch
-// filter that shares this filter's dq_inv cache, so the reference's cache behaviour (E2) carries over.
+// convolveBaseState / convolveFeature (:328-460): single evaluations on the device.  convolveFeature goes through this
+// filter's dq_inv cache with the reference's rule — keyed on omega only, so a call with an unchanged omega and a different dt
+// reuses the stale rotation (E2), and a miss leaves the cache at (omega, this dt) for the next process().
 Eigen::Matrix<float, BASE_STATE_SIZE, 1> TightlyCoupledEKF::convolveBaseState(Eigen::Matrix<float, BASE_STATE_SIZE, 1>& last, float dt) {
-    ekfvio_params p = current_params();
-    ekfvio_batch* s = nullptr;
-    EKF_CALL(ekfvio_batch_create(&s, 0, 1, 0, &p));
-    double mu[BASE_STATE_SIZE];
+    double mu[BASE_STATE_SIZE], out[BASE_STATE_SIZE];
     for (int k = 0; k < BASE_STATE_SIZE; ++k) mu[k] = last(k);
-    EKF_CALL(ekfvio_batch_set_state(s, mu, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
-    EKF_CALL(ekfvio_batch_process_dt(s, (double)dt, nullptr));
-    EKF_CALL(ekfvio_batch_get_state(s, mu, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
-    ekfvio_batch_destroy(s);
-    Eigen::Matrix<float, BASE_STATE_SIZE, 1> out;
-    for (int k = 0; k < BASE_STATE_SIZE; ++k) out(k) = (float)mu[k];
-    return out;
+    EKF_CALL(ekfvio_batch_convolve_base_h(dev_, 0, mu, (double)dt, out));
+    Eigen::Matrix<float, BASE_STATE_SIZE, 1> r;
+    for (int k = 0; k < BASE_STATE_SIZE; ++k) r(k) = (float)out[k];
+    return r;
 }
 
 Eigen::Vector3f TightlyCoupledEKF::convolveFeature(Eigen::Matrix<float, BASE_STATE_SIZE, 1>& base_state, Eigen::Vector3f& feature_state, float dt) {
-    ekfvio_params p = current_params();
-    ekfvio_batch* s = nullptr;
-    EKF_CALL(ekfvio_batch_create(&s, 0, 1, 1, &p));
-    double mu[BASE_STATE_SIZE], f3[3] = {feature_state(0), feature_state(1), feature_state(2)}, cache[7];
+    double mu[BASE_STATE_SIZE], f3[3] = {feature_state(0), feature_state(1), feature_state(2)}, out[3];
     for (int k = 0; k < BASE_STATE_SIZE; ++k) mu[k] = base_state(k);
-    int one = 1;
-    EKF_CALL(ekfvio_batch_get_state(dev_, nullptr, nullptr, nullptr, nullptr, cache, nullptr, nullptr, nullptr));
-    EKF_CALL(ekfvio_batch_set_state(s, mu, f3, nullptr, &one, cache, nullptr, nullptr));
-    EKF_CALL(ekfvio_batch_process_dt(s, (double)dt, nullptr));
-    EKF_CALL(ekfvio_batch_get_state(s, nullptr, f3, nullptr, nullptr, cache, nullptr, nullptr, nullptr));
-    EKF_CALL(ekfvio_batch_set_state(dev_, nullptr, nullptr, nullptr, nullptr, cache, nullptr, nullptr));
-    ekfvio_batch_destroy(s);
-    return Eigen::Vector3f((float)f3[0], (float)f3[1], (float)f3[2]);
+    EKF_CALL(ekfvio_batch_convolve_feature_h(dev_, 0, mu, f3, (double)dt, out));
+    return Eigen::Vector3f((float)out[0], (float)out[1], (float)out[2]);
 }
 
 Eigen::SparseMatrix<float> TightlyCoupledEKF::generateProcessNoise(float dt) {   // :123-174 (a constant diagonal)

@@ -875,7 +875,19 @@ cudaError_t launch_track(const Pyr& pyr, const uint8_t* prev_slot, const uint8_t
     double eps = prm.epsilon < 0 ? 0 : (prm.epsilon > 10 ? 10 : prm.epsilon);
     eps *= eps;
     dim3 grid((max_points + WARPS - 1) / WARPS, batch);
-    klt_track_kernel<<<grid, WARPS * 32, track_smem_bytes(prm.window_size), st>>>(pyr, prev_slot, next_slot, prev_pts, next_pts, status, err, npts,
+    const size_t smem = track_smem_bytes(prm.window_size);
+    if (smem > 48 * 1024) {                        // windows of 29 and 31 pixels need the opt-in shared-memory size
+        static size_t configured_on[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        size_t& configured = configured_on[(dev >= 0 && dev < 64) ? dev : 0];
+        if (smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(klt_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured = smem;
+        }
+    }
+    klt_track_kernel<<<grid, WARPS * 32, smem, st>>>(pyr, prev_slot, next_slot, prev_pts, next_pts, status, err, npts,
                                                                                  max_points, prm.window_size, mc, eps, prm.min_eigen,
                                                                                  prm.use_initial_flow, first_image, track_stride_mode(), prev_ext, next_ext);
     return cudaGetLastError();

@@ -5,6 +5,7 @@
 #ifndef EKFVIO_FRAME_H_
 #define EKFVIO_FRAME_H_
 
+#include <utility>
 #include <vector>
 
 #include "compat.h"
@@ -30,6 +31,10 @@ public:
     /* Frame.cpp:15-41: Frame(inv_scale, full-resolution image, CameraInfo::K, CameraInfo::D, stamp); defined in the facade
      * library (ekfvio_frame_resize_h).  d may hold fewer than five coefficients (missing ones stay 0). */
     Frame(int inv_scale, const cv::Mat& full_img, const double k[9], const std::vector<double>& d, ros::Time _t);
+    /* The reference's signature takes sensor_msgs::CameraInfo::K, a boost::array<double, 9> (Frame.h:39; EKFVIO.cpp:126 passes
+     * cam->K): any array type with operator[] and contiguous storage — boost::array, std::array — goes through here. */
+    template <class Array9, class = decltype(std::declval<const Array9&>().size())>
+    Frame(int inv_scale, const cv::Mat& full_img, const Array9& k, const std::vector<double>& d, ros::Time _t) : Frame(inv_scale, full_img, &k[0], d, _t) {}
     /* Frame.cpp:44-55 */
     bool isPixelInBox(cv::Point2f px) const {
         return !(px.x < KILL_PAD || px.y < KILL_PAD || this->img.cols - px.x < KILL_PAD || this->img.rows - px.y < KILL_PAD);

@@ -114,6 +114,12 @@ int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, c
  * of filter f to d_F[f][Nmax][Nmax] (row-major, leading dimension Nmax) without changing the
  * state — except the convolveFeature cache, exactly as in the reference. */
 int ekfvio_batch_linearize(ekfvio_batch* b, const double* d_dt, double* d_F, void* stream);
+/* convolveBaseState / convolveFeature (TightlyCoupledEKF.cpp:328-395, 397-460) as single evaluations for arbitrary arguments
+ * (test_ekf.cpp:156-204 calls them that way).  HOST pointers, synchronous.  Filter `f` of the batch lends its dq_inv cache to
+ * convolveFeature, which — like the reference's function-static cache — is keyed on omega only: a call with an unchanged omega
+ * reuses the rotation of an earlier dt (E2; EKFVIO_FLAG_FRESH_DQ_CACHE recomputes it).  The filter's state is not modified. */
+int ekfvio_batch_convolve_base_h(ekfvio_batch* b, int f, const double* h_base22, double dt, double* h_out22);
+int ekfvio_batch_convolve_feature_h(ekfvio_batch* b, int f, const double* h_base22, const double* h_feat3, double dt, double* h_out3);
 
 /* checkSigma (TightlyCoupledEKF.cpp:699-714): number of negative diagonal entries and
  * max |Sigma_ij - Sigma_ji| per filter.  Device outputs. */
@@ -130,11 +136,14 @@ int ekfvio_batch_get_state_range(ekfvio_batch* b, int first, int count, double* 
 int ekfvio_batch_set_state(ekfvio_batch* b, const double* h_mu, const double* h_feat, const double* h_P, const int* h_nfeat,
                            const double* h_cache, const uint8_t* h_flags, const double* h_klt_last);
 
-/* Host-buffer convenience wrappers (the calls the C++ facade and the e2e benchmark use): the copies
- * are enqueued on `stream` and the call returns after the work is enqueued.  Pageable inputs are
- * staged through the batch's pinned buffers (consumed before return); page-locked inputs
- * (cudaHostAlloc / cudaHostRegister) are DMA'd from where they are and must stay unchanged until
- * the stream has passed this call. */
+/* Host-buffer convenience wrappers (the calls the C++ facade and the e2e benchmark use): the kernels are
+ * enqueued on `stream` and the call returns after the work is enqueued.  The host->device copies run on a
+ * private copy stream that the kernels wait for — NOT behind earlier work of `stream`, so that the upload of a
+ * step's measurements overlaps the process() still running there.  Host buffers are therefore read as they are
+ * at call time: they must already hold their final contents when the function is called (as the reference's
+ * by-value std::vector arguments do), and page-locked ones (cudaHostAlloc / cudaHostRegister), which are DMA'd
+ * from where they are, must stay unchanged until the stream has passed this call.  Pageable inputs are staged
+ * through the batch's pinned buffers (consumed before return). */
 int ekfvio_batch_add_features_h(ekfvio_batch* b, const int* h_k, const double* h_uv, int kmax, void* stream);
 int ekfvio_batch_update_h(ekfvio_batch* b, const double* h_z, const double* h_R, const uint8_t* h_pass, void* stream);
 /* numericallyLinearizeProcess with one dt for all filters, Jacobians to HOST memory

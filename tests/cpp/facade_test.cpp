@@ -4,6 +4,8 @@
 // loop).  Prints "key: values" lines that tests/test_gpu_facade.py compares with the FP64 oracle.
 // Usage: facade_test <scenario.bin> [klt.bin]
 #include <cstdio>
+#include <array>
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 
@@ -143,6 +145,58 @@ int main(int argc, char** argv) {
         std::printf("\nklt_metric:"); for (int i = 0; i < n; ++i) std::printf(" %.9g %.9g", passed[i] ? measured_positions[i].x() : 0.f, passed[i] ? measured_positions[i].y() : 0.f);
         std::printf("\nklt_cov00:"); for (int i = 0; i < n; ++i) std::printf(" %.9g", unc[i](0, 0));
         std::printf("\n");
+    }
+    {   // accessors (TightlyCoupledEKF.cpp:663-697) and the E2 behaviour of convolveFeature through the class interface
+        TightlyCoupledEKF f;
+        std::vector<Eigen::Vector2f> fs; fs.push_back(Eigen::Vector2f(0.1f, 0.1f)); fs.push_back(Eigen::Vector2f(-0.2f, 0.05f));
+        f.addNewFeatures(fs);
+        f.base_mu(7) = 0.2f; f.base_mu(11) = 0.3f;
+        f.process(0.05f);
+        std::vector<Eigen::Matrix2f> cs; Eigen::Matrix2f c; c(0, 0) = 1e-5f; c(1, 1) = 1e-5f; cs.assign(2, c);
+        f.updateWithFeaturePositions(fs, cs, std::vector<bool>{true, true});
+        // getFeatureHomogenousCovariance = Sigma.block(start, start, 2, 2), getFeatureDepthVariance = Sigma(start + 2, start + 2)
+        for (int i = 0; i < 2; ++i) {
+            const int st = 22 + 3 * i;
+            Eigen::Matrix2f hc = f.getFeatureHomogenousCovariance(i);
+            CHECK(hc(0, 0) == f.Sigma(st, st) && hc(0, 1) == f.Sigma(st, st + 1) && hc(1, 0) == f.Sigma(st + 1, st) && hc(1, 1) == f.Sigma(st + 1, st + 1));
+            CHECK(f.getFeatureDepthVariance(i) == f.Sigma(st + 2, st + 2));
+            CHECK(hc(0, 0) > 0 && hc(0, 0) < 1e-4f && f.getFeatureDepthVariance(i) > 0);
+        }
+        // setFeatureHomogenousCovariance writes the four coefficients (and, like the reference, complains on stderr) and the
+        // change reaches the device: the next update sees it
+        Eigen::Matrix2f nc; nc(0, 0) = 3e-4f; nc(0, 1) = 1e-5f; nc(1, 0) = 1e-5f; nc(1, 1) = 4e-4f;
+        f.setFeatureHomogenousCovariance(1, nc);
+        Eigen::Matrix2f rb = f.getFeatureHomogenousCovariance(1);
+        CHECK(rb(0, 0) == 3e-4f && rb(0, 1) == 1e-5f && rb(1, 0) == 1e-5f && rb(1, 1) == 4e-4f);
+        f.process(0.05f);
+        CHECK(f.getFeatureHomogenousCovariance(1)(0, 0) > 3e-4f);          // F Sigma F' + Q on top of the value that was set
+        // getMetric2PixelMap / getPixel2MetricMap: diag(fx, fy) and its inverse (:680-697)
+        Eigen::Matrix3f K; K.setZero(); K(0, 0) = 400.f; K(1, 1) = 410.f; K(0, 2) = 320.f; K(1, 2) = 240.f; K(2, 2) = 1.f;
+        Eigen::SparseMatrix<float> m2p = f.getMetric2PixelMap(K), p2m = f.getPixel2MetricMap(K);
+        CHECK(m2p.rows() == 2 && m2p.cols() == 2 && m2p(0, 0) == 400.f && m2p(1, 1) == 410.f && m2p(0, 1) == 0.f && m2p(1, 0) == 0.f);
+        CHECK(p2m(0, 0) == 1.0f / 400.f && p2m(1, 1) == 1.0f / 410.f && p2m(0, 1) == 0.f);
+        // E2 through the class: two convolveFeature calls with the same omega and different dt — the second reuses the rotation
+        // cached for the first dt (function-static cache keyed on omega only, TightlyCoupledEKF.cpp:400-446); a filter that
+        // never saw the first call rotates by the second dt
+        TightlyCoupledEKF a, b;
+        Eigen::Matrix<float, BASE_STATE_SIZE, 1> mu; mu.setZero(); mu(3) = 1.f; mu(10) = 0.5f; mu(12) = -0.2f;
+        Eigen::Vector3f x(0.3f, -0.1f, 2.0f);
+        Eigen::Vector3f a1 = a.convolveFeature(mu, x, 0.1f), a2 = a.convolveFeature(mu, x, 0.3f), b2 = b.convolveFeature(mu, x, 0.3f);
+        CHECK(a2(0) == a1(0) && a2(1) == a1(1) && a2(2) == a1(2));            // no velocity: only the (stale) rotation acts
+        CHECK(std::fabs(b2(0) - a2(0)) + std::fabs(b2(1) - a2(1)) + std::fabs(b2(2) - a2(2)) > 1e-2f);   // the fresh rotation by 0.3 s differs
+        std::printf("convolve_stale: %.9g %.9g %.9g fresh: %.9g %.9g %.9g\n", a2(0), a2(1), a2(2), b2(0), b2(1), b2(2));
+        // numericallyLinearizeProcess with a foreign state leaves the filter's own mean alone
+        Eigen::Matrix<float, BASE_STATE_SIZE, 1> before = f.base_mu, other = f.base_mu; other(7) = 5.f;
+        Eigen::SparseMatrix<float> Fo = f.numericallyLinearizeProcess(other, f.features, 0.05f);
+        CHECK(Fo.rows() == 28);
+        for (int k2 = 0; k2 < BASE_STATE_SIZE; ++k2) CHECK(f.base_mu(k2) == before(k2));
+    }
+    {   // Frame with the reference's array type for K (Frame.h:39: boost::array<double, 9>; EKFVIO.cpp:126)
+        const int w = 32, h = 16;
+        std::vector<uint8_t> im((size_t)w * h, 7);
+        std::array<double, 9> ka = {300, 0, 16, 0, 310, 8, 0, 0, 1};
+        Frame fa(2, cv::Mat(h, w, im.data(), (size_t)w), ka, std::vector<double>{0, 0, 0, 0, 0}, ros::Time(2.0));
+        CHECK(fa.img.cols == 16 && fa.img.rows == 8 && fa.K(0, 0) == 150.f && fa.K(1, 2) == 4.f);
     }
     {   // Frame::Frame with resizing (Frame.cpp:15-41): 2x takes OpenCV's area-fast path (a+b+c+d+2)>>2, 4x the 11-bit bilinear
         const int w = 64, h = 48;

@@ -570,3 +570,30 @@ def test_config4_large_state_n300(cuda, flags):
             assert_close(g, o.state(), what=f"config 4 filter {f} update {s}")
             assert g["status"] == 0
     b.close()
+
+
+def test_single_convolve_calls_follow_the_reference_cache_rule(cuda):
+    """convolveBaseState / convolveFeature as a caller of the class invokes them (test/test_ekf.cpp:156-204): single evaluations
+    through the C ABI against the filter's dq_inv cache, which — like the reference's function-static one — is keyed on omega
+    only (E2): the same omega with another dt reuses the stale rotation, and what a call leaves in the cache shapes columns 7-9
+    of the next Jacobian.  Checked call by call against the oracle, whose cache follows TightlyCoupledEKF.cpp:400-446."""
+    import torch
+    feats = np.array([[0.1, 0.1], [-0.1, -0.1], [0.1, -0.1]])
+    b = make_batch(1, 3); b.add_features_h(np.array([3], np.int32), feats[None])
+    o = O.OracleFilter(); o.add_features(feats)
+    mu = np.zeros(22); mu[3] = 1.0; mu[7:10] = (0.3, -0.2, 0.1); mu[10:13] = (0.5, 0.0, -0.2); mu[13:16] = (0.05, 0.0, -0.02)
+    f3 = np.array([0.3, -0.1, 2.0])
+    for dt in (0.1, 0.3, 0.3, 0.05):                       # same omega throughout: every call after the first hits the stale cache
+        np.testing.assert_allclose(b.convolve_feature_h(mu, f3, dt), o.convolve_feature(mu, f3, dt), rtol=0, atol=1e-15)
+        np.testing.assert_allclose(b.convolve_base_h(mu, dt), o.convolve_base(mu, dt), rtol=0, atol=1e-15)
+    stale = b.convolve_feature_h(mu, f3, 0.3)
+    mu2 = mu.copy(); mu2[11] = 0.01                         # omega changes: cache miss, recomputed for this dt
+    np.testing.assert_allclose(b.convolve_feature_h(mu2, f3, 0.3), o.convolve_feature(mu2, f3, 0.3), rtol=0, atol=1e-15)
+    np.testing.assert_allclose(b.convolve_feature_h(mu, f3, 0.3), o.convolve_feature(mu, f3, 0.3), rtol=0, atol=1e-15)   # back: miss again, now fresh
+    assert np.abs(b.convolve_feature_h(mu, f3, 0.3) - stale).max() > 1e-3
+    np.testing.assert_array_equal(b.get_state()["cache"][0], o.state()["cache"])
+    # the filter's own state was not touched, and the cache the calls left behind enters the next linearisation (columns 7-9)
+    st = o.state(); o.set_state(mu=mu, feat=st["feat"], Pm=st["P"], cache=st["cache"]); b.set_state(mu=mu[None])
+    F = torch.zeros(1, 31, 31, dtype=torch.float64, device="cuda")
+    b.linearize(torch.full((1,), 0.2, dtype=torch.float64, device="cuda"), F); torch.cuda.synchronize()
+    assert rel(F[0].cpu().numpy(), o.linearize(0.2)) <= 1e-12

@@ -156,3 +156,105 @@ def test_frame_loop_with_feature_removal_keeps_tracking(cuda):
     assert not drop["flags"][:, :].any() or (drop["flags"].sum() < keep["flags"].sum())
     assert (drop["status"] == 0).all() and np.isfinite(drop["mu"]).all()
     assert (drop["nfeat"] <= NF).all() and (drop["nfeat"] > 0).all()
+
+
+def oracle_composed_sequence(frames, K9, dts, num_features, thr=50, min_dist=30, kill_pad=11):
+    """EKFVIO::addFrame / updateStateWithNewImage / replenishFeatures (EKFVIO.cpp:139-196, 201-217, 224-311) driven for ONE sequence
+    with nothing but the oracles: the FP64 EKF oracle (oracle/ekf_oracle.hpp), OpenCV's own cv2.calcOpticalFlowPyrLK with the
+    reference's arguments (KLTTracker.cpp:61-64) and the numpy FAST / greedy-scan oracle (pinned to cv2).  The host glue is the
+    reference's float32 arithmetic.  Yields the oracle filter's state after every frame."""
+    import cv2
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import replenish_oracle as RO
+    from tests import oracle_lib as O
+    T, h, w = frames.shape
+    K = K9.astype(np.float32)                      # column-major: K(0) = fx, K(4) = fy, K(2) = K(5) = 0 (E1), K(6), K(7) = principal point
+    o = O.OracleFilter()
+    crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
+    for t in range(T):
+        img = frames[t]
+        if t > 0:
+            o.process(float(dts[t]))                                                             # EKFVIO.cpp:163
+            st = o.state(); n = len(st["feat"])
+            if n:
+                kl = st["klt_last"].astype(np.float32); ft = st["feat"].astype(np.float32)
+                prev_pts = np.stack([kl[:, 0] * K[0] + K[2], kl[:, 1] * K[4] + K[5]], 1).astype(np.float32)      # Feature::metric2Pixel (KLTTracker.cpp:53-55)
+                init_pts = np.stack([K[0] * ft[:, 0] + K[2], K[4] * ft[:, 1] + K[5]], 1).astype(np.float32)      # Feature::getPixel (:57-59)
+                nxt, status, _ = cv2.calcOpticalFlowPyrLK(frames[t - 1], img, prev_pts.reshape(-1, 1, 2), init_pts.reshape(-1, 1, 2).copy(), winSize=(21, 21), maxLevel=3,
+                                                          criteria=crit, flags=cv2.OPTFLOW_USE_INITIAL_FLOW, minEigThreshold=1e-4)
+                nxt = nxt.reshape(-1, 2); status = status.reshape(-1)
+                x, y = nxt[:, 0], nxt[:, 1]
+                pad = np.float32(kill_pad)
+                ok = (status == 1) & ~((x < pad) | (y < pad) | (np.float32(w) - x < pad) | (np.float32(h) - y < pad))     # KLTTracker.cpp:73, Frame.cpp:44-55
+                sx = np.float32((1.0 / float(K[0])) ** 2); sy = np.float32((1.0 / float(K[4])) ** 2)
+                cov = np.zeros((n, 4), np.float32); cov[ok, 0] = np.float32(0.00001) * sx; cov[ok, 3] = np.float32(0.00001) * sy                 # :75-83
+                meas = np.zeros((n, 2), np.float32)
+                meas[ok, 0] = (x[ok] - K[2]) / K[0]; meas[ok, 1] = (y[ok] - K[5]) / K[4]                                                        # pixel2Metric, E1
+                o.update(meas.astype(np.float64), cov.astype(np.float64), ok.astype(np.uint8))                                                   # EKFVIO.cpp:217
+        st = o.state(); n = len(st["feat"]); ft = st["feat"].astype(np.float32)
+        existing = np.stack([K[0] * ft[:, 0] + K[2], K[4] * ft[:, 1] + K[5]], 1) if n else np.zeros((0, 2), np.float32)
+        kps, _ = RO.fast9_16(img, thr, True)                                                      # cv::FAST(img, kp, 50, true), EKFVIO.cpp:242
+        px, metric = RO.select_new_features(kps, existing, w, h, max(num_features - n, 0), min_dist, kill_pad, K9=K)
+        if len(px):
+            o.add_features(metric.astype(np.float64))                                             # EKFVIO.cpp:308
+        yield o.state()
+
+
+def test_frame_loop_against_the_oracle_composition(cuda):
+    """SURVEY.md §8f-3 against oracles only (not against a host composition of the same GPU kernels): 2 sequences x 5 frames.
+    After every frame: the same number of features (FAST + greedy selection bit-exact), the same lost / tracked flags (tracker
+    status + kill-pad bit-exact vs cv2), the last KLT results within 1e-5 (tracker positions agree with OpenCV's to ~2e-4 px,
+    i.e. ~1e-6 in metric units, and pass through the reference's float32 glue), Sigma within 1e-4, and the state within 2e-3:
+    the Kalman gain of the barely observed velocity / acceleration states is of order 1e2, so a 1e-6 difference in a measurement
+    legitimately moves those states by 1e-4."""
+    import torch
+    from ekf_vio_b200 import capi, workload
+    S, T, w, h, NF = 2, 5, 320, 240, 30
+    frames = workload.vio_sequences(11, S, T, w, h, speed=2.0)
+    K9 = np.zeros((S, 9), np.float32); K9[:, 0] = 210.0; K9[:, 4] = 205.0; K9[:, 6] = 160.0; K9[:, 7] = 120.0; K9[:, 8] = 1.0
+    dts = np.full((T, S), 0.05)
+    gens = [oracle_composed_sequence(frames[:, s], K9[s], dts[:, s], NF) for s in range(S)]
+    loop = capi.VioLoop(S, w, h, num_features=NF, use_cuda_graph=True)
+    dK = torch.from_numpy(K9).cuda()
+    rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)) if a.size else 0.0
+    worst = np.zeros(3)
+    for t in range(T):
+        loop.add_frame(torch.from_numpy(frames[t]).cuda(), dK, None if t == 0 else torch.from_numpy(dts[t]).cuda())
+        got = loop.filters.get_state()
+        for s in range(S):
+            o = next(gens[s])
+            n = len(o["feat"]); N = 22 + 3 * n
+            assert got["nfeat"][s] == n, f"frame {t} sequence {s}: {got['nfeat'][s]} features, oracle {n}"
+            np.testing.assert_array_equal(got["flags"][s, :n], o["flags"], err_msg=f"frame {t} sequence {s}: lost / tracked flags")
+            e = np.array([rel(got["klt_last"][s, :n], o["klt_last"]), rel(got["P"][s, :N, :N], o["P"]),
+                          rel(np.concatenate([got["mu"][s], got["feat"][s, :n].ravel()]), np.concatenate([o["mu"], o["feat"].ravel()]))])
+            worst = np.maximum(worst, e)
+            assert e[0] <= 1e-5 and e[1] <= 1e-4 and e[2] <= 2e-3, f"frame {t} sequence {s}: klt_last {e[0]:.3e} Sigma {e[1]:.3e} state {e[2]:.3e}"
+        assert t == 0 or got["nfeat"].min() > 5
+    print(f"frame loop vs oracle composition over {T} frames x {S} sequences: worst relative difference klt_last {worst[0]:.3e}, Sigma {worst[1]:.3e}, state {worst[2]:.3e}")
+    loop.close()
+
+
+def test_graph_is_recaptured_when_the_batch_was_stepped_behind_the_loops_back(cuda):
+    """The captured graph bakes in the batch's Sigma ping-pong buffer.  A caller that steps the batch handed out by
+    ekfvio_vio_filters() between two frames (here: one extra process()) flips that buffer; the loop must notice and record
+    again instead of replaying into the stale buffer — graph and eager loop stay bit-identical."""
+    import torch
+    from ekf_vio_b200 import capi, workload
+    S, T, w, h, NF = 2, 9, 320, 240, 24
+    frames = workload.vio_sequences(21, S, T, w, h, speed=2.0)
+    K9 = np.zeros((S, 9), np.float32); K9[:, 0] = 200.0; K9[:, 4] = 200.0; K9[:, 8] = 1.0
+    dK = torch.from_numpy(K9).cuda(); ddt = torch.full((S,), 0.05, dtype=torch.float64, device="cuda")
+    res = []
+    for graph in (True, False):
+        loop = capi.VioLoop(S, w, h, num_features=NF, use_cuda_graph=graph)
+        for t in range(T):
+            loop.add_frame(torch.from_numpy(frames[t]).cuda(), dK, None if t == 0 else ddt)
+            if t == 5:
+                loop.filters.process(0.01)              # behind the loop's back: one Sigma buffer flip
+        res.append(loop.filters.get_state())
+        loop.close()
+    for key in ("nfeat", "mu", "feat", "P", "klt_last", "flags"):
+        np.testing.assert_array_equal(res[0][key], res[1][key], err_msg=key)
+    assert np.isfinite(res[0]["mu"]).all()
