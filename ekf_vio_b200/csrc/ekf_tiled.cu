@@ -9,6 +9,8 @@
 // k-chunks with cp.async double buffering, the A operands come straight from global memory one
 // chunk ahead.  Shared-memory leading dimensions are == 4 (mod 8) doubles so every fragment load
 // is bank-conflict free.
+#include <cstdlib>
+
 #include "ekf_common.cuh"
 #include "ekf_kernels.h"
 #include "ekf_tiles.cuh"
@@ -172,12 +174,12 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const 
 // Cholesky (8x8 tiles) and the explicit inverses of the diagonal tiles.  128 threads per filter
 // and ~54 KB of shared memory, so four filters share an SM and hide each other's serial
 // diagonal-tile steps.  L tiles and inverse tiles go to global scratch in their swizzled layout.
-template <int NB>
-__global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double* __restrict__ Pin, const double* __restrict__ z,
+template <int NB, int NWC>
+__global__ void __launch_bounds__(NWC * 32, 4) ekf_chol_tiled(EkfPtrs p, const double* __restrict__ Pin, const double* __restrict__ z,
                                                          const double* __restrict__ Rin, const uint8_t* __restrict__ pass) {
     extern __shared__ __align__(16) double smc[];
     constexpr int NT = NB * (NB + 1) / 2;
-    constexpr int NWC = 4;
+    constexpr int NTH = NWC * 32;
     double* Ls = smc;                      // NT tiles
     double* Li = Ls + NT * 64;             // NB inverse diagonal tiles
     int* s_idx = reinterpret_cast<int*>(Li + NB * 64);   // NB*8
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
         // wrote the feature rows only up to their diagonal blocks
         double* Pw = const_cast<double*>(Pi);
         const int N = BASE + 3 * n;
-        for (int r = BASE + warp; r < N; r += 4) {
+        for (int r = BASE + warp; r < N; r += NWC) {
             for (int c = r + 1 + lane; c < N; c += 32) Pw[(size_t)r * ld + c] = Pw[(size_t)c * ld + r];
         }
         __syncthreads();
@@ -249,17 +251,18 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
     // lower(a,b), a >= b  <-  upper(S)(b,a) = Sigma(idx[b], idx[a]) + R(b,a)  (SimplicialLDLT::compute(S')
     // reads upper(S), :578); identity tail.  Four independent gathers in flight per thread.
     {
-        // 128 threads = two tiles at a time, thread (tile half, rr, cc); the tile pair (ib, jb) of the lower-triangular list is
+        // 64 threads per tile, thread (tile of the pass, rr, cc); the tile pair (ib, jb) of the lower-triangular list is
         // advanced incrementally; four tiles (= four independent gathers) in flight per thread
         const int ntiles = nb * (nb + 1) / 2;
         const int rr = (tid >> 3) & 7, cc = tid & 7;
+        constexpr int TPP = NTH / 64;               // tiles per pass of the CTA
         int ib = 0, jb = tid >> 6;
         while (jb > ib) { jb -= ib + 1; ++ib; }
-        for (int t0 = tid >> 6; t0 < ntiles; t0 += 8) {
+        for (int t0 = tid >> 6; t0 < ntiles; t0 += 4 * TPP) {
             double v[4]; int o[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int t = t0 + 2 * u;
+                const int t = t0 + TPP * u;
                 v[u] = 0.0; o[u] = -1;
                 if (t < ntiles) {
                     const int a = ib * 8 + rr, b = jb * 8 + cc;
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
                         }
                     }
                 }
-                jb += 2;
+                jb += TPP;
                 while (jb > ib) { jb -= ib + 1; ++ib; }
             }
 #pragma unroll
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
     __shared__ double s_sgn[NB * 8];
     __shared__ int s_neg, s_route;
     if (tid == 0) s_neg = 0;
-    for (int a = tid; a < NB * 8; a += 128) s_sgn[a] = 1.0;
+    for (int a = tid; a < NB * 8; a += NTH) s_sgn[a] = 1.0;
     __syncthreads();
     chol_tiles<NWC>(Ls, Li, nb, &s_bad, s_sgn, &s_neg);
     // Routing of this filter's update (ekf_kernels.h ROUTE_*).  Sigma - Z Z' is only taken where it is as accurate as the Joseph
@@ -320,7 +323,7 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
         // of which the last process() wrote the feature rows only up to their diagonal blocks — complete it
         double* Pw = const_cast<double*>(Pi);
         const int N = BASE + 3 * n;
-        for (int r = BASE + warp; r < N; r += 4) {
+        for (int r = BASE + warp; r < N; r += NWC) {
             for (int c = r + 1 + lane; c < N; c += 32) Pw[(size_t)r * ld + c] = Pw[(size_t)c * ld + r];
         }
     }
@@ -352,9 +355,9 @@ __global__ void __launch_bounds__(128, 4) ekf_chol_tiled(EkfPtrs p, const double
     // factor and inverse tiles to global scratch (same swizzled layout)
     double* Lg = p.L + (size_t)f * ((NT + NB) * 64 + NB * 8);
     const int used = nb * (nb + 1) / 2 * 64;
-    for (int e = tid * 2; e < used; e += 256) *reinterpret_cast<double2*>(Lg + e) = *reinterpret_cast<const double2*>(Ls + e);
-    for (int e = tid * 2; e < nb * 64; e += 256) *reinterpret_cast<double2*>(Lg + NT * 64 + e) = *reinterpret_cast<const double2*>(Li + e);
-    for (int a = tid; a < NB * 8; a += 128) Lg[(NT + NB) * 64 + a] = s_sgn[a];
+    for (int e = tid * 2; e < used; e += 2 * NTH) *reinterpret_cast<double2*>(Lg + e) = *reinterpret_cast<const double2*>(Ls + e);
+    for (int e = tid * 2; e < nb * 64; e += 2 * NTH) *reinterpret_cast<double2*>(Lg + NT * 64 + e) = *reinterpret_cast<const double2*>(Li + e);
+    for (int a = tid; a < NB * 8; a += NTH) Lg[(NT + NB) * 64 + a] = s_sgn[a];
 }
 
 // Kernel 2 of 2: K = Sigma(:,idx) inv(L)' inv(L), sparseView, mu += K y, W = Sigma(:,idx) - K S,
@@ -734,12 +737,18 @@ cudaError_t launch_gain_tiled_t(int which, const EkfPtrs& p, const double* Pin, 
     const size_t sm_c = (size_t)(NT + NB) * 64 * sizeof(double) + NB * 8 * sizeof(int);
     const size_t sm_s = (size_t)((NT + NB) * 64 + NB * NB * 64 + NB * 8) * sizeof(double) + NB * 8 * sizeof(int);
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(ekf_chol_tiled<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c);
+        cudaError_t e = cudaFuncSetAttribute(ekf_chol_tiled<NB, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_chol_tiled<NB, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ekf_solve_tiled<NW, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_s);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    if (which == 0) ekf_chol_tiled<NB><<<p.F, 128, sm_c, st>>>(p, Pin, z, R, pass);
+    if (which == 0) {
+        static int chol_warps = 0;                 // EKFVIO_CHOL_WARPS=4 / 8 (experiments)
+        if (!chol_warps) { const char* e = getenv("EKFVIO_CHOL_WARPS"); chol_warps = (e && atoi(e) == 8) ? 8 : 4; }
+        if (chol_warps == 4) ekf_chol_tiled<NB, 4><<<p.F, 128, sm_c, st>>>(p, Pin, z, R, pass);
+        else ekf_chol_tiled<NB, 8><<<p.F, 256, sm_c, st>>>(p, Pin, z, R, pass);
+    }
     else {
         // symmetric filters: forward substitution only, two CTAs per filter; the others (and all of them under
         // EKFVIO_FLAG_LITERAL_JOSEPH): the full solve.  Each kernel skips the filters of the other.

@@ -207,10 +207,11 @@ Eigen::SparseMatrix<float> TightlyCoupledEKF::numericallyLinearizeProcess(Eigen:
     Eigen::SparseMatrix<float> out(N, N);
     for (int r = 0; r < N; ++r) for (int c = 0; c < N; ++c) out(r, c) = (float)F[(size_t)r * Nm + c];
     if (foreign) {
+        pull();                                            // snapshot = the foreign state now on the device ...
         base_mu = saved_mu;
         size_t i = 0;
         for (auto& e : features) e.setMu(saved_feat[i++]);
-        pushIfEdited();
+        pushIfEdited();                                    // ... so that putting the filter's own mean back registers as an edit
     }
     pull();
     return out;
