@@ -72,8 +72,9 @@ def ekf_config(F: int, n: int, world: int) -> dict:
 KLT_BYTES_WITH_DERIVS = 2_140_800   # SURVEY.md §8d, 640x480 levels 0-3, read once + write levels 1-3 + int16x2 derivatives
 KLT_BYTES_NO_DERIVS = 508_800
 # dram__bytes_read.sum + dram__bytes_write.sum per image pair of the two pyramid kernels from the round's ncu --set full capture
-# (profiles/r02_ncu_klt_summary.txt); None until a capture of the current kernels exists
-KLT_NCU_TRAFFIC_PER_PAIR = None
+# (profiles/r02_ncu_klt_summary.txt: klt_level0_tma_kernel 157.97 MB read + 330.78 MB written, klt_levels_fused_kernel 39.44 + 61.84 MB, 256 pairs;
+# less than the 2 649 600 algorithmic bytes per pair because part of the output is still in L2 when the kernels end)
+KLT_NCU_TRAFFIC_PER_PAIR = (157.97e6 + 330.78e6 + 39.44e6 + 61.84e6) / 256
 
 
 class ClockSampler:
@@ -723,9 +724,10 @@ def main():
             # `reference_equivalent` rates the same launch in the FLOPs of the update as the reference writes it (4 N^2 m).
             "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA.8x8x4 / DFMA share one pipe on sm_100)", "kernel": "covariance update (ekf_joseph_sym)",
                          "achieved": cov_achieved, "peak": peak, "unit": "TFLOP/s", "frac": cov_achieved / peak if peak else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of ekf_joseph_sym from the ncu --set full capture in
-                         # profiles/r01_ncu_full_summary.txt (1.201 GB + 0.922 GB for 4096 filters), scaled to this launch's filter count
-                         "traffic": (1.201e9 + 0.922e9) / 4096 * F if n == 50 else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ekf_joseph_sym from this round's ncu --set full capture
+                         # (profiles/r02_ncu_ekf_summary.txt: 1.2013 GB + 0.9253 GB for 4096 filters), scaled to this launch's filter count;
+                         # a profiler figure cannot be re-measured inside a timed run
+                         "traffic": (1.2013e9 + 0.9253e9) / 4096 * F if n == 50 else None,
                          "peak_source": "measured live by ekfvio_measure_fp64_peak (register-resident DMMA/DFMA loops); MEASURED_PEAKS.json has no FP64 entry",
                          "flops_per_launch": F * flops_cov_update_executed(n),
                          "reference_equivalent": {"flops_per_launch": F * flops_cov_update(n), "achieved": cov_reference},

@@ -25,7 +25,8 @@ def _load():
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(make -C ekf_vio_b200/csrc).  There is no CPU fallback."
         )
-    return C.CDLL(LIB_PATH)
+    # EKFVIO_LIB_PATH: an alternative build of the same library (kernel-variant A/B runs, tools/); never a fallback
+    return C.CDLL(os.environ.get("EKFVIO_LIB_PATH", LIB_PATH))
 
 
 lib = _load()

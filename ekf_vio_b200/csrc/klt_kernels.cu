@@ -393,12 +393,18 @@ __device__ __forceinline__ void patch_rows(uint8_t* img, int pitch, int X0, int 
     }
 }
 
+#ifndef KLT_L0_CTAS
+#define KLT_L0_CTAS 3
+#endif
+#ifndef KLT_FUSED_THREADS
+#define KLT_FUSED_THREADS 256
+#endif
 constexpr int ATW = 256, ATH = 64;                 // tile of klt_level0_tma_kernel (pixels)
 constexpr int HX = 16;                             // halo columns staged left and right of a tile (TMA box start: 16-byte aligned)
 constexpr int ASW = ATW + 2 * HX, ASH = ATH + 4;   // staged: x0-16 .. x0+ATW+15, y0-2 .. y0+ATH+1
 constexpr int ANT = 256;                           // threads: 8 warps = 8 row bands of RPT rows, 32 lanes = 32 column groups of 8 pixels
 
-__global__ void __launch_bounds__(ANT, 3) klt_level0_tma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
+__global__ void __launch_bounds__(ANT, KLT_L0_CTAS) klt_level0_tma_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                                                                 TmaJob j0, TmaJob j1, int w, int h, int cpitch, size_t cstride, int dpitch,
                                                                 size_t dstride, int npitch, size_t nstride, int tiles_per_cta) {
     constexpr int TILE_STRIDE = (ASH * ASW + 127) / 128 * 128;   // TMA destinations are 128-byte aligned
@@ -454,7 +460,7 @@ __global__ void __launch_bounds__(ANT, 3) klt_level0_tma_kernel(const __grid_con
 // Levels 1 .. nl of one image per CTA (nl <= 3).  Shared memory: the levels with a halo of HX columns left / right and 2 rows
 // above / below (pitch = level pitch + 2 HX, rows = roundup(h, 8) + 4: a thread's 8-row block may overhang the image); level 3 reuses
 // the space of level 1, which is dead by then.
-constexpr int FNT = 256;
+constexpr int FNT = KLT_FUSED_THREADS;
 
 __global__ void __launch_bounds__(FNT, 2) klt_levels_fused_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
                                                                   FusedJob j0, FusedJob j1, FusedLevel l1, FusedLevel l2, FusedLevel l3, int nl) {
