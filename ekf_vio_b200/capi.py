@@ -112,6 +112,8 @@ SIGNATURES = {
     "ekfvio_klt_build_pyramid_pair_ref": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ekfvio_klt_track": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "ekfvio_klt_postprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ekfvio_klt_sample_uncertainty": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "ekfvio_klt_sample_uncertainty_h": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "ekfvio_klt_track_pair_h": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ekfvio_klt_track_next_h": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ekfvio_klt_read_level": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, C.POINTER(c_int), C.POINTER(c_int)]),
@@ -484,6 +486,15 @@ class FastDetector:
     @property
     def launches(self) -> int:
         return int(lib.ekfvio_fast_launch_count(self._h))
+
+
+def klt_sample_uncertainty_h(ref_img: np.ndarray, cur_img: np.ndarray, ref_pts: np.ndarray, pts: np.ndarray, device: int = 0) -> np.ndarray:
+    """KLTTracker::estimateUncertaintySampleBased for n features of one frame pair (host arrays) -> cov [n, 2, 2] f32."""
+    ref_img = np.ascontiguousarray(ref_img, np.uint8); cur_img = np.ascontiguousarray(cur_img, np.uint8)
+    ref_pts = np.ascontiguousarray(ref_pts, np.float32); pts = np.ascontiguousarray(pts, np.float32)
+    n = len(pts); cov = np.zeros((n, 4), np.float32)
+    _check(lib.ekfvio_klt_sample_uncertainty_h(device, _ptr(ref_img), _ptr(cur_img), ref_img.shape[1], ref_img.shape[0], ref_img.shape[1], _ptr(ref_pts), _ptr(pts), n, _ptr(cov)))
+    return cov.reshape(n, 2, 2)
 
 
 def frame_resize(src, inv_scale: int, dst=None):

@@ -77,11 +77,19 @@ Eigen::Matrix2f KLTTracker::estimateUncertainty(const Frame& cf, cv::Point2f mu)
     return A;
 }
 
-Eigen::Matrix2f KLTTracker::estimateUncertaintySampleBased(const Frame&, cv::Point2f, const Frame&, cv::Point2f) {
-    std::fprintf(stderr, "estimateUncertaintySampleBased: dead code in the reference (KLTTracker.cpp:111-175), not provided\n");
-    std::abort();
+// KLTTracker.cpp:111-175 (dead code in the reference): evaluated on the device for this one feature
+Eigen::Matrix2f KLTTracker::estimateUncertaintySampleBased(const Frame& lf, cv::Point2f mu_ref, const Frame& cf, cv::Point2f mu) {
+    KLT_ASSERT(lf.img.data && cf.img.data && lf.img.cols == cf.img.cols && lf.img.rows == cf.img.rows && lf.img.step == cf.img.step);
+    const float rp[2] = {mu_ref.x, mu_ref.y}, p[2] = {mu.x, mu.y};
+    float c[4] = {0, 0, 0, 0};
+    if (ekfvio_klt_sample_uncertainty_h(0, lf.img.data, cf.img.data, lf.img.cols, lf.img.rows, (int)lf.img.step, rp, p, 1, c)) {
+        std::fprintf(stderr, "estimateUncertaintySampleBased: %s\n", ekfvio_last_error());
+        std::abort();
+    }
+    Eigen::Matrix2f A;
+    A(0, 0) = c[0]; A(0, 1) = c[1]; A(1, 0) = c[2]; A(1, 1) = c[3];
+    return A;
 }
-
 
 // ---- Frame::Frame (Frame.cpp:15-41): resize on the device, scale K ---------------------------------------------------
 Frame::Frame(int inv_scale, const cv::Mat& full_img, const double k[9], const std::vector<double>& d, ros::Time _t) : t(_t) {

@@ -462,6 +462,41 @@ int ekfvio_klt_track_next_h(ekfvio_klt* k, const uint8_t* h_next, int pitch, int
     return 0;
 }
 
+// KLTTracker::estimateUncertaintySampleBased (KLTTracker.cpp:111-175) for a batch of frame pairs; device pointers.
+int ekfvio_klt_sample_uncertainty(int device, const uint8_t* d_ref_imgs, const uint8_t* d_cur_imgs, int width, int height, int pitch, int batch,
+                                  const float* d_ref_pts, const float* d_pts, const int* d_npts, int max_points, float* d_cov, void* stream) {
+    if (!d_ref_imgs || !d_cur_imgs || !d_ref_pts || !d_pts || !d_npts || !d_cov || width <= 0 || height <= 0 || pitch < width || batch <= 0 || max_points <= 0)
+        return fail_msg("ekfvio_klt_sample_uncertainty: bad arguments");
+    CU(cudaSetDevice(device));
+    CU(launch_sample_uncertainty(d_ref_imgs, d_cur_imgs, width, height, pitch, (size_t)pitch * height, batch, d_ref_pts, d_pts, d_npts, max_points, d_cov,
+                                 (cudaStream_t)stream));
+    return 0;
+}
+
+// The same for one frame pair in host memory (what the facade's single-feature call uses).
+int ekfvio_klt_sample_uncertainty_h(int device, const uint8_t* h_ref_img, const uint8_t* h_cur_img, int width, int height, int pitch, const float* h_ref_pts,
+                                    const float* h_pts, int n, float* h_cov) {
+    if (!h_ref_img || !h_cur_img || !h_ref_pts || !h_pts || !h_cov || n <= 0) return fail_msg("ekfvio_klt_sample_uncertainty_h: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail_msg("ekfvio_klt_sample_uncertainty_h: no CUDA device (this library has no CPU path)");
+    CU(cudaSetDevice(device));
+    const size_t ib = (size_t)pitch * height;
+    uint8_t* d_img = nullptr; float* d_f = nullptr; int* d_n = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_img, 2 * ib);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_f, (size_t)n * 8 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_n, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(d_img, h_ref_img, ib, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_img + ib, h_cur_img, ib, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_f, h_ref_pts, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_f + 2 * n, h_pts, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_n, &n, sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_sample_uncertainty(d_img, d_img + ib, width, height, pitch, ib, 1, d_f, d_f + 2 * n, d_n, n, d_f + 4 * n, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(h_cov, d_f + 4 * n, (size_t)n * 4 * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d_img); cudaFree(d_f); cudaFree(d_n);
+    if (e != cudaSuccess) return ekfvio::fail("ekfvio_klt_sample_uncertainty_h", e);
+    return 0;
+}
+
 int ekfvio_klt_read_level(ekfvio_klt* k, int slot, int img, int level, uint8_t* h_img, int16_t* h_deriv, int* w_out, int* h_out) {
     if (slot < 0 || slot >= k->num_slots || level < 0 || level >= k->pyr.levels || img < 0 || img >= k->max_batch) return fail_msg("ekfvio_klt_read_level: bad index");
     CU(cudaSetDevice(k->device));

@@ -821,9 +821,74 @@ __global__ void klt_postprocess_kernel(const float* __restrict__ next_pts, const
     }
 }
 
+// KLTTracker::estimateUncertaintySampleBased (KLTTracker.cpp:111-175; dead code in the reference — nothing calls it): a 5x5
+// reference patch around mu_ref in the last frame (cv::getRectSubPix, CV_32F) against 5x5 patches of the current frame at the 25
+// offsets (du, dv) in {-10, -5, 0, 5, 10}^2 around mu; rd = exp(-0.01 * SSD / 25) weights the second moments of the offsets.
+// One warp per feature: lane s < 25 evaluates sample s, lane 0 accumulates the four sums in the reference's order (du outer,
+// dv inner), so the float result does not depend on a reduction tree.  getRectSubPix as OpenCV's 8u -> 32f routine evaluates it:
+// a = max(frac x, 1e-4), a running "prev" term along the row, replicated borders.
+__device__ __forceinline__ void rect_subpix5(const uint8_t* __restrict__ img, int pitch, int w, int h, float cx, float cy, float (&out)[25]) {
+    cx -= 2.f; cy -= 2.f;                               // (win_size - 1) * 0.5
+    const int ix = (int)floorf(cx), iy = (int)floorf(cy);
+    float a = cx - ix; const float b = cy - iy;
+    a = fmaxf(a, 0.0001f);
+    const float a12 = a * (1.f - b), a22 = a * b, b1 = 1.f - b, b2 = b, sc = (1.f - a) / a;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        const int y0 = min(max(iy + i, 0), h - 1), y1 = min(max(iy + i + 1, 0), h - 1);
+        const uint8_t* r0 = img + (size_t)y0 * pitch;
+        const uint8_t* r1 = img + (size_t)y1 * pitch;
+        const int x0 = min(max(ix, 0), w - 1);
+        float prev = (1.f - a) * (b1 * (float)r0[x0] + b2 * (float)r1[x0]);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int x1 = min(max(ix + j + 1, 0), w - 1);
+            const float t = a12 * (float)r0[x1] + a22 * (float)r1[x1];
+            out[i * 5 + j] = prev + t;
+            prev = t * sc;
+        }
+    }
+}
+
+__global__ void klt_sample_uncertainty_kernel(const uint8_t* __restrict__ ref_imgs, const uint8_t* __restrict__ cur_imgs, int w, int h, int pitch,
+                                              size_t stride, const float* __restrict__ ref_pts, const float* __restrict__ pts,
+                                              const int* __restrict__ npts, int max_points, float* __restrict__ cov) {
+    const int lane = threadIdx.x & 31, b = blockIdx.y, pt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pt >= npts[b]) return;
+    const size_t o = (size_t)b * max_points + pt;
+    const uint8_t* I = ref_imgs + (size_t)b * stride;
+    const uint8_t* J = cur_imgs + (size_t)b * stride;
+    float rd = 0.f;
+    if (lane < 25) {
+        float ref[25], smp[25];
+        rect_subpix5(I, pitch, w, h, ref_pts[o * 2], ref_pts[o * 2 + 1], ref);
+        const float du = (float)(lane / 5) * 5.f - 10.f, dv = (float)(lane % 5) * 5.f - 10.f;
+        rect_subpix5(J, pitch, w, h, pts[o * 2] + du, pts[o * 2 + 1] + dv, smp);
+        float ssd = 0.f;
+#pragma unroll
+        for (int k = 0; k < 25; ++k) { const float d = ref[k] - smp[k]; ssd += (float)pow((double)d, 2.0); }
+        ssd /= 25.f;
+        rd = (float)exp((double)(-0.01f * ssd));
+    }
+    float s = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+    for (int k = 0; k < 25; ++k) {                      // the reference's accumulation order
+        const float r = __shfl_sync(0xffffffffu, rd, k);
+        const float du = (float)(k / 5) * 5.f - 10.f, dv = (float)(k % 5) * 5.f - 10.f;
+        s += r; sxx += r * du * du; syy += r * dv * dv; sxy += r * du * dv;
+    }
+    if (lane == 0) { cov[o * 4] = sxx / s; cov[o * 4 + 3] = syy / s; cov[o * 4 + 1] = sxy / s; cov[o * 4 + 2] = sxy / s; }
+}
+
 }  // namespace
 
 namespace kltdev {
+
+cudaError_t launch_sample_uncertainty(const uint8_t* ref_imgs, const uint8_t* cur_imgs, int w, int h, int pitch, size_t stride, int batch,
+                                      const float* ref_pts, const float* pts, const int* npts, int max_points, float* cov, cudaStream_t st) {
+    dim3 grid((max_points + 3) / 4, batch);
+    klt_sample_uncertainty_kernel<<<grid, 128, 0, st>>>(ref_imgs, cur_imgs, w, h, pitch, stride, ref_pts, pts, npts, max_points, cov);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_level(const LevelJob& j0, const LevelJob& j1, int w, int h, int cpitch, size_t cstride, int dpitch, size_t dstride,
                          int npitch, size_t nstride, cudaStream_t st) {

@@ -18,6 +18,8 @@ cudaError_t launch_level0_tma(const CUtensorMap& m0, const CUtensorMap& m1, cons
                               int dpitch, size_t dstride, int npitch, size_t nstride, cudaStream_t st);
 cudaError_t launch_levels_fused(const CUtensorMap& m0, const CUtensorMap& m1, const FusedJob& j0, const FusedJob& j1, const FusedLevel* lv, int nl,
                                 size_t smem, cudaStream_t st);
+cudaError_t launch_sample_uncertainty(const uint8_t* ref_imgs, const uint8_t* cur_imgs, int w, int h, int pitch, size_t stride, int batch,
+                                      const float* ref_pts, const float* pts, const int* npts, int max_points, float* cov, cudaStream_t st);
 size_t track_smem_bytes(int win);
 cudaError_t launch_track(const Pyr& pyr, const uint8_t* prev_slot, const uint8_t* next_slot, const float* prev_pts, float* next_pts,
                          uint8_t* status, float* err, const int* npts, int max_points, int first_image, int batch, const ekfvio_klt_params& prm,

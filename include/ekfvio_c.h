@@ -246,6 +246,15 @@ int ekfvio_klt_track(ekfvio_klt* k, int prev_slot, int next_slot, const float* d
 int ekfvio_klt_postprocess(ekfvio_klt* k, const float* d_next_pts, const uint8_t* d_status, const int* d_npts, const float* d_K9,
                            int batch, float* d_measured, float* d_cov, uint8_t* d_passed, void* stream);
 
+/* KLTTracker::estimateUncertaintySampleBased (KLTTracker.cpp:111-175; dead code in the reference, provided for completeness):
+ * per feature a 2x2 covariance in pixel units from a 5x5 reference patch (cv::getRectSubPix) compared with 25 shifted patches of
+ * the current frame.  d_cov[batch][max_points][4] row-major.  Parity: OpenCV's getRectSubPix (cv2 4.13) + the reference's loop
+ * restated in numpy (tests/test_gpu_klt.py); the reference has no test for it. */
+int ekfvio_klt_sample_uncertainty(int device, const uint8_t* d_ref_imgs, const uint8_t* d_cur_imgs, int width, int height, int pitch, int batch,
+                                  const float* d_ref_pts, const float* d_pts, const int* d_npts, int max_points, float* d_cov, void* stream);
+int ekfvio_klt_sample_uncertainty_h(int device, const uint8_t* h_ref_img, const uint8_t* h_cur_img, int width, int height, int pitch,
+                                    const float* h_ref_pts, const float* h_pts, int n, float* h_cov);
+
 /* Host-buffer convenience: build both pyramids from host images, track, post-process, copy the
  * results back; synchronous.  The KLTTracker facade's findNewFeaturePositions is this call. */
 int ekfvio_klt_track_pair_h(ekfvio_klt* k, const uint8_t* h_prev, const uint8_t* h_next, int pitch, int batch, const float* h_prev_pts,

@@ -272,3 +272,40 @@ def test_pyramid_pair_by_reference_tracks_like_the_copying_build(cuda):
         for a, b in zip(res[0][3], res[1][3]):
             np.testing.assert_array_equal(a[0], b[0]); np.testing.assert_array_equal(a[1], b[1])
         assert res[0][1].sum() > 0.8 * B * npts
+
+
+def test_sample_based_uncertainty_matches_getrectsubpix_restatement(cuda):
+    """KLTTracker::estimateUncertaintySampleBased (KLTTracker.cpp:111-175, dead code in the reference: parity unpinned there).
+    Oracle: the reference's loop restated with OpenCV's own cv2.getRectSubPix(patchType=CV_32F) — interior features, features
+    whose samples reach over the image border (replicated), integer and fractional positions."""
+    cv2 = pytest.importorskip("cv2")
+    from ekf_vio_b200 import capi, workload
+    g = workload.config2_fixture()
+    ref_img, cur_img = g["gray0"], g["gray_moved"]
+    rng = np.random.default_rng(9)
+    mu_ref = np.concatenate([g["pts200"][:40], rng.uniform([2, 2], [637, 477], (20, 2)), np.array([[3.0, 3.0], [636.5, 476.25], [320.0, 5.0]])]).astype(np.float32)
+    mu = (mu_ref + rng.uniform(-3, 3, mu_ref.shape)).astype(np.float32)
+    mu[:10] = np.round(mu[:10])                                   # integer positions: a = max(0, 1e-4) branch of getRectSubPix
+    got = capi.klt_sample_uncertainty_h(ref_img, cur_img, mu_ref, mu)
+    want = np.zeros_like(got)
+    for i in range(len(mu)):
+        ref = cv2.getRectSubPix(ref_img, (5, 5), (float(mu_ref[i, 0]), float(mu_ref[i, 1])), patchType=cv2.CV_32F)
+        s = sxx = syy = sxy = np.float32(0)
+        for du in (-10.0, -5.0, 0.0, 5.0, 10.0):
+            for dv in (-10.0, -5.0, 0.0, 5.0, 10.0):
+                smp = cv2.getRectSubPix(cur_img, (5, 5), (float(np.float32(mu[i, 0] + np.float32(du))), float(np.float32(mu[i, 1] + np.float32(dv)))), patchType=cv2.CV_32F)
+                ssd = np.float32(0)
+                for a in range(5):
+                    for b in range(5):
+                        ssd = np.float32(ssd + np.float32(np.float64(ref[a, b] - smp[a, b]) ** 2))
+                ssd = np.float32(ssd / np.float32(25))
+                rd = np.float32(np.exp(np.float64(np.float32(-0.01) * ssd)))
+                s = np.float32(s + rd); sxx = np.float32(sxx + np.float32(np.float32(rd * np.float32(du)) * np.float32(du)))
+                syy = np.float32(syy + np.float32(np.float32(rd * np.float32(dv)) * np.float32(dv))); sxy = np.float32(sxy + np.float32(np.float32(rd * np.float32(du)) * np.float32(dv)))
+        want[i] = [[sxx / s, sxy / s], [sxy / s, syy / s]]
+    assert np.isfinite(got).all()
+    # float exp / pow of two libraries and OpenCV's vectorised getRectSubPix: agreement to ~1e-4 of each feature's covariance scale
+    err = np.abs(got - want).reshape(len(mu), -1).max(1) / np.abs(want).reshape(len(mu), -1).max(1)
+    print(f"sample-based uncertainty: worst relative difference {err.max():.2e} over {len(mu)} features")
+    assert err.max() <= 5e-4
+    assert np.abs(got[:, 0, 1] - got[:, 1, 0]).max() == 0
