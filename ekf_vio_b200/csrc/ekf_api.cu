@@ -31,6 +31,7 @@ static EkfPtrs ptrs(const ekfvio_batch* b) {
     p.klt_last = b->d_klt_last; p.status = b->d_status; p.idx = b->d_idx; p.y = b->d_y; p.m = b->d_m; p.K = b->d_K; p.W = b->d_W; p.L = b->d_L; p.asym = b->d_asym; p.route = b->d_route;
     p.F = b->F; p.nmax = b->nmax; p.Nmax = b->Nmax; p.ldP = b->ldP; p.ldK = b->ldK; p.mmax = b->mmax;
     p.flags = b->prm.flags;
+    p.fused = 0;
     p.sigma_lower = b->upper_stale ? 1 : 0;
     p.depth = b->prm.default_point_depth; p.depth_var = b->prm.default_point_depth_variance;
     p.uv_var = b->prm.default_point_homogenous_variance;
@@ -142,6 +143,8 @@ int ekfvio_batch_create(ekfvio_batch** out, int device, int num_filters, int max
         const EkfPtrs pp = ptrs(b);
         b->lower_ok = !(b->prm.flags & (EKFVIO_FLAG_FORCE_GENERAL_PATH | EKFVIO_FLAG_LITERAL_JOSEPH | 0x100u | 0x200u | 0x400u)) && !b->large &&
                       gain_tiled_supported(pp) && joseph_sym_supported(pp) && process_lower_capable(pp);
+        const char* nf = getenv("EKFVIO_NO_FUSED_UPDATE");       // (experiments: the round-1/2 three-kernel update)
+        b->fused_ok = b->lower_ok && update_fused_supported(pp) && !(nf && atoi(nf) != 0);
     }
     if (cudaStreamCreateWithFlags(&b->copy_st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming) != cudaSuccess ||
@@ -207,7 +210,8 @@ int ekfvio_batch_remove_features(ekfvio_batch* b, const uint8_t* d_remove, void*
 
 int ekfvio_batch_process(ekfvio_batch* b, const double* d_dt, void* stream) {
     CU(cudaSetDevice(b->device));
-    if (ensure_full_sigma(b, (cudaStream_t)stream)) return 1;     // (two process() calls in a row)
+    // (a lower-mode process reads rows 0..21 and each feature row up to its diagonal block only: a stale upper part does no harm)
+    if (!b->lower_ok && ensure_full_sigma(b, (cudaStream_t)stream)) return 1;
     b->timer.begin(0, (cudaStream_t)stream);
     CU(launch_process_general(ptrs(b), b->d_P[b->cur], b->d_P[b->cur ^ 1], d_dt, 0, nullptr, (cudaStream_t)stream, &b->launches, b->lower_ok ? 1 : 0));
     b->timer.end((cudaStream_t)stream);
@@ -253,6 +257,16 @@ int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, c
         size_t bytes = (size_t)b->F * ((size_t)b->mmax * b->mmax + b->mmax) * sizeof(double);
         CU(cudaMalloc((void**)&b->d_S, bytes));
     }
+    const bool fused = b->fused_ok && gain_tiled;
+    if (fused) {
+        // the whole update of every symmetric, well-conditioned filter in one kernel; it marks those filters ROUTE_DONE and the
+        // launches below only serve the rest (normally none: a few flag reads per CTA)
+        b->timer.begin(4, st);
+        CU(launch_update_fused(pp, b->d_P[b->cur], b->d_P[b->cur ^ 1], d_z, d_R, d_pass, st));
+        b->timer.end(st);
+        b->launches += 1;
+        pp.fused = 1;
+    }
     if (gain_tiled) {
         b->timer.begin(1, st);
         CU(launch_gain_tiled(0, pp, b->d_P[b->cur], d_z, d_R, d_pass, st));
@@ -283,7 +297,7 @@ int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, c
     }
     b->timer.end(st);
     b->cur ^= 1;
-    b->upper_stale = false;     // the covariance kernels write the whole matrix
+    b->upper_stale = fused;     // the covariance kernels write the whole matrix, ekf_update_fused its lower form
     b->launches += 2;
     return 0;
 }

@@ -175,5 +175,8 @@ struct ekfvio_batch {
     // complete only up to their diagonal blocks; the update that follows restores the full matrix, any other reader
     // of Sigma gets it mirrored first (ensure_full_sigma)
     bool lower_ok = false, upper_stale = false;
+    // fused mode: ekf_update_fused (Sigma in registers, block-sequential update) runs first and leaves Sigma' in the same
+    // lower form; the tiled kernels behind it serve the filters it leaves alone
+    bool fused_ok = false;
     cudaStream_t last_stream = nullptr;       // stream of the last process()
 };

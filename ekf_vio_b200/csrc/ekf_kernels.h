@@ -24,6 +24,11 @@ inline int current_device_slot() { int dev = 0; return (cudaGetDevice(&dev) == c
 //   ROUTE_JOSEPH_FULL asymmetric R or Sigma: the Joseph form with no symmetry assumption (ekf_solve_tiled + ekf_joseph_tiled)
 // (EKFVIO_FLAG_FORCE_GENERAL_PATH bypasses all of this: the general kernels, LDL^T exactly as the oracle's.)
 constexpr int ROUTE_SYM = 0, ROUTE_JOSEPH_SYM = 1, ROUTE_JOSEPH_FULL = 2;
+//   ROUTE_DONE        (fused mode only) ekf_update_fused has already carried out the whole update of this filter — the block-sequential
+//                     form of ROUTE_SYM with Sigma resident in registers (ekf_fused.cu); every other update kernel skips it.  Filters
+//                     the fused kernel leaves alone (asymmetric Sigma or R, S not positive definite or beyond ILLCOND_RATIO) are
+//                     marked -1 there and routed by ekf_chol_tiled as above.
+constexpr int ROUTE_DONE = 3;
 // max pivot / min pivot of the factor of S.  Healthy updates sit at 1e5 (first update: cond(S) ~ 9e5).  Measured on the config-3
 // streams against the extended-precision oracle (tools/step_error_probe.py, profiles/r02_illcond_sweep.log): up to 1e9 every
 // reduced update stays within the FP64 oracle's own rounding error of the step; at 1e11 the first ones do not.
@@ -36,6 +41,7 @@ struct EkfPtrs {
     int* route;        // per update: ROUTE_SYM / ROUTE_JOSEPH_SYM / ROUTE_JOSEPH_FULL
     int F, nmax, Nmax, ldP, ldK, mmax;
     uint32_t flags;
+    int fused;         // ekf_update_fused ran first: filters with route == ROUTE_DONE are finished
     int sigma_lower;   // the input Sigma of symmetric filters is valid only up to the diagonal block of each feature row (after a lower-mode process)
     double depth, depth_var, uv_var;
     double illcond;    // pivot-ratio threshold of the reduced update (ILLCOND_RATIO; EKFVIO_ILLCOND in the environment overrides it for experiments)
@@ -70,6 +76,11 @@ cudaError_t launch_gain_tiled(int which, const EkfPtrs& p, const double* Pin, co
 cudaError_t launch_joseph_tiled(const EkfPtrs& p, const double* Pin, double* Pout, int only_asym, cudaStream_t st);
 bool joseph_sym_supported(const EkfPtrs& p);
 cudaError_t launch_joseph_sym(const EkfPtrs& p, const double* Pin, double* Pout, cudaStream_t st);
+
+// fused sequential update, Sigma in registers (ekf_fused.cu)
+bool update_fused_supported(const EkfPtrs& p);
+cudaError_t launch_update_fused(const EkfPtrs& p, const double* Pin, double* Pout, const double* z, const double* R, const uint8_t* pass,
+                                cudaStream_t st);
 
 // large-state blocked path (ekf_large.cu)
 struct LargePtrs { double* S; double* L; double* T; int mp; int nblk; int nrt_max; };

@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(NWC * 32, 4) ekf_chol_tiled(EkfPtrs p, const d
     __shared__ int s_m, s_bad;
 
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (p.fused && p.route[f] == ROUTE_DONE) return;       // ekf_update_fused has finished this filter
     const int n = p.nfeat[f];
     const int ld = p.ldP, nmax = p.nmax;
     const double* Pi = Pin + (size_t)f * ld * ld;
@@ -605,7 +606,7 @@ __device__ __forceinline__ void solve_tiled_filter(const EkfPtrs& p, const doubl
 template <int NW, int NB>
 __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const double* __restrict__ Pin, const double* __restrict__ Rin) {
     for (int f = blockIdx.x; f < p.F; f += gridDim.x) {   // persistent: see ekf_joseph_tiled
-        if (p.route[f] == ROUTE_SYM) continue;   // ekf_fwd_tiled
+        if (p.route[f] == ROUTE_SYM || p.route[f] == ROUTE_DONE) continue;   // ekf_fwd_tiled / ekf_update_fused
         solve_tiled_filter<NW, NB>(p, Pin, Rin, f);
         __syncthreads();
     }
@@ -805,7 +806,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
     auto meta = [&](int f) {
         Meta M; M.f = f; M.schur = true;
         const int route = f < p.F ? p.route[f] : ROUTE_JOSEPH_FULL;
-        if (route != ROUTE_JOSEPH_FULL) {
+        if (route != ROUTE_JOSEPH_FULL && route != ROUTE_DONE) {
             M.N = BASE + 3 * p.nfeat[f]; M.m = p.m[f]; M.schur = route == ROUTE_SYM;
         } else { M.N = 0; M.m = 0; }                        // nothing to do (asymmetric filters: ekf_joseph_tiled)
         const bool schur = M.schur;
@@ -852,7 +853,10 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
     for (int i = tid; i < cur.m; i += NW * 32) s_idx[0][i] = p.idx[(size_t)cur.f * p.mmax + i];
     __syncthreads();
     issue(cur, 0, s_idx[0]); issue(cur, 1, s_idx[0]);
-    int gc = 0;                                            // stages consumed so far
+    // Ring position of the current / next filter's stage 0.  Stage v of a filter is group g0 + v: a filter with fewer than two
+    // stages (nothing to do here, or m = 0) still advances the ring by the two (empty) groups issued for it, so the consumer must
+    // follow the issue counter, not a count of stages consumed.
+    int g0_cur = 0, g0_nxt = 0;
 
     while (cur.f < p.F) {
         Meta nxt = meta(cur.f + gridDim.x);
@@ -890,10 +894,9 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
             cp_async_wait<SNST - 2>();
             __syncthreads();
             if (v + 2 < cur.nv) issue(cur, v + 2, s_idx[ib]);
-            else { issue(nxt, issued_next, s_idx[ib ^ 1]); ++issued_next; }
-            const double* A = sms + (gc % SNST) * STAGE;
+            else { if (issued_next == 0) g0_nxt = gs; issue(nxt, issued_next, s_idx[ib ^ 1]); ++issued_next; }
+            const double* A = sms + ((g0_cur + v) % SNST) * STAGE;
             const double* B = cur.schur ? A : A + A_DOUBLES;
-            ++gc;
             const bool phase1 = cur.schur || v >= cur.nch;
 #pragma unroll
             for (int kk = 0; kk < SKC / 4; ++kk) {
@@ -914,7 +917,8 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
                 }
             }
         }
-        while (issued_next < 2) { issue(nxt, issued_next, s_idx[ib ^ 1]); ++issued_next; }   // short filters (nv < 2)
+        if (issued_next < 2 && cur.nv > 0) __syncthreads();   // a one-stage filter: the refill below reuses the buffer just consumed
+        while (issued_next < 2) { if (issued_next == 0) g0_nxt = gs; issue(nxt, issued_next, s_idx[ib ^ 1]); ++issued_next; }   // short filters (nv < 2)
 
         // epilogue: Sigma'(I,J) and its mirror Sigma'(J,I); the mirror goes through an 8x8 transpose in
         // shared memory so that both stores are row-contiguous
@@ -958,7 +962,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
                 }
             }
         }
-        cur = nxt; ib ^= 1;
+        cur = nxt; ib ^= 1; g0_cur = g0_nxt;
     }
     cp_async_wait<0>();
 }
