@@ -31,7 +31,7 @@ static EkfPtrs ptrs(const ekfvio_batch* b) {
     p.klt_last = b->d_klt_last; p.status = b->d_status; p.idx = b->d_idx; p.y = b->d_y; p.m = b->d_m; p.K = b->d_K; p.W = b->d_W; p.L = b->d_L; p.asym = b->d_asym; p.route = b->d_route;
     p.F = b->F; p.nmax = b->nmax; p.Nmax = b->Nmax; p.ldP = b->ldP; p.ldK = b->ldK; p.mmax = b->mmax;
     p.flags = b->prm.flags;
-    p.fused = 0;
+    p.fused = 0; p.fb = nullptr;
     p.sigma_lower = b->upper_stale ? 1 : 0;
     p.depth = b->prm.default_point_depth; p.depth_var = b->prm.default_point_depth_variance;
     p.uv_var = b->prm.default_point_homogenous_variance;
@@ -74,7 +74,7 @@ int ekfvio_batch_destroy(ekfvio_batch* b) {
     cudaSetDevice(b->device);
     cudaFree(b->d_mu); cudaFree(b->d_feat); cudaFree(b->d_P[0]); cudaFree(b->d_P[1]); cudaFree(b->d_nfeat); cudaFree(b->d_cache);
     cudaFree(b->d_flags); cudaFree(b->d_klt_last); cudaFree(b->d_status); cudaFree(b->d_dt); cudaFree(b->d_K); cudaFree(b->d_W);
-    cudaFree(b->d_S); cudaFree(b->d_L); cudaFree(b->d_asym); cudaFree(b->d_route); cudaFree(b->d_LS); cudaFree(b->d_LL); cudaFree(b->d_LT); cudaFree(b->d_y); cudaFree(b->d_idx); cudaFree(b->d_m); cudaFree(b->d_fjac);
+    cudaFree(b->d_S); cudaFree(b->d_L); cudaFree(b->d_asym); cudaFree(b->d_route); cudaFree(b->d_fb); cudaFree(b->d_LS); cudaFree(b->d_LL); cudaFree(b->d_LT); cudaFree(b->d_y); cudaFree(b->d_idx); cudaFree(b->d_m); cudaFree(b->d_fjac);
     cudaFree(b->dd_z); cudaFree(b->dd_R); cudaFree(b->dd_pass);
     cudaFreeHost(b->h_z); cudaFreeHost(b->h_R); cudaFreeHost(b->h_pass); cudaFreeHost(b->h_out);
     if (b->copy_st) cudaStreamDestroy(b->copy_st);
@@ -124,6 +124,7 @@ int ekfvio_batch_create(ekfvio_batch** out, int device, int num_filters, int max
     ALLOC(b->d_m, F * sizeof(int));
     ALLOC(b->d_asym, F * sizeof(int));
     ALLOC(b->d_route, F * sizeof(int));
+    ALLOC(b->d_fb, (F + 1) * sizeof(int));
     if (b->Nmax <= 176 && b->mmax <= 104) ALLOC(b->d_L, F * gain_tiled_scratch_doubles(b->mmax) * sizeof(double));
     if (b->large) {
         ALLOC(b->d_LS, F * large_scratch_doubles_S(b->mmax) * sizeof(double));
@@ -262,6 +263,8 @@ int ekfvio_batch_update(ekfvio_batch* b, const double* d_z, const double* d_R, c
         // the whole update of every symmetric, well-conditioned filter in one kernel; it marks those filters ROUTE_DONE and the
         // launches below only serve the rest (normally none: a few flag reads per CTA)
         b->timer.begin(4, st);
+        pp.fb = b->d_fb;
+        CU(cudaMemsetAsync(b->d_fb, 0, sizeof(int), st));
         CU(launch_update_fused(pp, b->d_P[b->cur], b->d_P[b->cur ^ 1], d_z, d_R, d_pass, st));
         b->timer.end(st);
         b->launches += 1;

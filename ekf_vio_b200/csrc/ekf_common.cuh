@@ -159,6 +159,7 @@ struct ekfvio_batch {
     int* d_m = nullptr;            // [F]
     int* d_asym = nullptr;         // [F] sticky: Sigma or an R block of this filter is not symmetric
     int* d_route = nullptr;        // [F] update path of the current update (ekf_kernels.h ROUTE_*)
+    int* d_fb = nullptr;           // [1 + F] fused mode: the filters ekf_update_fused left to the tiled kernels (count, indices)
     double* d_fjac = nullptr;      // [F][(22*22 + nmax*27 + nmax*9)] A | B | D
     // pinned staging + device input buffers for the *_h entry points
     double* h_z = nullptr; double* h_R = nullptr; uint8_t* h_pass = nullptr;

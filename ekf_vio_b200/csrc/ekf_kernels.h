@@ -42,6 +42,7 @@ struct EkfPtrs {
     int F, nmax, Nmax, ldP, ldK, mmax;
     uint32_t flags;
     int fused;         // ekf_update_fused ran first: filters with route == ROUTE_DONE are finished
+    int* fb;           // fused mode: [0] number of filters ekf_update_fused left alone, [1..] their indices; nullptr otherwise
     int sigma_lower;   // the input Sigma of symmetric filters is valid only up to the diagonal block of each feature row (after a lower-mode process)
     double depth, depth_var, uv_var;
     double illcond;    // pivot-ratio threshold of the reduced update (ILLCOND_RATIO; EKFVIO_ILLCOND in the environment overrides it for experiments)

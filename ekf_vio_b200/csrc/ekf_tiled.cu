@@ -148,7 +148,9 @@ __device__ __forceinline__ void joseph_tiled_filter(const EkfPtrs& p, const doub
 // when there are none, the whole launch is a few flag reads.
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const double* __restrict__ Pin, double* __restrict__ Pout, int only_asym) {
-    for (int f = blockIdx.x; f < p.F; f += gridDim.x) {
+    const int total = p.fb ? p.fb[0] : p.F;                // behind ekf_update_fused: only the filters it left alone
+    for (int li = blockIdx.x; li < total; li += gridDim.x) {
+        const int f = p.fb ? p.fb[1 + li] : li;
         if (only_asym && p.route[f] != ROUTE_JOSEPH_FULL) continue;   // the symmetric routes went to ekf_joseph_sym
         joseph_tiled_filter<NW>(p, Pin, Pout, f);
         __syncthreads();                                  // shared memory is reused by the next filter
@@ -175,8 +177,8 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const 
 // and ~54 KB of shared memory, so four filters share an SM and hide each other's serial
 // diagonal-tile steps.  L tiles and inverse tiles go to global scratch in their swizzled layout.
 template <int NB, int NWC>
-__global__ void __launch_bounds__(NWC * 32, 4) ekf_chol_tiled(EkfPtrs p, const double* __restrict__ Pin, const double* __restrict__ z,
-                                                         const double* __restrict__ Rin, const uint8_t* __restrict__ pass) {
+__device__ __forceinline__ void chol_tiled_filter(const EkfPtrs& p, const double* __restrict__ Pin, const double* __restrict__ z,
+                                                  const double* __restrict__ Rin, const uint8_t* __restrict__ pass, const int f) {
     extern __shared__ __align__(16) double smc[];
     constexpr int NT = NB * (NB + 1) / 2;
     constexpr int NTH = NWC * 32;
@@ -185,8 +187,7 @@ __global__ void __launch_bounds__(NWC * 32, 4) ekf_chol_tiled(EkfPtrs p, const d
     int* s_idx = reinterpret_cast<int*>(Li + NB * 64);   // NB*8
     __shared__ int s_m, s_bad;
 
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (p.fused && p.route[f] == ROUTE_DONE) return;       // ekf_update_fused has finished this filter
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = p.nfeat[f];
     const int ld = p.ldP, nmax = p.nmax;
     const double* Pi = Pin + (size_t)f * ld * ld;
@@ -359,6 +360,19 @@ __global__ void __launch_bounds__(NWC * 32, 4) ekf_chol_tiled(EkfPtrs p, const d
     for (int e = tid * 2; e < used; e += 2 * NTH) *reinterpret_cast<double2*>(Lg + e) = *reinterpret_cast<const double2*>(Ls + e);
     for (int e = tid * 2; e < nb * 64; e += 2 * NTH) *reinterpret_cast<double2*>(Lg + NT * 64 + e) = *reinterpret_cast<const double2*>(Li + e);
     for (int a = tid; a < NB * 8; a += NTH) Lg[(NT + NB) * 64 + a] = s_sgn[a];
+}
+
+// One CTA per filter — or, behind ekf_update_fused (p.fb != nullptr), a small grid that walks over the list of filters the fused
+// kernel left alone (normally none: the launch is one read of the list length per CTA).
+template <int NB, int NWC>
+__global__ void __launch_bounds__(NWC * 32, 4) ekf_chol_tiled(EkfPtrs p, const double* __restrict__ Pin, const double* __restrict__ z,
+                                                         const double* __restrict__ Rin, const uint8_t* __restrict__ pass) {
+    if (p.fb == nullptr) { chol_tiled_filter<NB, NWC>(p, Pin, z, Rin, pass, blockIdx.x); return; }
+    const int cnt = p.fb[0];
+    for (int li = blockIdx.x; li < cnt; li += gridDim.x) {
+        chol_tiled_filter<NB, NWC>(p, Pin, z, Rin, pass, p.fb[1 + li]);
+        __syncthreads();
+    }
 }
 
 // Kernel 2 of 2: K = Sigma(:,idx) inv(L)' inv(L), sparseView, mu += K y, W = Sigma(:,idx) - K S,
@@ -605,7 +619,9 @@ __device__ __forceinline__ void solve_tiled_filter(const EkfPtrs& p, const doubl
 
 template <int NW, int NB>
 __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const double* __restrict__ Pin, const double* __restrict__ Rin) {
-    for (int f = blockIdx.x; f < p.F; f += gridDim.x) {   // persistent: see ekf_joseph_tiled
+    const int total = p.fb ? p.fb[0] : p.F;                // behind ekf_update_fused: only the filters it left alone
+    for (int li = blockIdx.x; li < total; li += gridDim.x) {   // persistent: see ekf_joseph_tiled
+        const int f = p.fb ? p.fb[1 + li] : li;
         if (p.route[f] == ROUTE_SYM || p.route[f] == ROUTE_DONE) continue;   // ekf_fwd_tiled / ekf_update_fused
         solve_tiled_filter<NW, NB>(p, Pin, Rin, f);
         __syncthreads();
@@ -618,7 +634,7 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_solve_tiled(EkfPtrs p, const d
 // 16-row strips each, strips in registers as in ekf_solve_tiled) and two CTAs per SM, so that one CTA's
 // factor copy and gathers overlap the other's substitution.  v = inv(L) y comes from ekf_chol_tiled (in p.y).
 template <int NW, int NB>
-__global__ void __launch_bounds__(NW * 32, 2) ekf_fwd_tiled(EkfPtrs p, const double* __restrict__ Pin) {
+__device__ __forceinline__ void fwd_tiled_filter(const EkfPtrs& p, const double* __restrict__ Pin, const int f) {
     extern __shared__ __align__(16) double smf[];
     constexpr int NT = NB * (NB + 1) / 2;
     double* Ls = smf;                      // NT tiles
@@ -626,7 +642,7 @@ __global__ void __launch_bounds__(NW * 32, 2) ekf_fwd_tiled(EkfPtrs p, const dou
     double* s_v = Li + NB * 64;            // NB*8: inv(L) y
     int* s_idx = reinterpret_cast<int*>(s_v + NB * 8);   // NB*8
 
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m = p.m[f];
     if (m == 0 || p.route[f] != ROUTE_SYM) return;  // the others: ekf_solve_tiled
     const int n = p.nfeat[f], N = BASE + 3 * n;
@@ -731,6 +747,16 @@ __global__ void __launch_bounds__(NW * 32, 2) ekf_fwd_tiled(EkfPtrs p, const dou
 }
 
 template <int NW, int NB>
+__global__ void __launch_bounds__(NW * 32, 2) ekf_fwd_tiled(EkfPtrs p, const double* __restrict__ Pin) {
+    if (p.fb == nullptr) { fwd_tiled_filter<NW, NB>(p, Pin, blockIdx.x); return; }
+    const int cnt = p.fb[0];
+    for (int li = blockIdx.x; li < cnt; li += gridDim.x) {
+        fwd_tiled_filter<NW, NB>(p, Pin, p.fb[1 + li]);
+        __syncthreads();
+    }
+}
+
+template <int NW, int NB>
 cudaError_t launch_gain_tiled_t(int which, const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, cudaStream_t st) {
     static bool configured_on[64] = {false};
     bool& configured = configured_on[current_device_slot()];
@@ -747,8 +773,9 @@ cudaError_t launch_gain_tiled_t(int which, const EkfPtrs& p, const double* Pin, 
     if (which == 0) {
         static int chol_warps = 0;                 // EKFVIO_CHOL_WARPS=4 / 8 (experiments)
         if (!chol_warps) { const char* e = getenv("EKFVIO_CHOL_WARPS"); chol_warps = (e && atoi(e) == 8) ? 8 : 4; }
-        if (chol_warps == 4) ekf_chol_tiled<NB, 4><<<p.F, 128, sm_c, st>>>(p, Pin, z, R, pass);
-        else ekf_chol_tiled<NB, 8><<<p.F, 256, sm_c, st>>>(p, Pin, z, R, pass);
+        const int grid = (p.fb && p.F > 148) ? 148 : p.F;
+        if (chol_warps == 4) ekf_chol_tiled<NB, 4><<<grid, 128, sm_c, st>>>(p, Pin, z, R, pass);
+        else ekf_chol_tiled<NB, 8><<<grid, 256, sm_c, st>>>(p, Pin, z, R, pass);
     }
     else {
         // symmetric filters: forward substitution only, two CTAs per filter; the others (and all of them under
@@ -762,7 +789,7 @@ cudaError_t launch_gain_tiled_t(int which, const EkfPtrs& p, const double* Pin, 
             if (e != cudaSuccess) return e;
             configured_f = true;
         }
-        if (!(p.flags & EKFVIO_FLAG_LITERAL_JOSEPH)) ekf_fwd_tiled<NWF, NB><<<dim3(p.F, 2), NWF * 32, sm_f, st>>>(p, Pin);
+        if (!(p.flags & EKFVIO_FLAG_LITERAL_JOSEPH)) ekf_fwd_tiled<NWF, NB><<<dim3((p.fb && p.F > 148) ? 148 : p.F, 2), NWF * 32, sm_f, st>>>(p, Pin);
         ekf_solve_tiled<NW, NB><<<p.F < 148 ? p.F : 148, NW * 32, sm_s, st>>>(p, Pin, R);
     }
     return cudaGetLastError();
@@ -802,9 +829,12 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
     // schur: the gain kernel left Z = Sigma(:,idx) inv(L)' in the K panel and Sigma' = Sigma - Z Z' is one phase;
     // otherwise (EKFVIO_FLAG_LITERAL_JOSEPH) the K and W panels go through the two phases of the Joseph form.
     // (per filter: ROUTE_SYM one phase with Z, ROUTE_JOSEPH_SYM two phases with K and W)
-    struct Meta { int f, N, m, nch, nv; bool schur; const double* Pi; const double* Kf; const double* Wf; };
-    auto meta = [&](int f) {
-        Meta M; M.f = f; M.schur = true;
+    // (behind ekf_update_fused the CTA walks over the list of filters that kernel left alone instead of the whole batch)
+    const int total = p.fb ? p.fb[0] : p.F;
+    struct Meta { int li, f, N, m, nch, nv; bool schur; const double* Pi; const double* Kf; const double* Wf; };
+    auto meta = [&](int li) {
+        const int f = li < total ? (p.fb ? p.fb[1 + li] : li) : p.F;
+        Meta M; M.li = li; M.f = f; M.schur = true;
         const int route = f < p.F ? p.route[f] : ROUTE_JOSEPH_FULL;
         if (route != ROUTE_JOSEPH_FULL && route != ROUTE_DONE) {
             M.N = BASE + 3 * p.nfeat[f]; M.m = p.m[f]; M.schur = route == ROUTE_SYM;
@@ -858,8 +888,8 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_sym(EkfPtrs p, const do
     // follow the issue counter, not a count of stages consumed.
     int g0_cur = 0, g0_nxt = 0;
 
-    while (cur.f < p.F) {
-        Meta nxt = meta(cur.f + gridDim.x);
+    while (cur.li < total) {
+        Meta nxt = meta(cur.li + gridDim.x);
         for (int i = tid; i < nxt.m; i += NW * 32) s_idx[ib ^ 1][i] = p.idx[(size_t)nxt.f * p.mmax + i];
         __syncthreads();
         const int N = cur.N;

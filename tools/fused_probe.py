@@ -37,12 +37,13 @@ def run(tag, timing=False):
         kms, kcnt = b.timing()
         print(tag, "kernel ms:", {k: round(float(kms[i] / max(kcnt[i], 1)), 4) for i, k in enumerate(["process", "chol", "cov", "fwd/solve", "fused"])})
         if has_clk:
-            out = (C.c_ulonglong * 16)()
+            out = (C.c_ulonglong * 24)()
             capi.lib.ekfvio_debug_fused_clocks(out, 1)
             v = np.array(list(out), dtype=np.float64) / (F * steps * 3)        # three runs since the last reset
             names = ["map", "load", "panel", "update", "barrier", "store", "tail", "-"]
             print(tag, "clocks per filter, warp 0 :", dict(zip(names, v[:8].round(0))), "sum", v[:8].sum().round(0))
-            print(tag, "clocks per filter, warp 15:", dict(zip(names, v[8:].round(0))), "sum", v[8:].sum().round(0))
+            print(tag, "clocks per filter, warp 15:", dict(zip(names, v[8:16].round(0))), "sum", v[8:16].sum().round(0))
+            print(tag, "factor_block per filter [load, LDL, checks+rs, inverse, store]:", v[16:21].round(0))
     else:
         print(tag, "routes [-1, sym, joseph_sym, joseph_full, done]:", routes.tolist())
     st = b.get_state()
@@ -59,7 +60,7 @@ if not np.array_equal(a["P"], b["P"], equal_nan=True):
     print("  filters that differ:", np.nonzero(d > 0)[0][:20], "max", d.max())
 run("fused timed", timing=True)
 if has_clk:
-    (C.c_ulonglong * 16)()
+    pass
 os.environ["EKFVIO_NO_FUSED_UPDATE"] = "1"
 c = run("three-kernel")
 c2 = run("three-kernel run 2")
