@@ -131,6 +131,32 @@ __device__ __forceinline__ double rcp_fast(double d) {
 
 __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
 
+// bulk (TMA) row copies global -> shared memory behind an mbarrier
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // private copy of a measurement diagonal tile: T -= Z_I Z_I'
 __device__ __forceinline__ void diag_update(double* T, const double* Zt, int lane) {
     const int r = lane >> 2, q = lane & 3;
@@ -277,6 +303,7 @@ __global__ void __launch_bounds__(FW * 32, 1) ekf_update_fused(EkfPtrs p, const 
     double* Ts = Ob + OB_DOUBLES;                     // the tiles no warp holds in registers (tsw layout; NTS * 64)
     __shared__ double s_y[NBM * 8], s_x[NTR * 8], s_R[NBM * 16];
     __shared__ int s_perm[NTR * 8], s_pinv[NTR * 8];
+    __shared__ unsigned long long s_bar;              // mbarrier of the bulk row loads
     __shared__ int s_m, s_elig, s_abort;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -303,6 +330,11 @@ __global__ void __launch_bounds__(FW * 32, 1) ekf_update_fused(EkfPtrs p, const 
         const long long until = clock64() + (long long)(blockIdx.x & 7) * 5000;
         while (clock64() < until) __nanosleep(200);
     }
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned bar_phase = 0;
     for (int f = blockIdx.x; f < p.F; f += gridDim.x) {
         const int n = p.nfeat[f], N = BASE + 3 * n;
         const double* Pi = Pin + (size_t)f * ld * ld;
@@ -310,17 +342,14 @@ __global__ void __launch_bounds__(FW * 32, 1) ekf_update_fused(EkfPtrs p, const 
         double* mu_g = p.mu + (size_t)f * BASE;
         double* feat_g = p.feat + (size_t)f * nmax * 3;
 
+        fence_proxy_async();                               // (the copy-out's reads of Ob before the bulk loads' writes)
         __syncthreads();                                   // shared memory of the previous filter is free
 #ifdef EKFVIO_PROFILE_CLOCKS
         long long t_prev = clock64();
 #endif
-        // the lower triangle of Sigma, row by row (coalesced 16-byte cp.async), into the buffer that stages the result later
-        for (int a = warp; a < N; a += FW) {
-            const double* src = Pi + (size_t)a * ld;
-            double* dst = Ob + in_off(a);
-            for (int c = 2 * lane; c <= a; c += 64) cp_async16(dst + c, src + c);
-        }
-        cp_async_commit();
+        // the lower triangle of Sigma, one bulk copy (TMA) per row, into the buffer that stages the result later
+        if (tid == 0) mbar_expect_tx(&s_bar, 8u * (unsigned)in_off(N));
+        if (tid < N) bulk_load(Ob + in_off(tid), Pi + (size_t)tid * ld, 8u * (unsigned)((tid + 2) & ~1), &s_bar);
         if (warp == 0) {
             // formFeatureMeasurementMap (:634-661) + bookkeeping of :506-529 for features lane and lane + 32, all loads issued
             // at once; then the permutation: measured rows in measurement order, the other state rows behind them in their own order
@@ -374,7 +403,8 @@ __global__ void __launch_bounds__(FW * 32, 1) ekf_update_fused(EkfPtrs p, const 
             // the mean, in its own order
             for (int a = tid - 32; a < N; a += (FW - 1) * 32) s_x[a] = a < BASE ? mu_g[a] : feat_g[a - BASE];
         }
-        cp_async_wait<0>();
+        mbar_wait(&s_bar, bar_phase);
+        bar_phase ^= 1;
         __syncthreads();
         if (!s_elig) {
             if (tid == 0) { p.route[f] = -1; p.fb[1 + atomicAdd(p.fb, 1)] = f; }      // pending: ekf_chol_tiled decides
@@ -653,7 +683,13 @@ __global__ void __launch_bounds__(FW * 32, 1) ekf_update_fused(EkfPtrs p, const 
                     if (c < len[u]) Po[(size_t)(a0 + FW * u) * ld + c] = prune(staged(Ob, pa[u], pc));
             }
         }
+#ifdef EKFVIO_PROFILE_CLOCKS
+        if (tid == 0) { long long t_ = clock64(); atomicAdd(&g_fclk[21], (unsigned long long)(t_ - t_prev)); }
+#endif
         __syncthreads();
+#ifdef EKFVIO_PROFILE_CLOCKS
+        if (tid == 0) { long long t_ = clock64(); atomicAdd(&g_fclk[22], (unsigned long long)(t_ - t_prev)); }
+#endif
         if (warp == 0) {  // renormalise the quaternion (:605-609) and flag non-finite states
             const double qn = sqrt(s_x[3] * s_x[3] + s_x[4] * s_x[4] + s_x[5] * s_x[5] + s_x[6] * s_x[6]);
             double v = lane < BASE ? s_x[lane] : 0.0;

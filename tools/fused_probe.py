@@ -43,7 +43,7 @@ def run(tag, timing=False):
             names = ["map", "load", "panel", "update", "barrier", "store", "tail", "-"]
             print(tag, "clocks per filter, warp 0 :", dict(zip(names, v[:8].round(0))), "sum", v[:8].sum().round(0))
             print(tag, "clocks per filter, warp 15:", dict(zip(names, v[8:16].round(0))), "sum", v[8:16].sum().round(0))
-            print(tag, "factor_block per filter [load, LDL, checks+rs, inverse, store]:", v[16:21].round(0))
+            print(tag, "factor_block per filter [load, LDL, checks+rs, inverse, store]:", v[16:21].round(0), "tail: own copy-out done / barrier passed", v[21:23].round(0))
     else:
         print(tag, "routes [-1, sym, joseph_sym, joseph_full, done]:", routes.tolist())
     st = b.get_state()
