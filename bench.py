@@ -40,6 +40,10 @@ def flops_per_filter_step(n: int) -> float:
     return f_proc + f_upd
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one ekf_update_fused launch over 4096 filters x 50 features (ncu --set full, this round)
+NCU_FUSED_DRAM_BYTES = None
+
+
 def flops_cov_update(n: int) -> float:
     """Covariance update as the reference writes it (Joseph form): 4 N^2 m."""
     N, m = 22 + 3 * n, 2 * n
@@ -52,11 +56,21 @@ def flops_cov_update_executed(n: int) -> float:
     return 1.0 * N * N * m
 
 
-def flops_per_filter_step_executed(n: int) -> float:
-    """Same process step; update = Cholesky m^3/3 + one triangular solve N m^2 + symmetric rank-m update N^2 m."""
+def flops_update_fused_executed(n: int) -> float:
+    """What ekf_update_fused executes per filter: m/8 block steps, each the panel Z_j = Sigma(:,j) inv(L_j)' (2 DMMA per
+    tile row: N*8*8*2) and the rank-8 update of the padded lower triangle (2 DMMA = 1024 FLOPs per 8x8 tile, T(T+1)/2 tiles,
+    T = ceil((N+1)/8) tile rows incl. the innovation row).  Neither the forward substitution (N m^2) nor a separate factorisation of S
+    (m^3/3) exists in this form; the 8x8 factorisations on the FP64 CUDA cores are ~1 % and not counted."""
     N, m = 22 + 3 * n, 2 * n
+    T = (N + 1 + 7) // 8
+    steps = (m + 7) // 8
+    return steps * (T * 8 * 8 * 8 * 2 + T * (T + 1) / 2 * 1024.0)
+
+
+def flops_per_filter_step_executed(n: int) -> float:
+    """Same process step; update as ekf_update_fused executes it."""
     f_proc = 486 * n * n + 5.7e3 * n + 4.3e4 + (1.75e3 * n + 5.3e3)
-    return f_proc + m ** 3 / 3 + N * m * m + N * N * m
+    return f_proc + flops_update_fused_executed(n)
 
 
 def ekf_config(F: int, n: int, world: int) -> dict:
@@ -65,7 +79,8 @@ def ekf_config(F: int, n: int, world: int) -> dict:
                         "(body velocity and angular rate ~ U(-0.2, 0.2), depth sigma 0.01, R = 1e-5 I)",
             "l2": "working set per step (two 1.0 GB Sigma buffers + 1.3 GB gain panels at 4096 filters) is larger than the 126 MB L2; no flush needed",
             "filters_total": F * world, "features": n,
-            "update_form": "library default: per filter and update, the Joseph form of a symmetric filter is evaluated as Sigma - Z Z' where S is positive definite with a "
+            "update_form": "library default (ekf_update_fused): the measurement blocks applied one after the other with Sigma resident in registers — the block-sequential "
+                           "form of Sigma - Z Z', equal to the batch update because R is block diagonal; per filter and update, where S is positive definite with a "
                            "pivot ratio <= 1e9, term by term (signed factor S = L J L') otherwise; EKFVIO_FLAG_LITERAL_JOSEPH = always term by term"}
 
 
@@ -252,9 +267,11 @@ def bench_ekf(args, rank, world, local, comm=None):
     res = {
         "value": value, "ms_per_step": ms_total / K, "launches": int(launches), "clocks": clocks,
         "e2e": {"value": total_filters * K / e2e_s, "unit": "filter-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-        "kernel_ms": {"process": kms[0] / max(kcnt[0], 1), "gain_chol": kms[1] / max(kcnt[1], 1), "gain_solve": kms[3] / max(kcnt[3], 1),
-                      "cov_update": kms[2] / max(kcnt[2], 1)},
-        "kernel_share": {k: float(v) for k, v in zip(("process", "gain_chol", "cov_update", "gain_solve"), kms[:4] / max(kms[:4].sum(), 1e-12))},
+        # update_fused: ekf_update_fused; gain_chol / gain_solve / cov_update: the tiled kernels behind it, which serve the filters it leaves
+        # alone (S not positive definite or ill conditioned: a handful per step) — their time is the latency of those few filters
+        "kernel_ms": {"process": kms[0] / max(kcnt[0], 1), "update_fused": kms[4] / max(kcnt[4], 1), "gain_chol": kms[1] / max(kcnt[1], 1),
+                      "gain_solve": kms[3] / max(kcnt[3], 1), "cov_update": kms[2] / max(kcnt[2], 1)},
+        "kernel_share": {k: float(v) for k, v in zip(("process", "gain_chol", "cov_update", "gain_solve", "update_fused"), kms[:5] / max(kms[:5].sum(), 1e-12))},
         "status_nonzero": bad, "ldlt_filters": ldlt, "finite": finite, "arms_agree": arms_agree, "gen_s": gen_s, "oracle": oracle, "oracle_filters": spot,
         "mc_stats": {"rmse_pos": float(np.sqrt(acc[0] / max(acc[3], 1))), "rmse_vel": float(np.sqrt(acc[1] / max(acc[3], 1))), "count": float(acc[3])},
     }
@@ -707,9 +724,12 @@ def main():
         fstep = flops_per_filter_step(n)
         F = args.filters
         peak = max(dmma_peak, dfma_peak)
-        cov_ms = ekf["kernel_ms"]["cov_update"]
-        cov_achieved = F * flops_cov_update_executed(n) / (cov_ms * 1e-3) / 1e12 if cov_ms > 0 else 0.0
-        cov_reference = F * flops_cov_update(n) / (cov_ms * 1e-3) / 1e12 if cov_ms > 0 else 0.0
+        fused = ekf["kernel_ms"]["update_fused"] > 0
+        cov_ms = ekf["kernel_ms"]["update_fused"] if fused else ekf["kernel_ms"]["cov_update"]
+        cov_flops = flops_update_fused_executed(n) if fused else flops_cov_update_executed(n)
+        cov_ref_flops = (flops_per_filter_step(n) - (486 * n * n + 5.7e3 * n + 4.3e4 + (1.75e3 * n + 5.3e3))) if fused else flops_cov_update(n)
+        cov_achieved = F * cov_flops / (cov_ms * 1e-3) / 1e12 if cov_ms > 0 else 0.0
+        cov_reference = F * cov_ref_flops / (cov_ms * 1e-3) / 1e12 if cov_ms > 0 else 0.0
         step_achieved = (ekf["value"] / world) * fstep / 1e12
         step_executed = (ekf["value"] / world) * flops_per_filter_step_executed(n) / 1e12
         line = {
@@ -719,18 +739,19 @@ def main():
             "clocks": ekf["clocks"],
             "e2e": ekf["e2e"],
             "gpu_launches": ekf["launches"] + (klt["gpu_launches"] if klt else 0),
-            # The default path evaluates the reference's Joseph-form update of a symmetric filter as Sigma - Z Z'
-            # (DESIGN.md §5): `achieved` / `frac` count the FLOPs the kernel really executes (N^2 m — what the FP64 pipe sees);
-            # `reference_equivalent` rates the same launch in the FLOPs of the update as the reference writes it (4 N^2 m).
-            "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA.8x8x4 / DFMA share one pipe on sm_100)", "kernel": "covariance update (ekf_joseph_sym)",
+            # The dominant kernel is the whole measurement update, ekf_update_fused: `achieved` / `frac` count the FLOPs its
+            # DMMAs really execute (flops_update_fused_executed — what the FP64 pipe sees); `reference_equivalent` rates the same launch in
+            # the FLOPs of the update as the reference writes it (4 N^2 m + 2 N m^2 + m^3/3).
+            "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA.8x8x4 / DFMA share one pipe on sm_100)",
+                         "kernel": "measurement update (ekf_update_fused)" if fused else "covariance update (ekf_joseph_sym)",
                          "achieved": cov_achieved, "peak": peak, "unit": "TFLOP/s", "frac": cov_achieved / peak if peak else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of ekf_joseph_sym from this round's ncu --set full capture
-                         # (profiles/r02_ncu_ekf_summary.txt: 1.2013 GB + 0.9253 GB for 4096 filters), scaled to this launch's filter count;
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the kernel from this round's ncu --set full capture
+                         # (profiles/r02b_ncu_ekf_summary.txt, 4096 filters), scaled to this launch's filter count;
                          # a profiler figure cannot be re-measured inside a timed run
-                         "traffic": (1.2013e9 + 0.9253e9) / 4096 * F if n == 50 else None,
+                         "traffic": ((NCU_FUSED_DRAM_BYTES if fused else 1.2013e9 + 0.9253e9) / 4096 * F) if (n == 50 and (NCU_FUSED_DRAM_BYTES or not fused)) else None,
                          "peak_source": "measured live by ekfvio_measure_fp64_peak (register-resident DMMA/DFMA loops); MEASURED_PEAKS.json has no FP64 entry",
-                         "flops_per_launch": F * flops_cov_update_executed(n),
-                         "reference_equivalent": {"flops_per_launch": F * flops_cov_update(n), "achieved": cov_reference},
+                         "flops_per_launch": F * cov_flops,
+                         "reference_equivalent": {"flops_per_launch": F * cov_ref_flops, "achieved": cov_reference},
                          "whole_step": {"flops_per_filter_step": fstep, "achieved": step_achieved, "frac": step_achieved / peak if peak else None,
                                         "note": "SURVEY.md §8d algorithmic count of the reference's update (Joseph form)",
                                         "executed_flops_per_filter_step": flops_per_filter_step_executed(n), "executed_achieved": step_executed,

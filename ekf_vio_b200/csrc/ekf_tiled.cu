@@ -774,7 +774,9 @@ cudaError_t launch_gain_tiled_t(int which, const EkfPtrs& p, const double* Pin, 
         static int chol_warps = 0;                 // EKFVIO_CHOL_WARPS=4 / 8 (experiments)
         if (!chol_warps) { const char* e = getenv("EKFVIO_CHOL_WARPS"); chol_warps = (e && atoi(e) == 8) ? 8 : 4; }
         const int grid = (p.fb && p.F > 148) ? 148 : p.F;
-        if (chol_warps == 4) ekf_chol_tiled<NB, 4><<<grid, 128, sm_c, st>>>(p, Pin, z, R, pass);
+        // behind ekf_update_fused only a handful of filters arrive here and their latency is what counts: eight warps per filter
+        if (p.fb) ekf_chol_tiled<NB, 8><<<grid, 256, sm_c, st>>>(p, Pin, z, R, pass);
+        else if (chol_warps == 4) ekf_chol_tiled<NB, 4><<<grid, 128, sm_c, st>>>(p, Pin, z, R, pass);
         else ekf_chol_tiled<NB, 8><<<grid, 256, sm_c, st>>>(p, Pin, z, R, pass);
     }
     else {

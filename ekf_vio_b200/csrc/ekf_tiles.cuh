@@ -47,33 +47,41 @@ __device__ void chol_tiles(double* Ls, double* Li, int nb, int* bad_flag, double
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = lane >> 2, q = lane & 3;
     for (int jb = 0; jb < nb; ++jb) {
-        if (warp == 0) {   // diagonal tile: lane rr (< 8) owns row rr
+        if (warp == 0) {   // diagonal tile: lane rr (< 8) owns row rr (the other lanes replicate)
+            // Elimination in LDL^T form: one reciprocal per column on the dependency chain, the square roots (one per row, after the
+            // loop) only scale the finished columns; L = L_ldl |D|^1/2, J = sign D.
             double* T = Ls + tile_of(jb, jb);
             const int rr = lane & 7;
             double a[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) a[c] = T[tsw(rr, c)];
-            bool bad = false, neg = false;
-            double rd[8], sg[8];
+            for (int c = 0; c < 8; c += 2) { const double2 v = *reinterpret_cast<const double2*>(&T[tsw(rr, c)]); a[c] = v.x; a[c + 1] = v.y; }
+            double own = 1.0;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-                double dcc = __shfl_sync(0xffffffffu, a[c], c);
-                double sc = 1.0;
-                if (sgn) {
-                    if (dcc < 0.0) { sc = -1.0; dcc = -dcc; neg = true; }
-                    if (!(dcc > 0.0)) bad = true;          // zero or NaN pivot
-                } else if (!(dcc > 0.0)) bad = true;
-                sg[c] = sc;
-                double piv = sqrt(dcc);
-                double rpiv = 1.0 / piv;       // one reciprocal per column instead of a division per row
-                rd[c] = rpiv;
-                if (rr == c) a[c] = piv; else if (rr > c) a[c] = a[c] * (rpiv * sc);
+                const double d = __shfl_sync(0xffffffffu, a[c], c);            // pivot (signed)
+                double l[8];
 #pragma unroll
-                for (int c2 = c + 1; c2 < 8; ++c2) {
-                    double l = __shfl_sync(0xffffffffu, a[c], c2);
-                    if (rr >= c2) a[c2] -= a[c] * (l * sc);
-                }
+                for (int c2 = c + 1; c2 < 8; ++c2) l[c2] = __shfl_sync(0xffffffffu, a[c], c2);
+                if (c == rr) own = d;
+                const double t = a[c] * __drcp_rn(d);
+#pragma unroll
+                for (int c2 = c + 1; c2 < 8; ++c2)
+                    if (rr >= c2) a[c2] -= t * l[c2];
             }
+            double sc = 1.0, ad = own;
+            bool bad = false, neg = false;
+            if (sgn) {
+                if (own < 0.0) { sc = -1.0; ad = -own; neg = true; }
+                if (!(ad > 0.0)) bad = true;               // zero or NaN pivot
+            } else if (!(own > 0.0)) bad = true;
+            const double piv = sqrt(ad), myrs = 1.0 / piv;
+            bad = __any_sync(0xffffffffu, bad); neg = __any_sync(0xffffffffu, neg);
+            double rs[8], sg[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { rs[c] = __shfl_sync(0xffffffffu, myrs, c); sg[c] = __shfl_sync(0xffffffffu, sc, c); }
+            // scaled factor: L(rr, c) = a(rr, c) sign_c / sqrt|d_c|
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a[c] = (c < rr) ? a[c] * (rs[c] * sg[c]) : ((c == rr) ? piv : 0.0);
             // column j = rr of inv(L): forward substitution with rows fetched by shuffle
             double x[8];
 #pragma unroll
@@ -81,7 +89,7 @@ __device__ void chol_tiles(double* Ls, double* Li, int nb, int* bad_flag, double
                 double sacc = (i == rr) ? 1.0 : 0.0;
 #pragma unroll
                 for (int k = 0; k < i; ++k) sacc -= __shfl_sync(0xffffffffu, a[k], i) * x[k];
-                x[i] = sacc * rd[i];
+                x[i] = sacc * rs[i];
             }
             if (lane < 8) {
 #pragma unroll
@@ -92,8 +100,7 @@ __device__ void chol_tiles(double* Ls, double* Li, int nb, int* bad_flag, double
                 if (bad && lane == 0) *bad_flag = 1;
                 if (sgn) {
                     if (neg && lane == 0) *neg_flag = 1;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) if (rr == c) sgn[jb * 8 + c] = sg[c];
+                    sgn[jb * 8 + rr] = sc;
                 }
             }
         }
