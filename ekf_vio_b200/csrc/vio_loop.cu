@@ -40,6 +40,7 @@ struct ekfvio_vio {
     cudaGraphExec_t graph[2] = {nullptr, nullptr};
     long long graph_launches[2] = {0, 0};    // kernel launches one replay stands for
     int graph_batch_state[2] = {-1, -1};     // ekfvio_batch_graph_state at capture: a graph is only replayed in that state
+    int graph_state_after[2] = {-1, -1};     // ... and the state the recorded frame leaves the batch's bookkeeping in
     int parity_seen[2] = {0, 0};
     cudaStream_t own_st = nullptr;           // capture is not allowed on the legacy default stream: graph frames of such callers run here
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -250,6 +251,7 @@ int ekfvio_vio_add_frame(ekfvio_vio* v, const uint8_t* d_frames, int pitch, cons
         if (rc) { if (g) cudaGraphDestroy(g); return rc; }
         if (e != cudaSuccess) return ekfvio::fail("cudaStreamEndCapture", e);
         v->graph_batch_state[parity] = batch_state;
+        v->graph_state_after[parity] = ekfvio_batch_graph_state(v->ekf);
         v->graph_launches[parity] = ekfvio_vio_launch_count(v) - before;
         v->launches -= v->graph_launches[parity];            // counted again by the launch below
         e = cudaGraphInstantiate(&v->graph[parity], g, 0);
@@ -257,7 +259,8 @@ int ekfvio_vio_add_frame(ekfvio_vio* v, const uint8_t* d_frames, int pitch, cons
         if (e != cudaSuccess) return ekfvio::fail("cudaGraphInstantiate", e);
     }
     CU(cudaGraphLaunch(v->graph[parity], st));
-    if (!captured_now) RC(ekfvio_batch_graph_replayed(v->ekf, v->prm.remove_lost_features ? 3 : 2));   // process + update (+ remove) flip the Sigma buffers
+    // a replay leaves the batch's host-side bookkeeping (Sigma ping-pong buffer, lower form, pending covariance pass) where the recording did
+    if (!captured_now) RC(ekfvio_batch_graph_state_restore(v->ekf, v->graph_state_after[parity]));
     if (legacy) { CU(cudaEventRecord(v->ev_out, st)); CU(cudaStreamWaitEvent(caller, v->ev_out, 0)); }
     v->launches += v->graph_launches[parity];
     v->cur_slot ^= 1;
