@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const do
                                                           int pre, int lower) {
     extern __shared__ double sm[];
     const int f = blockIdx.x, tid = threadIdx.x;
+    if (lower == 2 && p.asym[f] == 0) return;   // symmetric filters were served by ekf_process_cov_tiles (ekf_process_tiles.cu)
     const int n = p.nfeat[f], N = BASE + 3 * n;
     const int ld = p.ldP;
     ProcSmem s(sm, n);
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(PT, 2) ekf_process_general(EkfPtrs p, const do
         // needed up to its own diagonal block — columns c < BASE + 3 fi + 3 of T and of Sigma' — which removes
         // almost half of both passes and of the traffic; rows 0..21 stay complete.  The upper part of the feature
         // rows of the output is then stale (ekf_api.cu mirrors it on demand).
-        const bool low = lower && p.asym[f] == 0;
+        const bool low = lower == 1 && p.asym[f] == 0;
         auto prefetch = [&](int t) {
             if (t >= 8 && t < ntask) {
                 const double* own = Pi + (size_t)(BASE + 3 * (t - 8)) * ld;
@@ -919,13 +920,23 @@ cudaError_t launch_process_general(const EkfPtrs& p, const double* Pin, double* 
         if (ysplit > 16) ysplit = 16;
     }
     // fused path on a batch that fills the GPU: linearisation in its own small-CTA launch
+    // lower mode: the covariance pass of the symmetric filters runs on DMMA tiles (ekf_process_tiles.cu) behind the same
+    // linearisation launch; this kernel then only serves the filters whose Sigma is not symmetric
+    const bool tiles = fused && lower && process_tiles_capable(p);
     int pre = 0;
-    if (fused && p.F >= 2 * 148 && (size_t)p.ldP * p.ldK >= (size_t)22 * 23 + 36 * (size_t)p.nmax && proc_smem_bytes(p.nmax) <= 48 * 1024) {
+    if (fused && (p.F >= 2 * 148 || tiles) && (size_t)p.ldP * p.ldK >= (size_t)22 * 23 + 36 * (size_t)p.nmax && proc_smem_bytes(p.nmax) <= 48 * 1024) {
         ekf_linearize_kernel<<<p.F, 128, proc_smem_bytes(p.nmax), st>>>(p, dts);
         pre = 1;
         if (launches) *launches += 1;
     }
-    ekf_process_general<<<dim3(p.F, ysplit), PT, sm, st>>>(p, Pin, Pout, dts, mode, F_out, fused, pre, (fused && lower) ? 1 : 0);
+    int low = (fused && lower) ? 1 : 0;
+    if (tiles && pre) {
+        cudaError_t e = launch_process_cov_tiles(p, Pin, Pout, dts, st);
+        if (e != cudaSuccess) return e;
+        if (launches) *launches += 1;
+        low = 2;
+    }
+    ekf_process_general<<<dim3(p.F, ysplit), PT, sm, st>>>(p, Pin, Pout, dts, mode, F_out, fused, pre, low);
     if (ysplit > 1) ekf_commit_state_kernel<<<p.F, 128, 0, st>>>(p);
     if (launches) *launches += ysplit > 1 ? 2 : 1;
     return cudaGetLastError();

@@ -54,6 +54,9 @@ struct EkfPtrs {
 cudaError_t launch_process_general(const EkfPtrs& p, const double* Pin, double* Pout, const double* dts, int mode, double* F_out, cudaStream_t st,
                                    long long* launches, int lower);
 bool process_lower_capable(const EkfPtrs& p);
+// ekf_process_tiles.cu: covariance pass of process() on DMMA tiles (symmetric filters, lower mode)
+bool process_tiles_capable(const EkfPtrs& p);
+cudaError_t launch_process_cov_tiles(const EkfPtrs& p, const double* Pin, double* Pout, const double* dts, cudaStream_t st);
 cudaError_t launch_mirror_lower(const EkfPtrs& p, double* P0, cudaStream_t st);
 // only_route < 0: every filter; otherwise only the filters the Cholesky kernel routed there (p.route[f] == only_route)
 cudaError_t launch_gain_general(const EkfPtrs& p, const double* Pin, const double* z, const double* R, const uint8_t* pass, double* Sg,
