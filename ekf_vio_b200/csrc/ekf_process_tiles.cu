@@ -131,16 +131,14 @@ __global__ void __launch_bounds__(CT, 2) ekf_process_cov_tiles(EkfPtrs p, const 
     }
     {   // C_j(q, k) = sum_q' D_j(q, q') Sigma(7 + k, 22 + 3 j + q')
         const int rows = 24 * cov_groups(nmax);
-        for (int e = tid; e < 9 * rows; e += CT) {
-            const int k = e / rows, row = e - k * rows;
-            double v = 0.0;
-            if (row < 3 * n) {
-                const int j = row / 3, qq = row - 3 * j;
-                const double* sg = Pb9 + k * ld + BASE + 3 * j;
-                const double* d = Ds + j * 9 + qq * 3;
-                v = d[0] * sg[0] + d[1] * sg[1] + d[2] * sg[2];
-            }
-            Rm[row * LDR + 9 + k] = v;
+        for (int row = tid; row < rows; row += CT) {
+            const int j = row / 3, qq = row - 3 * j;
+            const bool live = row < 3 * n;
+            double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+            if (live) { const double* d = Ds + j * 9 + qq * 3; d0 = d[0]; d1 = d[1]; d2 = d[2]; }
+            const double* sg = Pb9 + BASE + 3 * j;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) Rm[row * LDR + 9 + k] = live ? d0 * sg[k * ld] + d1 * sg[k * ld + 1] + d2 * sg[k * ld + 2] : 0.0;
         }
     }
     __syncthreads();
@@ -164,18 +162,21 @@ __global__ void __launch_bounds__(CT, 2) ekf_process_cov_tiles(EkfPtrs p, const 
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                              // Own(g) landed; the base tiles / previous group are done with Tb
         PCLK(3);
-        // (a) block-scaled part of T(:, b): Tb(3i+r', c) = sum_r'' D_i(r', r'') Own(3i+r'', c); zero beyond the data
-        for (int e = tid; e < 8 * 24; e += CT) {
-            const int i = e / 24, c = e - 24 * i;
-            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-            if (i < nfe && c < BASE) {
-                const double* d = Ds + (8 * g + i) * 9;
-                const double o0 = Own[(3 * i) * ldo + c], o1 = Own[(3 * i + 1) * ldo + c], o2 = Own[(3 * i + 2) * ldo + c];
-                t0 = d[0] * o0 + d[1] * o1 + d[2] * o2;
-                t1 = d[3] * o0 + d[4] * o1 + d[5] * o2;
-                t2 = d[6] * o0 + d[7] * o1 + d[8] * o2;
+        // T(:, b) = D_I Sigma(I, b) + B_I Sigma(b9, b) on 3 x 3 tiles: the block-scaled part is formed in the accumulator layout, then
+        // K = 9 (lanes whose k runs past it read a zero of Rm)
+        for (int u = warp; u < 9; u += CT / 32) {
+            const int rt = u / 3, ct = u - 3 * rt, row = 8 * rt + r, il = row / 3, rp = row - 3 * il, col = 8 * ct + 2 * q;
+            double c0 = 0.0, c1 = 0.0;
+            if (il < nfe && col < BASE) {
+                const double* d = Ds + (8 * g + il) * 9 + rp * 3;
+                const double* o = Own + (3 * il) * ldo + col;
+                c0 = d[0] * o[0] + d[1] * o[ldo] + d[2] * o[2 * ldo];
+                c1 = d[0] * o[1] + d[1] * o[ldo + 1] + d[2] * o[2 * ldo + 1];
             }
-            Tb[(3 * i) * LDT + c] = t0; Tb[(3 * i + 1) * LDT + c] = t1; Tb[(3 * i + 2) * LDT + c] = t2;
+            const double* arow = Rm + (24 * g + row) * LDR;
+            tile_mma(c0, c1, 3, [&](int s) { const int k = 4 * s + q; return arow[k < 9 ? k : 18]; },
+                     [&](int s) { return Sbb[(7 + 4 * s + q) * LDT + 8 * ct + r]; });
+            *reinterpret_cast<double2*>(&Tb[row * LDT + col]) = make_double2(c0, c1);
         }
         // (b) X_ij = D_i Sigma_ij D_j' in place, blocks on and below the diagonal
         {
@@ -203,17 +204,6 @@ __global__ void __launch_bounds__(CT, 2) ekf_process_cov_tiles(EkfPtrs p, const 
         }
         __syncthreads();
         PCLK(4);
-        // T(:, b) += B_I Sigma(b9, b): K = 9 (lanes whose k runs past it read a zero of Rm)
-        for (int u = warp; u < 9; u += CT / 32) {
-            const int rt = u / 3, ct = u - 3 * rt;
-            double* t = &Tb[(8 * rt + r) * LDT + 8 * ct + 2 * q];
-            double2 c = *reinterpret_cast<double2*>(t);
-            const double* arow = Rm + (24 * g + 8 * rt + r) * LDR;
-            tile_mma(c.x, c.y, 3, [&](int s) { const int k = 4 * s + q; return arow[k < 9 ? k : 18]; },
-                     [&](int s) { return Sbb[(7 + 4 * s + q) * LDT + 8 * ct + r]; });
-            *reinterpret_cast<double2*>(t) = c;
-        }
-        __syncthreads();
         PCLK(5);
         // Sigma'(I, b) = T(:, b) A' and its transpose Sigma'(b, I)
         for (int u = warp; u < 9; u += CT / 32) {
