@@ -464,6 +464,10 @@ int ekfvio_batch_update_h(ekfvio_batch* b, const double* h_z, const double* h_R,
     void* dst[3] = {b->dd_z, b->dd_R, b->dd_pass};
     const size_t bytes[3] = {F * nm * 2 * sizeof(double), F * nm * 4 * sizeof(double), F * nm};
     if (b->inputs_ev_valid) CU(cudaStreamWaitEvent(b->copy_st, b->ev_inputs_free, 0));
+    else if (!stream_is_capturing(st)) {   // no record of the last reader of the device input buffers: order the upload behind the caller's stream
+        CU(cudaEventRecord(b->ev_entry, st));
+        CU(cudaStreamWaitEvent(b->copy_st, b->ev_entry, 0));
+    }
     // (not ordered behind earlier work on `stream`: that is what lets the upload overlap process(); the host buffers must hold
     // their final contents when this function is called — see include/ekfvio_c.h)
     bool synced = false;
