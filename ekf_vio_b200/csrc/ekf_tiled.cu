@@ -158,6 +158,22 @@ __global__ void __launch_bounds__(NW * 32, 1) ekf_joseph_tiled(EkfPtrs p, const 
 }
 
 
+// Completes the feature rows of a Sigma in lower form (row r valid up to its diagonal block) from the columns below the diagonal.
+// The column reads are strided (one cache line per lane): eight of them are in flight per lane before the first store, because a
+// single filter's latency through this kernel is what the launch behind ekf_update_fused costs.
+template <int NWC>
+__device__ __forceinline__ void mirror_lower_rows(double* Pw, int ld, int N, int warp, int lane) {
+    for (int r = BASE + warp; r < N; r += NWC) {
+        for (int c0 = r + 1 + lane; c0 < N; c0 += 256) {
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const int c = c0 + 32 * k; v[k] = c < N ? Pw[(size_t)c * ld + r] : 0.0; }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const int c = c0 + 32 * k; if (c < N) Pw[(size_t)r * ld + c] = v[k]; }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // ekf_gain_tiled: measurement map, residual, S, Cholesky, K, W, state update — the DMMA version
 // of ekf_gain_general (TightlyCoupledEKF.cpp:475-580, 600-620).
@@ -243,9 +259,7 @@ __device__ __forceinline__ void chol_tiled_filter(const EkfPtrs& p, const double
         // wrote the feature rows only up to their diagonal blocks
         double* Pw = const_cast<double*>(Pi);
         const int N = BASE + 3 * n;
-        for (int r = BASE + warp; r < N; r += NWC) {
-            for (int c = r + 1 + lane; c < N; c += 32) Pw[(size_t)r * ld + c] = Pw[(size_t)c * ld + r];
-        }
+        mirror_lower_rows<NWC>(Pw, ld, N, warp, lane);
         __syncthreads();
     }
     const bool low = p.sigma_lower && sym_now;     // then Sigma(idx[b], idx[a]) is read through its mirror image
@@ -325,9 +339,7 @@ __device__ __forceinline__ void chol_tiled_filter(const EkfPtrs& p, const double
         // of which the last process() wrote the feature rows only up to their diagonal blocks — complete it
         double* Pw = const_cast<double*>(Pi);
         const int N = BASE + 3 * n;
-        for (int r = BASE + warp; r < N; r += NWC) {
-            for (int c = r + 1 + lane; c < N; c += 32) Pw[(size_t)r * ld + c] = Pw[(size_t)c * ld + r];
-        }
+        mirror_lower_rows<NWC>(Pw, ld, N, warp, lane);
     }
     // Symmetric filters (ekf_fwd_tiled): v = inv(L) y replaces y, so that K y = Z v needs no K.  Block forward
     // substitution by one warp: t = y_jb - sum_k L(jb,k) v_k, v_jb = inv(L_jb,jb) t (explicit inverse tiles).

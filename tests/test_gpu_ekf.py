@@ -393,6 +393,41 @@ def test_sigma_reads_between_process_and_update_do_not_change_the_result(cuda):
         assert rel(sa["P"][0], orc.state()["P"]) <= TOL
 
 
+@pytest.mark.parametrize("nmax", [50, 33, 9])
+def test_process_tile_kernel_matches_row_block_kernel_and_oracle(cuda, nmax):
+    """process() of symmetric filters in lower mode runs its covariance pass on DMMA tiles (ekf_process_cov_tiles); the row-block
+    kernel (debug flag 0x1000 selects it for every filter) keeps the asymmetric filters of the same batch.  Ragged feature counts
+    (0 ... nmax, every group remainder), two filters made asymmetric by an asymmetric R block: after updates and one more process()
+    both kernels agree to rounding and each filter matches the FP64 oracle seeded with the batch's own state before that process()."""
+    from ekf_vio_b200 import workload
+    F, steps = 2 * (nmax + 1), 3
+    uv, meas, _ = workload.ekf_streams(0, F, nmax, steps)
+    nf = (np.arange(F) % (nmax + 1)).astype(np.int32)
+    R = np.tile(np.array([1e-5, 0, 0, 1e-5]), (F, nmax, 1)); ps = np.ones((F, nmax), np.uint8)
+    asym_filters = [f for f in (F - 1, F - 3) if nf[f] >= 2]
+    for f in asym_filters:
+        R[f, 1] = [1e-5, 2e-6, 1e-6, 1e-5]
+    tiles, rows = make_batch(F, nmax), make_batch(F, nmax, 0x1000)
+    for x in (tiles, rows):
+        x.add_features_h(nf, uv)
+        for s in range(steps):
+            x.process(0.05); x.update(*torch_inputs(meas[s], R, ps))
+    before = tiles.get_state()
+    np.testing.assert_allclose(before["P"], rows.get_state()["P"], rtol=0, atol=1e-9 * np.abs(before["P"]).max())
+    rows.set_state(mu=before["mu"], feat=before["feat"], P=before["P"], cache=before["cache"], flags=before["flags"], klt_last=before["klt_last"])
+    tiles.process(0.05); rows.process(0.05)
+    st, sr = tiles.get_state(), rows.get_state()
+    for f in range(F):
+        n = int(nf[f]); N = 22 + 3 * n
+        assert rel(st["P"][f, :N, :N], sr["P"][f, :N, :N]) <= 1e-12, f"filter {f} (n={n}): tile vs row-block kernel"
+        np.testing.assert_array_equal(st["mu"][f], sr["mu"][f])
+        if f % 5 == 0 or f in asym_filters:
+            o = O.OracleFilter(); o.add_features(uv[f, :n])
+            o.set_state(mu=before["mu"][f], feat=before["feat"][f, :n], Pm=before["P"][f, :N, :N], cache=before["cache"][f])
+            o.process(0.05)
+            assert rel(st["P"][f, :N, :N], o.state()["P"]) <= 1e-11, f"filter {f} (n={n}): tile kernel vs oracle"
+
+
 @pytest.mark.parametrize("n", [12, 70])
 def test_feature_removal_marginalises_and_filter_continues(cuda, n):
     """SURVEY.md §8f-4 (no counterpart in the reference: parity unpinned).  Removing features must delete their mean entries
