@@ -785,8 +785,10 @@ cudaError_t launch_gain_tiled_t(int which, const EkfPtrs& p, const double* Pin, 
     if (which == 0) {
         static int chol_warps = 0;                 // EKFVIO_CHOL_WARPS=4 / 8 (experiments)
         if (!chol_warps) { const char* e = getenv("EKFVIO_CHOL_WARPS"); chol_warps = (e && atoi(e) == 8) ? 8 : 4; }
-        const int grid = (p.fb && p.F > 148) ? 148 : p.F;
-        // behind ekf_update_fused only a handful of filters arrive here and their latency is what counts: eight warps per filter
+        // behind ekf_update_fused: the filters it left alone (0 ... 5 % of the batch per step on the config-3 streams,
+        // tools/fallback_stats_probe.py).  The factorisation of one filter is a serial chain, so up to four CTAs share an SM (53 KB of
+        // shared memory each) and the list is served in one wave; eight warps per filter
+        const int grid = (p.fb && p.F > 4 * 148) ? 4 * 148 : p.F;
         if (p.fb) ekf_chol_tiled<NB, 8><<<grid, 256, sm_c, st>>>(p, Pin, z, R, pass);
         else if (chol_warps == 4) ekf_chol_tiled<NB, 4><<<grid, 128, sm_c, st>>>(p, Pin, z, R, pass);
         else ekf_chol_tiled<NB, 8><<<grid, 256, sm_c, st>>>(p, Pin, z, R, pass);
