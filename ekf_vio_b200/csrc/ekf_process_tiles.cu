@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(CT, 2) ekf_process_cov_tiles(EkfPtrs p, const 
             double2 c[2][2][3];
 #pragma unroll
             for (int un = 0; un < 2; ++un) {
-                const int ct0 = 2 * warp + un * 2 * (CT / 32);
+                const int ct0 = un == 0 ? 2 * warp : 2 * (CT / 32) + 2 * (CT / 32 - 1 - warp);   // second round dealt from the last warp down
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(CT, 2) ekf_process_cov_tiles(EkfPtrs p, const 
             const double qf = 0.0001 * dt;            // process_noise_diag of a feature row
 #pragma unroll
             for (int un = 0; un < 2; ++un) {
-                const int ct0 = 2 * warp + un * 2 * (CT / 32);
+                const int ct0 = un == 0 ? 2 * warp : 2 * (CT / 32) + 2 * (CT / 32 - 1 - warp);   // second round dealt from the last warp down
                 if (ct0 >= nct) break;
                 const bool two = ct0 + 1 < nct;
                 const double* b0 = Rm + (8 * ct0 + r) * LDR + q;
