@@ -48,7 +48,8 @@ extern "C" {
 #define EKFVIO_FLAG_FRESH_DQ_CACHE 0x2u     /* fix E2: never reuse a dq_inv computed for another dt */
 /* Diagnostic bits (tools/diag_parity.py, tools/process_probe.py; no effect on results other than the path taken):
  * 0x100 general gain kernel, 0x200 general covariance kernel, 0x400 tiled covariance kernel without the symmetric
- * variant, 0x800 process() stops after linearisation + state propagation. */
+ * variant, 0x800 process() stops after linearisation + state propagation, 0x1000 process() keeps the row-block covariance kernel
+ * for every filter (instead of the DMMA tile kernel for symmetric filters; tools/process_tiles_probe.py, tests). */
 #define EKFVIO_FLAG_LITERAL_JOSEPH 0x4u     /* evaluate (I-KH) Sigma (I-KH)' + K R K' term by term even where Sigma and R are
                                              * symmetric; by default such filters use the algebraically identical
                                              * Sigma - Z Z', Z = Sigma(:,idx) inv(L)', S = L L'  */
