@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(CT, 2) ekf_process_cov_tiles(EkfPtrs p, const 
             }
         }
         PCLK(6);
-        // Sigma'(I, J) = X + [U_I | B_I] [B_J | C_J]', U_I = T(:, b9): a warp takes two column tiles at a time (at most two such
-        // units) and all three row tiles.  The accumulators and the A fragments are taken out of Own / Tb first, so that the next
+        // Sigma'(I, J) = X + [U_I | B_I] [B_J | C_J]', U_I = T(:, b9): a warp takes up to three column tiles, one after the other, and all
+        // three row tiles of each.  The accumulators and the A fragments are taken out of Own / Tb first, so that the next
         // group's rows travel while the DMMAs run.
         {
             double a[3][5];
@@ -231,57 +231,49 @@ __global__ void __launch_bounds__(CT, 2) ekf_process_cov_tiles(EkfPtrs p, const 
                     a[rt][s] = (k < 9) ? Tb[(8 * rt + r) * LDT + 7 + k] : Rm[(24 * g + 8 * rt + r) * LDR + (k < 18 ? k - 9 : k)];
             }
             const int nct = min(3 * (g + 1), ncta);
-            double2 c[2][2][3];
+            // column tile of slot un: the first round goes up the warps, the second and third come back down, so that the warps with
+            // two T / base-column tiles are not the ones with the most column tiles
+            auto ctof = [&](int un) { return un == 0 ? warp : (un + 1) * (CT / 32) - 1 - warp; };
+            double2 c[3][3];
 #pragma unroll
-            for (int un = 0; un < 2; ++un) {
-                const int ct0 = un == 0 ? 2 * warp : 2 * (CT / 32) + 2 * (CT / 32 - 1 - warp);   // second round dealt from the last warp down
+            for (int un = 0; un < 3; ++un) {
+                const int ct = ctof(un);
 #pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int rt = 0; rt < 3; ++rt)
-                        c[un][h][rt] = (ct0 + h < nct) ? *reinterpret_cast<const double2*>(&Own[(8 * rt + r) * ldo + BASE + 8 * (ct0 + h) + 2 * q]) : make_double2(0.0, 0.0);
+                for (int rt = 0; rt < 3; ++rt)
+                    c[un][rt] = (ct < nct) ? *reinterpret_cast<const double2*>(&Own[(8 * rt + r) * ldo + BASE + 8 * ct + 2 * q]) : make_double2(0.0, 0.0);
             }
             __syncthreads();                          // everybody is done with Own and Tb
             PCLK(7);
             if (g + 1 < ngroups) load_group(g + 1);
             const double qf = 0.0001 * dt;            // process_noise_diag of a feature row
 #pragma unroll
-            for (int un = 0; un < 2; ++un) {
-                const int ct0 = un == 0 ? 2 * warp : 2 * (CT / 32) + 2 * (CT / 32 - 1 - warp);   // second round dealt from the last warp down
-                if (ct0 >= nct) break;
-                const bool two = ct0 + 1 < nct;
-                const double* b0 = Rm + (8 * ct0 + r) * LDR + q;
-                const double* b1 = two ? b0 + 8 * LDR : b0;
+            for (int un = 0; un < 3; ++un) {
+                const int ct = ctof(un);
+                if (ct >= nct) continue;
+                const double* b0 = Rm + (8 * ct + r) * LDR + q;
 #pragma unroll
                 for (int s = 0; s < 5; ++s) {
-                    const double bv0 = b0[4 * s], bv1 = b1[4 * s];
+                    const double bv = b0[4 * s];
+#pragma unroll
+                    for (int rt = 0; rt < 3; ++rt) dmma884(c[un][rt].x, c[un][rt].y, a[rt][s], bv);
+                }
+                const int gamma = 8 * ct + 2 * q;                                 // feature-relative column
+                double* dst = Po + (size_t)(BASE + 24 * g + r) * ld + BASE + gamma;
+                if (ct < 3 * g && 24 * g + 24 <= 3 * n) {                          // left of the group's diagonal square, all rows live
+#pragma unroll
+                    for (int rt = 0; rt < 3; ++rt)
+                        *reinterpret_cast<double2*>(dst + (size_t)8 * rt * ld) = make_double2(prune(c[un][rt].x), prune(c[un][rt].y));
+                } else {
 #pragma unroll
                     for (int rt = 0; rt < 3; ++rt) {
-                        dmma884(c[un][0][rt].x, c[un][0][rt].y, a[rt][s], bv0);
-                        dmma884(c[un][1][rt].x, c[un][1][rt].y, a[rt][s], bv1);
-                    }
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (h == 1 && !two) break;
-                    const int ct = ct0 + h, gamma = 8 * ct + 2 * q;                 // feature-relative column
-                    double* dst = Po + (size_t)(BASE + 24 * g + r) * ld + BASE + gamma;
-                    if (ct < 3 * g && 24 * g + 24 <= 3 * n) {                        // left of the group's diagonal square, all rows live
-#pragma unroll
-                        for (int rt = 0; rt < 3; ++rt)
-                            *reinterpret_cast<double2*>(dst + (size_t)8 * rt * ld) = make_double2(prune(c[un][h][rt].x), prune(c[un][h][rt].y));
-                    } else {
-#pragma unroll
-                        for (int rt = 0; rt < 3; ++rt) {
-                            const int rho = 24 * g + 8 * rt + r;                    // feature-relative row
-                            if (rho >= 3 * n) continue;
-                            double v0 = c[un][h][rt].x, v1 = c[un][h][rt].y;
-                            if (rho == gamma) v0 += qf;
-                            if (rho == gamma + 1) v1 += qf;
-                            const int lim = 3 * (rho / 3) + 3;                      // end of the row's own diagonal block
-                            if (gamma + 1 < lim) *reinterpret_cast<double2*>(dst + (size_t)8 * rt * ld) = make_double2(prune(v0), prune(v1));
-                            else if (gamma < lim) dst[(size_t)8 * rt * ld] = prune(v0);
-                        }
+                        const int rho = 24 * g + 8 * rt + r;                      // feature-relative row
+                        if (rho >= 3 * n) continue;
+                        double v0 = c[un][rt].x, v1 = c[un][rt].y;
+                        if (rho == gamma) v0 += qf;
+                        if (rho == gamma + 1) v1 += qf;
+                        const int lim = 3 * (rho / 3) + 3;                        // end of the row's own diagonal block
+                        if (gamma + 1 < lim) *reinterpret_cast<double2*>(dst + (size_t)8 * rt * ld) = make_double2(prune(v0), prune(v1));
+                        else if (gamma < lim) dst[(size_t)8 * rt * ld] = prune(v0);
                     }
                 }
             }
@@ -297,7 +289,7 @@ namespace ekfvio {
 bool process_tiles_capable(const EkfPtrs& p) {
     static int off = -1;
     if (off < 0) { const char* e = getenv("EKFVIO_NO_TILED_PROCESS"); off = (e && e[0] == '1') ? 1 : 0; }
-    return !off && !(p.flags & 0x1000u) && p.nmax >= 1 && (3 * p.nmax + 7) / 8 <= 4 * (CT / 32)   /* 0x1000: debug bit, row-block kernel for everything */ && cov_smem_doubles(p.nmax, p.ldP) * sizeof(double) <= 112 * 1024 &&
+    return !off && !(p.flags & 0x1000u) && p.nmax >= 1 && (3 * p.nmax + 7) / 8 <= 3 * (CT / 32)   /* 0x1000: debug bit, row-block kernel for everything */ && cov_smem_doubles(p.nmax, p.ldP) * sizeof(double) <= 112 * 1024 &&
            (size_t)p.ldP * p.ldK >= (size_t)22 * 23 + 36 * (size_t)p.nmax;
 }
 
