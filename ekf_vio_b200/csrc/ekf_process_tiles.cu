@@ -164,7 +164,9 @@ __global__ void __launch_bounds__(CT, 2) ekf_process_cov_tiles(EkfPtrs p, const 
         PCLK(3);
         // T(:, b) = D_I Sigma(I, b) + B_I Sigma(b9, b) on 3 x 3 tiles: the block-scaled part is formed in the accumulator layout, then
         // K = 9 (lanes whose k runs past it read a zero of Rm)
-        for (int u = warp; u < 9; u += CT / 32) {
+        for (int k = 0; k < 2; ++k) {                        // (the ninth tile goes to the last warp: its share of the block scaling below is the smallest)
+            if (k == 1 && warp != CT / 32 - 1) break;
+            const int u = k == 0 ? warp : 8;
             const int rt = u / 3, ct = u - 3 * rt, row = 8 * rt + r, il = row / 3, rp = row - 3 * il, col = 8 * ct + 2 * q;
             double c0 = 0.0, c1 = 0.0;
             if (il < nfe && col < BASE) {
