@@ -583,7 +583,7 @@ def load_peaks():
 
 # ------------------------------------------------------------------------------------------------
 def cpu_baseline_ekf(sample_filters: int, sample_steps: int, threads: int = 0):
-    """Times the FP64 oracle (a port: the reference needs Eigen/ROS/OpenCV headers that are absent)
+    """Times the FP64 oracle (a port; DESIGN.md section 3 says why oracle/_ref is not the timed arm)
     on the host cores, OpenMP over filters.  bench.py's cpu_baseline leg is one of the two places
     allowed to execute oracle/."""
     import ctypes as C
@@ -660,7 +660,7 @@ def run_reference(args, result_out=sys.stdout):
         "impl": "reference", "metric": "EKF filter-steps/s", "value": v, "unit": "filter-steps/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * args.filters * max(args.gpus, 1) / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {**ekf_config(args.filters, N_FEAT, max(args.gpus, 1)),
-                   "note": "reference EKF cannot be compiled here (Eigen/ROS/OpenCV C++ headers absent): FP64 oracle port timed on a bounded sample"},
+                   "note": "FP64 oracle port timed on a bounded sample (OpenMP over filters); oracle/_ref, the reference's own sources built against stand-in Eigen headers, is the parity pin, not the timed arm: its process-wide static cache (E2) rules out threads and its speed would be the shim's, not Eigen's"},
         "cpu_baseline": {**t, "value": v},
         "e2e": {"value": v, "unit": "filter-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "klt": {"metric": "KLT features tracked/s at 640x480", "value": kl["value"], "unit": "features/s", "cpu_baseline": kl},
