@@ -302,7 +302,8 @@ __global__ void __launch_bounds__(FW * 32, 1) ekf_update_fused(EkfPtrs p, const 
     __shared__ __align__(16) double Li[64];           // inv(L_j)
     double* Ts = Ob + OB_DOUBLES;                     // the tiles no warp holds in registers (tsw layout; NTS * 64)
     __shared__ double s_y[NBM * 8], s_x[NTR * 8], s_R[NBM * 16];
-    __shared__ int s_perm[NTR * 8], s_pinv[NTR * 8];
+    __shared__ int s_perm[NTR * 8];
+    __shared__ int2 s_hl[NTR * 8];                   // copy-out: per stored index, the staged offset of its permuted position as the larger (.x) / smaller (.y) index of a pair
     __shared__ unsigned long long s_bar;              // mbarrier of the bulk row loads
     __shared__ int s_m, s_elig, s_abort;
 
@@ -657,7 +658,9 @@ __global__ void __launch_bounds__(FW * 32, 1) ekf_update_fused(EkfPtrs p, const 
             if (tid == 0) { p.route[f] = -1; p.fb[1 + atomicAdd(p.fb, 1)] = f; }      // ekf_chol_tiled routes it (Joseph form / signed factor)
             continue;
         }
-        if (tid < N) s_pinv[s_perm[tid]] = tid;
+        // staged(pa, pc) = x(max) + y(min) with x(p) = tri(p / 8) 64 + (p % 8) 8 and y(p) = (p / 8) 64 + p % 8; y is monotonic in p, so the
+        // comparison of two permuted positions is the comparison of their y: the copy-out needs one look-up per stored index
+        if (tid < N) s_hl[s_perm[tid]] = make_int2(tri(tid >> 3, 0) * 64 + (tid & 7) * 8, (tid >> 3) * 64 + (tid & 7));
         __syncthreads();
         FCLK(5);
         // mu += K y (:600): permuted row N of the result is y - dmu over the measured columns and -dmu over the others
@@ -668,19 +671,23 @@ __global__ void __launch_bounds__(FW * 32, 1) ekf_update_fused(EkfPtrs p, const 
         // rows of Sigma' in their own order, a warp per row: the lower triangle, rows 0..21 complete and the 3x3 diagonal block
         // of each feature complete (what the readers of a lower-mode Sigma rely on)
         for (int a0 = warp; a0 < N; a0 += 4 * FW) {          // four rows in flight per warp: independent shared-memory look-ups
-            int pa[4], len[4];
+            int rx[4], ry[4], len[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int a = a0 + FW * u;
-                pa[u] = a < N ? s_pinv[a] : 0;
+                const int2 h = s_hl[a < N ? a : 0];
+                rx[u] = h.x; ry[u] = h.y;
                 len[u] = a < N ? (a < BASE ? N : BASE + 3 * ((a - BASE) / 3) + 3) : 0;
             }
             const int maxlen = max(max(len[0], len[1]), max(len[2], len[3]));
+            double* po = Po + (size_t)a0 * ld;
+            // (the bounds test stays around the look-up: with the eight look-ups of two column groups issued ahead of predicated
+            // stores the launch was 2 % slower, 1.330 against 1.301 ms — DESIGN.md section 8)
             for (int c = lane; c < maxlen; c += 32) {
-                const int pc = s_pinv[c];
+                const int2 h = s_hl[c];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (c < len[u]) Po[(size_t)(a0 + FW * u) * ld + c] = prune(staged(Ob, pa[u], pc));
+                    if (c < len[u]) po[(size_t)(FW * u) * ld + c] = prune(Ob[ry[u] >= h.y ? rx[u] + h.y : h.x + ry[u]]);
             }
         }
 #ifdef EKFVIO_PROFILE_CLOCKS
