@@ -561,8 +561,8 @@ __device__ __forceinline__ unsigned dp2a_hi(unsigned a_u16x2, unsigned b_u8x4, u
 // Bilinear taps of one 7-pixel row segment: v[k] = c[k] + w00 t[k] + w01 t[k+1] + w10 b[k] + w11 b[k+1]
 // where t / b are the 8 tile bytes of the segment in the upper / lower row.  wt = w00 | w01 << 16,
 // wb = w10 | w11 << 16 (Q14 weights fit signed 16 bits), two IDP2A per pixel.
-__device__ __forceinline__ void seg_taps(const uint8_t* Jt, int JS, int r, int sg, unsigned wt, unsigned wb, const int (&c)[SEG], int (&v)[SEG]) {
-    const int off = SEG * sg, sh = (off & 3) * 8;
+__device__ __forceinline__ void seg_taps(const uint8_t* Jt, int JS, int al, int r, int sg, unsigned wt, unsigned wb, const int (&c)[SEG], int (&v)[SEG]) {
+    const int off = SEG * sg + al, sh = (off & 3) * 8;        // al: byte offset of the tile's first column inside the staged row (0..3)
     const unsigned* tr = reinterpret_cast<const unsigned*>(Jt + r * JS) + (off >> 2);
     const unsigned* br = tr + (JS >> 2);
     const unsigned t0 = tr[0], t1 = tr[1], t2 = tr[2], b0 = br[0], b1 = br[1], b2 = br[2];
@@ -617,10 +617,26 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
     const float FLT_SCALE = 1.f / (1 << 20);
     const int top = pyr.levels - 1;
 
-    // stage a (win+1)^2 tile of an 8-bit image at (ox, oy) with REFLECT_101 borders
-    auto stage_u8 = [&](const uint8_t* img, int ipitch, const Level& L, int ox, int oy) {
-        if (lane < jw1) {
-            const bool inside = ox >= 0 && oy >= 0 && ox + win < L.w && oy + win < L.h;
+    // stage a (win+1)^2 tile of an 8-bit image at (ox, oy) with REFLECT_101 borders; returns the byte offset of the tile's first
+    // column inside the staged rows.  A tile whose columns lie inside an image with word-aligned rows is fetched as aligned 32-bit words — eight
+    // word slots per row, four rows per pass, all lanes loading (six passes for a 22-row tile, every load issued before the first
+    // store can block) — and keeps its alignment offset; the per-column byte loop (22 dependent-latency rounds of 22 bytes each,
+    // the kernel's largest stall: long_scoreboard 29 %, profiles/r02_ncu_klt_summary.txt) remains for tiles across the left / right border and odd pitches.
+    const int jwords_max = (3 + jw1 + 3) >> 2;
+    const bool words_fit = jwords_max <= 8 && JS >= 4 * jwords_max && JS >= 4 * (((SEG * (SPR - 1) + 3) >> 2) + 3);   // (a segment reads three words from its start)
+    auto stage_u8 = [&](const uint8_t* img, int ipitch, const Level& L, int ox, int oy) -> int {
+        const bool in_x = ox >= 0 && ox + win < L.w, in_y = oy >= 0 && oy + win < L.h, inside = in_x && in_y;
+        int al = 0;
+        if (in_x && words_fit && ((reinterpret_cast<size_t>(img) | (size_t)ipitch) & 3) == 0) {      // (rows may still reflect)
+            al = ox & 3;
+            const int nw = (al + jw1 + 3) >> 2, w = lane & 7;
+            const uint8_t* p = img + (ox - al) + 4 * w;
+            if (w < nw)
+                for (int y = lane >> 3; y < jw1; y += 4) {
+                    const int Y = in_y ? oy + y : reflect101(oy + y, L.h);
+                    *reinterpret_cast<unsigned*>(Jt + y * JS + 4 * w) = *reinterpret_cast<const unsigned*>(p + (size_t)Y * ipitch);
+                }
+        } else if (lane < jw1) {
             if (inside) {
                 const uint8_t* p = img + (size_t)oy * ipitch + ox + lane;
                 for (int y = 0; y < jw1; ++y) Jt[y * JS + lane] = p[(size_t)y * ipitch];
@@ -630,6 +646,7 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
             }
         }
         __syncwarp();
+        return al;
     };
 
     for (int level = top; level >= 0; --level) {
@@ -658,7 +675,7 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
         lk_weights(px - ipx, py - ipy, w00, w01, w10, w11);
         // stage the I tile (into Jt) and the derivative tile (zero outside the image)
         __syncwarp();
-        stage_u8(I, ipitch, L, ipx, ipy);
+        const int ial = stage_u8(I, ipitch, L, ipx, ipy);
         if (lane < jw1) {
             const int X = ipx + lane;
             const bool xin = (unsigned)X < (unsigned)L.w;
@@ -674,7 +691,7 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
             const int c256[SEG] = {256, 256, 256, 256, 256, 256, 256};
             for (int sI = lane, r = r_first, sg = sg_first; sI < nseg; sI += 32) {
                 int v[SEG];
-                seg_taps(Jt, JS, r, sg, wt, wb, c256, v);
+                seg_taps(Jt, JS, ial, r, sg, wt, wb, c256, v);
                 int cw[8];
                 unsigned dw[8];
 #pragma unroll
@@ -712,7 +729,7 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
         D = 1.f / D;
         nx -= half; ny -= half;
         float pdx = 0.f, pdy = 0.f;
-        int sjx = INT_MIN, sjy = INT_MIN;         // cell of the J tile currently staged (none: Jt holds the I tile)
+        int sjx = INT_MIN, sjy = INT_MIN, jal = 0;   // cell (and alignment offset) of the J tile currently staged (none: Jt holds the I tile)
         for (int j = 0; j < max_count; ++j) {
             int inx = (int)floorf(nx), iny = (int)floorf(ny);
             if (inx < -win || inx >= L.w || iny < -win || iny >= L.h) {
@@ -722,7 +739,7 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
             lk_weights(nx - inx, ny - iny, w00, w01, w10, w11);
             if (inx != sjx || iny != sjy) {       // the staged J tile is reused while the integer cell does not move
                 __syncwarp();
-                stage_u8(J, jpitch, L, inx, iny);
+                jal = stage_u8(J, jpitch, L, inx, iny);
                 sjx = inx; sjy = iny;
             }
             int sb1 = 0, sb2 = 0;                 // <= 35 slots x 8160 x 4080 fits 32 bits
@@ -734,7 +751,7 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
                     const int c[SEG] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z};
                     const unsigned dw[SEG] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z};
                     int v[SEG];
-                    seg_taps(Jt, JS, r, sg, wt, wb, c, v);
+                    seg_taps(Jt, JS, jal, r, sg, wt, wb, c, v);
 #pragma unroll
                     for (int k = 0; k < SEG; ++k) {   // unused slots carry zero derivatives
                         const int diff = v[k] >> 9;
@@ -766,7 +783,7 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
                 lk_weights(fx - inx, fy - iny, w00, w01, w10, w11);
                 if (inx != sjx || iny != sjy) {
                     __syncwarp();
-                    stage_u8(J, jpitch, L, inx, iny);
+                    jal = stage_u8(J, jpitch, L, inx, iny);
                 }
                 int es = 0;                       // <= 35 slots x 8160
                 {
@@ -775,7 +792,7 @@ __global__ void __launch_bounds__(WARPS * 32) klt_track_kernel(Pyr pyr, const ui
                         const int4 c0 = *reinterpret_cast<const int4*>(Cp + sI * 4), c1 = *reinterpret_cast<const int4*>(Cp + (nseg + sI) * 4);
                         const int c[SEG] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z};
                         int v[SEG];
-                        seg_taps(Jt, JS, r, sg, wt, wb, c, v);
+                        seg_taps(Jt, JS, jal, r, sg, wt, wb, c, v);
 #pragma unroll
                         for (int k = 0; k < SEG; ++k) {
                             const int diff = v[k] >> 9;
