@@ -162,6 +162,25 @@ def test_batched_synthetic_pairs_vs_oracle(cuda):
         assert not st[b, c:].any()                  # entries beyond npts are untouched
 
 
+@pytest.mark.parametrize("win", [7, 9, 15, 27, 31])
+def test_other_window_sizes_vs_oracle(cuda, win):
+    """Window sizes around the tracker's tile-staging cases (aligned words with an offset where the row stride has room for it,
+    the byte loop at 31): status as the oracle's on points inside, on and beyond every border."""
+    rng = np.random.default_rng(100 + win)
+    w, h, mp = 320, 240, 128
+    a, c = synth_pair(rng, w, h, (int(rng.integers(-4, 5)), int(rng.integers(-4, 5))))
+    pts = np.stack([rng.uniform(-3, w + 3, mp), rng.uniform(-3, h + 3, mp)], 1).astype(np.float32)
+    pts[:8] = [[0, 0], [w - 1, h - 1], [win / 2, win / 2], [w - win / 2, 5], [1.5, h / 2], [w / 2, 1.5], [w - 1.5, h / 2], [w / 2, h - 1.5]]
+    trk = make_tracker(w, h, 1, mp, window_size=win)
+    nn = pts[None].copy()
+    st, er = trk.track_pair_h(a[None], c[None], pts[None], nn, np.array([mp], np.int32))
+    on, ost, oer, _ = O.klt_calc_optical_flow(a, c, pts, pts, win=win)
+    np.testing.assert_array_equal(st[0], ost)
+    both = ost == 1
+    assert both.sum() > mp // 2
+    assert np.abs(nn[0][both] - on[both]).max() <= 2e-3
+
+
 def test_property_known_translation_at_full_size(cuda):
     """Size-independent property at BASELINE's 640x480: a pure integer translation is recovered."""
     rng = np.random.default_rng(9)
