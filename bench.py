@@ -41,7 +41,7 @@ def flops_per_filter_step(n: int) -> float:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one ekf_update_fused launch over 4096 filters x 50 features (ncu --set full, this round)
-NCU_FUSED_DRAM_BYTES = 562.128e6 + 577.263e6     # profiles/r02c_ncu_ekf_summary.txt
+NCU_FUSED_DRAM_BYTES = 561.662e6 + 579.152e6     # profiles/r02f_ncu_ekf_summary.txt (the final kernel; r02c's capture: 562.1 + 577.3)
 
 
 def flops_cov_update(n: int) -> float:
@@ -752,7 +752,7 @@ def main():
                          "kernel": "measurement update (ekf_update_fused)" if fused else "covariance update (ekf_joseph_sym)",
                          "achieved": cov_achieved, "peak": peak, "unit": "TFLOP/s", "frac": cov_achieved / peak if peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of the kernel from this round's ncu --set full capture
-                         # (profiles/r02b_ncu_ekf_summary.txt, 4096 filters), scaled to this launch's filter count;
+                         # (profiles/r02f_ncu_ekf_summary.txt, 4096 filters), scaled to this launch's filter count;
                          # a profiler figure cannot be re-measured inside a timed run
                          "traffic": ((NCU_FUSED_DRAM_BYTES if fused else 1.2013e9 + 0.9253e9) / 4096 * F) if (n == 50 and (NCU_FUSED_DRAM_BYTES or not fused)) else None,
                          "peak_source": "measured live by ekfvio_measure_fp64_peak (register-resident DMMA/DFMA loops); MEASURED_PEAKS.json has no FP64 entry",
